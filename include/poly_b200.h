@@ -1,0 +1,173 @@
+/*
+ * poly_b200.h -- C ABI of libpolyb200.so: the B200 (sm_100a) implementation of
+ * bebop/poly's search/mash sketching hot path plus the two secondary batched
+ * kernels (search/align.SmithWaterman score, primers.SantaLucia).
+ *
+ * The reference is pure Go and has NO FFI/plugin interface; the
+ * drop-in boundary is the exported Go API of three leaf packages.  Each entry
+ * point below names the reference function it replaces (file:line under
+ * /root/reference); INTEGRATION.md shows the cgo binding for each.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types, no exceptions across the ABI;
+ *   - every function returns PG_OK (0) or a PG_ERR_* code; pg_last_error() gives a
+ *     thread-local message;
+ *   - the caller owns every buffer; the library never retains a caller pointer
+ *     after return (cgo pointer rule) and never frees caller memory;
+ *   - functions without the _dev suffix take HOST pointers and perform the
+ *     host<->device copies themselves; *_dev functions take DEVICE pointers on the
+ *     current device plus a CUDA stream (cudaStream_t cast to void*, NULL = the
+ *     legacy default stream) and are asynchronous with respect to the host;
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry
+ *     point fails with PG_ERR_NO_DEVICE.
+ */
+#ifndef POLY_B200_H
+#define POLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_ERR_CUDA 1        /* a CUDA runtime call failed (see pg_last_error)          */
+#define PG_ERR_ARG 2         /* invalid argument                                         */
+#define PG_ERR_NO_DEVICE 3   /* no CUDA device / not an sm_100 part                      */
+#define PG_ERR_PANIC 4       /* >= 1 item hits an input on which the Go reference panics */
+#define PG_ERR_UNSUPPORTED 5 /* >= 1 item is outside the supported domain                */
+#define PG_ERR_NOMEM 6
+
+/* per-item status codes (status arrays) */
+#define PG_ITEM_OK 0
+#define PG_ITEM_PANIC 1       /* reference panics (index out of range) on this item     */
+#define PG_ITEM_UNSUPPORTED 2 /* e.g. byte >= 0x80 passed to SantaLucia (ToUpper)       */
+
+/* ---- library / device management -------------------------------------------- */
+int pg_version(void);
+/* Bind the calling process to CUDA device `device` (one process per GPU).  Optional:
+ * the first compute call initialises device 0 (or the current device). */
+int pg_init(int device);
+int pg_shutdown(void);
+const char *pg_last_error(void);
+int pg_device_count(int *count);
+int pg_device_sm_count(int *sms);
+/* Pinned host memory for callers that want full PCIe bandwidth (optional). */
+int pg_host_alloc(void **ptr, size_t bytes);
+int pg_host_free(void *ptr);
+/* Device memory helpers for C/Go callers of the *_dev entry points. */
+int pg_dev_alloc(void **dptr, size_t bytes);
+int pg_dev_free(void *dptr);
+int pg_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int pg_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int pg_stream_sync(void *stream);
+
+/* ---- mash.Sketch -- replaces (*Mash).Sketch on a fresh mash.New(k, s) -----------
+ * search/mash/mash.go:59-65 (New) and :68-104 (Sketch), one sketch per read.
+ *
+ * Read i is bases[offsets[i] .. offsets[i+1]) (raw bytes, any value; the hash is
+ * MurmurHash3_x86_32(seed 0) of the k raw bytes, mash.go:74-76).  With
+ * n_i = max(len_i - k, 0) hashes (mash.go:73 visits L-k windows, not L-k+1):
+ *   n_i <  s : out row i = the n_i hashes in positional order   (mash.go:81-84)
+ *   n_i >= s : out row i = ascending bottom-s multiset          (mash.go:87-102)
+ * count[i] = min(n_i, s) informative words; row i starts at out + i*row_stride.
+ * The zero tail that a fresh Mash holds beyond count[i] is NOT written unless
+ * PG_SKETCH_PAD_ZERO is set (then row_stride must be >= s and s words are written).
+ * status[i] (may be NULL) reports per-read PG_ITEM_PANIC for s in {0,1} inputs on
+ * which mash.go:96-98 indexes Sketches[-1]; k < 0 or s < 0 is PG_ERR_ARG.
+ */
+#define PG_SKETCH_PAD_ZERO 1u
+
+int pg_mash_sketch_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int32_t k,
+                         int32_t s, uint32_t flags, uint32_t *out, uint64_t row_stride,
+                         uint32_t *count, int32_t *status);
+/* Same, for fixed-length reads stored back to back (read i at bases + i*read_len):
+ * no offsets array, count is min(max(read_len-k,0), s) for every read. */
+int pg_mash_sketch_uniform(const uint8_t *bases, uint64_t n_reads, uint32_t read_len, int32_t k,
+                           int32_t s, uint32_t flags, uint32_t *out, uint64_t row_stride,
+                           int32_t *status);
+/* Device-resident variants (inputs already in HBM, outputs stay in HBM). */
+int pg_mash_sketch_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                             uint64_t max_read_len, int32_t k, int32_t s, uint32_t flags,
+                             uint32_t *d_out, uint64_t row_stride, uint32_t *d_count,
+                             int32_t *d_status, void *stream);
+int pg_mash_sketch_uniform_dev(const uint8_t *d_bases, uint64_t n_reads, uint32_t read_len,
+                               int32_t k, int32_t s, uint32_t flags, uint32_t *d_out,
+                               uint64_t row_stride, int32_t *d_status, void *stream);
+/* Name of the kernel the last uniform call on this thread dispatched to and how many
+ * kernels it launched (bench.py's gpu_launches evidence). */
+const char *pg_last_kernel(void);
+uint64_t pg_launch_count(void);
+
+/* ---- (*Mash).Similarity / Distance -- search/mash/mash.go:107-140 ----------------
+ * Sketch j is words sketches[sk_offsets[j] .. sk_offsets[j+1]) and its length is its
+ * SketchSize (the full array a Go Mash holds, zero tail included).  For pair p the
+ * receiver is pair_a[p], the argument pair_b[p].  Literal reference semantics:
+ * larger/smaller by SketchSize with the receiver "larger" on ties (:109-115), the
+ * range early-out (:117-119), the two-pointer walk (:121-132) -- exact also for
+ * unsorted (n < s) sketches.  same[p] = matching count, similarity[p] =
+ * same/smaller.SketchSize (:134), distance[p] = 1 - similarity (:139).  Any of
+ * same/similarity/distance may be NULL.  A sketch of size 0 is PG_ITEM_PANIC.
+ */
+int pg_mash_similarity_pairs(const uint32_t *sketches, const uint64_t *sk_offsets,
+                             uint64_t n_sketches, const uint32_t *pair_a, const uint32_t *pair_b,
+                             uint64_t n_pairs, int64_t *same, double *similarity,
+                             double *distance, int32_t *status);
+int pg_mash_similarity_pairs_dev(const uint32_t *d_sketches, const uint64_t *d_sk_offsets,
+                                 uint64_t n_sketches, const uint32_t *d_pair_a,
+                                 const uint32_t *d_pair_b, uint64_t n_pairs, int64_t *d_same,
+                                 double *d_similarity, double *d_distance, int32_t *d_status,
+                                 void *stream);
+/* All pairs of a row block against a set of equal-size sketches: rows
+ * [row_begin, row_end) of the n x n matrix, receiver = row, argument = column.
+ * sketches is n x s (full Go arrays).  same is (row_end-row_begin) x n uint32,
+ * distance likewise double (either may be NULL).  Same literal semantics. */
+int pg_mash_distance_block(const uint32_t *sketches, uint64_t n, int32_t s, uint64_t row_begin,
+                           uint64_t row_end, uint32_t *same, double *distance);
+int pg_mash_distance_block_dev(const uint32_t *d_sketches, uint64_t n, int32_t s,
+                               uint64_t row_begin, uint64_t row_end, uint32_t *d_same,
+                               double *d_distance, void *stream);
+
+/* ---- align.SmithWaterman score -- search/align/align.go:171-203 -------------------
+ * One template against n queries.  query_is_a != 0: stringA = query (outer loop),
+ * stringB = template; else swapped.  lut_a/lut_b: byte -> index into the first /
+ * second alphabet, -1 = not in alphabet (alphabet/alphabet.go:35-41); table is
+ * n_a x n_b row-major (search/align/matrix/matrix.go:28-38); gap is ADDED
+ * (align.go:193-194).  Per query: score (align.go:197-201 running max),
+ * err_code 0 / 1 (symbol of stringA) / 2 (symbol of stringB) and err_pos (byte
+ * index in that string) of the first failing cell in the reference's row-major
+ * visiting order (align.go:188-191); on error score is 0.
+ */
+int pg_sw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table,
+                      int32_t n_a, int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code,
+                      int64_t *err_pos);
+int pg_sw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets, uint64_t n_queries,
+                          uint64_t max_query_len, const uint8_t *d_templ, uint64_t templ_len,
+                          int32_t query_is_a, const int16_t *lut_a_host, const int16_t *lut_b_host,
+                          const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
+                          int64_t *d_score, int32_t *d_err_code, int64_t *d_err_pos, void *stream);
+
+/* ---- primers.SantaLucia / MeltingTemp -- primers/primers.go:70-105,121-128 --------
+ * tm/dh/ds may each be NULL.  status: PG_ITEM_PANIC for an empty primer
+ * (primers.go:89), PG_ITEM_UNSUPPORTED for a byte >= 0x80 (strings.ToUpper would
+ * re-encode it, primers.go:71).  MeltingTemp == cp 500e-9, na 50e-3, mg 0. */
+int pg_tm_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n, double cp, double na,
+                double mg, double *tm, double *dh, double *ds, int32_t *status);
+int pg_tm_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n, double cp,
+                    double na, double mg, double *d_tm, double *d_dh, double *d_ds,
+                    int32_t *d_status, void *stream);
+
+/* ---- synthetic workloads (bench/test tooling, not a reference API) ---
+ * kind 0: independent reads  base(i,j) = code(seed, i*L + j)
+ * kind 1: family reads       (family = reads per template, 1/64 substitutions)
+ * Writes n_reads*read_len bytes for reads [first_read, first_read+n_reads). */
+int pg_synth_reads_dev(uint8_t *d_bases, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
+                       uint64_t seed, int32_t kind, uint32_t family, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLY_B200_H */

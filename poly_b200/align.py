@@ -1,0 +1,135 @@
+"""Host-side mirror of poly's search/align (Smith-Waterman SCORE), alphabet and
+search/align/matrix packages over libpolyb200.so.
+
+Mirrors /root/reference/alphabet/alphabet.go:25-61 (`NewAlphabet`, `Encode`, `Error`),
+search/align/matrix/matrix.go:13-38 (`NewSubstitutionMatrix`, `Score`, `Default`),
+search/align/matrix/matrices.go:33-40 (`NUC_4`) and search/align/align.go:73-95,171-203
+(`Scoring`, `NewScoring`, the fill + running max of `SmithWaterman`).  The traceback
+strings (align.go:205-231) are a "next" row of SURVEY.md 8f: `SmithWaterman` here
+returns the score and raises the reference's `alphabet.Error`; it does not build the
+aligned strings.  All DP cells are computed on the GPU.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .mash import BytesLike, _as_bytes, flatten
+
+
+class AlphabetError(Exception):
+    """alphabet.Error (alphabet.go:14-22)."""
+
+
+class Alphabet:
+    """alphabet.Alphabet (alphabet.go:9-12): symbols are strings; a sequence byte b is
+    looked up as Go's string(b), i.e. the UTF-8 encoding of code point b (align.go:90)."""
+
+    def __init__(self, symbols: Sequence[str]):
+        self.symbols = list(symbols)
+        self.encoding = {}
+        for i, sym in enumerate(self.symbols):  # alphabet.go:27-30 (later duplicates win)
+            self.encoding[sym] = i
+
+    def Encode(self, symbol: str) -> int:
+        if symbol not in self.encoding:
+            raise AlphabetError(f"Symbol {symbol} not in alphabet")  # alphabet.go:38
+        return self.encoding[symbol]
+
+    def Symbols(self) -> List[str]:
+        return self.symbols
+
+    def byte_lut(self) -> np.ndarray:
+        lut = np.full(256, -1, dtype=np.int16)
+        for b in range(256):
+            lut[b] = self.encoding.get(chr(b), -1)
+        return lut
+
+
+def NewAlphabet(symbols: Sequence[str]) -> Alphabet:
+    return Alphabet(symbols)
+
+
+class SubstitutionMatrix:
+    """matrix.SubstitutionMatrix (matrix.go:13-17)."""
+
+    def __init__(self, first: Alphabet, second: Alphabet, scores):
+        scores = np.asarray(scores, dtype=np.int64)
+        if scores.ndim != 2 or len(first.Symbols()) != scores.shape[0] or len(second.Symbols()) != scores.shape[1]:
+            raise ValueError("invalid dimensions of substitution matrix")  # matrix.go:21-23
+        self.FirstAlphabet, self.SecondAlphabet, self.scores = first, second, scores
+
+    def Score(self, a: str, b: str) -> int:  # matrix.go:28-38
+        return int(self.scores[self.FirstAlphabet.Encode(a), self.SecondAlphabet.Encode(b)])
+
+
+def NewSubstitutionMatrix(first: Alphabet, second: Alphabet, scores) -> SubstitutionMatrix:
+    return SubstitutionMatrix(first, second, scores)
+
+
+_LETTERS = [chr(ord("A") + i) for i in range(26)]
+Default = SubstitutionMatrix(Alphabet(_LETTERS), Alphabet(_LETTERS), 2 * np.eye(26, dtype=np.int64) - 1)  # matrix.go:41-74
+NUC_4 = [[0, 0, 0, 0, 0], [0, 5, -4, -4, -4], [0, -4, 5, -4, -4], [0, -4, -4, 5, -4], [0, -4, -4, -4, 5]]  # matrices.go:33-40
+
+
+class Scoring:
+    """align.Scoring (align.go:73-76)."""
+
+    def __init__(self, substitution_matrix: Optional[SubstitutionMatrix], gap_penalty: int):
+        self.SubstitutionMatrix = substitution_matrix if substitution_matrix is not None else Default  # align.go:80-82
+        self.GapPenalty = int(gap_penalty)
+
+
+def NewScoring(substitution_matrix: Optional[SubstitutionMatrix], gap_penalty: int) -> Scoring:
+    return Scoring(substitution_matrix, gap_penalty)
+
+
+def sw_scores_arrays(q_bases: np.ndarray, q_offsets: np.ndarray, template: BytesLike, scoring: Scoring,
+                     query_is_a: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(score, err_code, err_pos) for every query against one template."""
+    m = scoring.SubstitutionMatrix
+    lut_a, lut_b = m.FirstAlphabet.byte_lut(), m.SecondAlphabet.byte_lut()
+    table = np.ascontiguousarray(m.scores, dtype=np.int64)
+    t = _as_bytes(template)
+    q_bases = np.ascontiguousarray(q_bases, dtype=np.uint8)
+    q_offsets = np.ascontiguousarray(q_offsets, dtype=np.uint64)
+    n = len(q_offsets) - 1
+    score, ec, ep = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int64)
+    rc = _lib.lib().pg_sw_score_batch(q_bases.ctypes.data, q_offsets.ctypes.data, n, t.ctypes.data, len(t), int(query_is_a),
+                                      lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[0], table.shape[1],
+                                      scoring.GapPenalty, score.ctypes.data, ec.ctypes.data, ep.ctypes.data)
+    _lib.check(rc)
+    return score, ec, ep
+
+
+def _error_for(ec: int, ep: int, a: np.ndarray, b: np.ndarray) -> AlphabetError:
+    byte = int(a[ep]) if ec == 1 else int(b[ep])
+    return AlphabetError(f"Symbol {chr(byte)} not in alphabet")  # alphabet.go:38 via align.go:189-191
+
+
+def SmithWatermanScores(queries: Sequence[BytesLike], template: BytesLike, scoring: Scoring,
+                        query_is_a: bool = True) -> Tuple[List[int], List[Optional[AlphabetError]]]:
+    """Batched addition: score (and error) of SmithWaterman(query, template) per query
+    (or SmithWaterman(template, query) with query_is_a=False)."""
+    bases, offsets = flatten(queries)
+    score, ec, ep = sw_scores_arrays(bases, offsets, template, scoring, query_is_a)
+    t = _as_bytes(template)
+    errs: List[Optional[AlphabetError]] = []
+    for i in range(len(queries)):
+        if ec[i]:
+            q = bases[int(offsets[i]): int(offsets[i + 1])]
+            errs.append(_error_for(int(ec[i]), int(ep[i]), q if query_is_a else t, t if query_is_a else q))
+        else:
+            errs.append(None)
+    return [int(x) for x in score], errs
+
+
+def SmithWaterman(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> int:
+    """Score of align.SmithWaterman(stringA, stringB, scoring) (align.go:171-203).
+    Raises AlphabetError where the reference returns (0, "", "", err)."""
+    scores, errs = SmithWatermanScores([stringA], stringB, scoring, query_is_a=True)
+    if errs[0] is not None:
+        raise errs[0]
+    return scores[0]

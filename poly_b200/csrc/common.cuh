@@ -1,0 +1,63 @@
+// common.cuh -- shared declarations of libpolyb200 (internal; the public surface is
+// include/poly_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/poly_b200.h"
+
+namespace pg {
+
+// thread-local error string + helpers (api.cu)
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+void note_launch(const char *kernel_name);
+
+#define PG_CUDA(call)                                                     \
+    do {                                                                  \
+        cudaError_t _e = (call);                                          \
+        if (_e != cudaSuccess) return ::pg::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PG_LAUNCH_CHECK(name)                                             \
+    do {                                                                  \
+        ::pg::note_launch(name);                                          \
+        cudaError_t _e = cudaGetLastError();                              \
+        if (_e != cudaSuccess) return ::pg::cuda_fail(_e, name, __FILE__, __LINE__); \
+    } while (0)
+
+int sm_count();
+
+// ---- kernel launchers (one per .cu) -------------------------------------------
+// sketch_fill.cu
+int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t read_len, int k, int s,
+                          uint32_t flags, uint32_t *d_out, uint64_t row_stride, int32_t *d_status,
+                          cudaStream_t st);
+int launch_sketch_ragged(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                         uint64_t max_read_len, int k, int s, uint32_t flags, uint32_t *d_out,
+                         uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st);
+// sketch_select.cu  (reads with n >= s; uniform: read_len != 0 and d_offsets == nullptr)
+int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len,
+                         uint64_t n_reads, int k, int s, uint32_t flags, uint32_t *d_out,
+                         uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st);
+// distance.cu
+int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_t n_sk,
+                            const uint32_t *d_a, const uint32_t *d_b, uint64_t n_pairs,
+                            int64_t *d_same, double *d_sim, double *d_dist, int32_t *d_status,
+                            cudaStream_t st);
+int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin,
+                          uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st);
+// sw_score.cu
+int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen,
+                    const uint8_t *d_t, uint64_t tlen, int query_is_a, const int16_t *lut_a,
+                    const int16_t *lut_b, const int64_t *table, int n_a, int n_b, int64_t gap,
+                    int64_t *d_score, int32_t *d_err, int64_t *d_errpos, cudaStream_t st);
+// tm.cu
+int launch_tm(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double cp, double na,
+              double mg, double *d_tm, double *d_dh, double *d_ds, int32_t *d_status,
+              cudaStream_t st);
+// synth.cu
+int launch_synth_reads(uint8_t *d_bases, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
+                       uint64_t seed, int kind, uint32_t family, cudaStream_t st);
+
+}  // namespace pg

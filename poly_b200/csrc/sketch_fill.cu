@@ -1,0 +1,320 @@
+// sketch_fill.cu -- K1: mash.Sketch in the fill regime (L-k < s): every k-mer hash is
+// written positionally (/root/reference/search/mash/mash.go:73-84).
+//
+// Fast path (fixed-length reads, k in the instantiated set, compact output):
+//   * one CTA = one tile of R reads; the R*L input bytes are contiguous in HBM and are
+//     brought in by ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier; SASS UBLKCP);
+//   * one THREAD per read walks the read 4 bytes per step.  The murmur3 block pre-mix
+//     K(p) = rotl(w(p)*c1,15)*c2 of the 4 bytes at position p is computed ONCE and kept
+//     in a register ring shared by the k/4 k-mers that consume it, so the cost per
+//     k-mer is the body chain + fmix, not k/4 pre-mixes (integer-issue is the
+//     co-limit of this kernel);
+//   * hashes are staged in shared memory ([read][pos], stride L-k words: bank-conflict
+//     free when L-k is odd) and leave as ONE bulk store per tile (the compact output
+//     [n][L-k] of a tile is contiguous in HBM).
+// All global traffic is therefore full-line TMA traffic; the SM only touches smem.
+//
+// Generic path (any k >= 0, ragged reads, any row stride): one warp per read, every
+// k-mer hashed from scratch.  Slower, same results.
+#include <algorithm>
+
+#include "common.cuh"
+#include "murmur3.cuh"
+
+namespace pg {
+
+// ---- PTX wrappers: mbarrier + 1-D bulk async copy --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- K1 fast path ----------------------------------------------------------------
+// smem: [0,16) mbarrier | in tile (R*L bytes + 16 B over-read pad, 16-B rounded) | out tile
+__host__ __device__ inline uint32_t k1_in_bytes(uint32_t R, uint32_t L) {
+    return (R * L + 16u + 15u) & ~15u;
+}
+
+template <int K, int R>
+__global__ void __launch_bounds__(R)
+sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, uint32_t *__restrict__ out,
+                           uint32_t L, uint32_t nk) {
+    constexpr int NB = K / 4;      // 4-byte body blocks per k-mer
+    constexpr int TAIL = K % 4;    // tail bytes per k-mer
+    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
+    static_assert(NB >= 1, "fast path needs k >= 4");
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *s_in = smem + 16;
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_in + k1_in_bytes(R, L));
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t tile = blockIdx.x;
+    const uint32_t in_bytes = R * L;  // multiple of 16 (host guarantees)
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, in_bytes);
+        bulk_g2s(s_in, bases + tile * in_bytes, in_bytes, bar);
+    }
+    __syncthreads();  // barrier init visible to the waiters
+    mbar_wait(bar, 0);
+
+    // my read: bytes [tid*L, tid*L+L) of the tile, realigned to words on the fly
+    const uint32_t b0 = tid * L;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_in) + (b0 >> 2);
+    const uint32_t sh = (b0 & 3u) * 8u;
+    uint32_t *my_out = s_out + tid * nk;
+
+    uint32_t raw_prev = sw[0], raw = sw[1];
+    uint32_t w_cur = __funnelshift_r(raw_prev, raw, sh);  // bytes 4Q .. 4Q+3 of the read
+    raw_prev = raw;
+    raw = sw[2];
+    uint32_t w_nxt = __funnelshift_r(raw_prev, raw, sh);  // bytes 4Q+4 .. 4Q+7
+    raw_prev = raw;
+
+    uint32_t ring[4][NB];  // ring[r][*]: pre-mixes K(4q+r) of the last NB word steps
+
+    // prologue: word steps 0 .. NB-1 only fill the ring
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        ring[0][q] = mm3_kmix(w_cur);
+        ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
+        ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
+        ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
+        w_cur = w_nxt;
+        raw = sw[q + 3];
+        w_nxt = __funnelshift_r(raw_prev, raw, sh);
+        raw_prev = raw;
+    }
+
+    // main loop: at word step Q = NB + i0/4 the k-mers i0+r (r = 0..3) complete: their
+    // body blocks are ring[r][oldest .. newest], their tail bytes are the low bytes of
+    // the window at position i0 + r + 4*NB, i.e. the windows formed in this very step.
+    for (uint32_t i0 = 0; i0 < nk; i0 += 4 * NB) {
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const uint32_t i = i0 + 4 * u;
+            if (i < nk) {
+                uint32_t w[4];
+                w[0] = w_cur;
+                w[1] = __funnelshift_r(w_cur, w_nxt, 8);
+                w[2] = __funnelshift_r(w_cur, w_nxt, 16);
+                w[3] = __funnelshift_r(w_cur, w_nxt, 24);
+                uint32_t h[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    uint32_t x = mm3_round0(ring[r][u]);
+#pragma unroll
+                    for (int j = 1; j < NB; ++j) x = mm3_round(x, ring[r][(u + j) % NB]);
+                    if (TAIL) x ^= mm3_kmix(w[r] & TAILMASK);
+                    x ^= (uint32_t)K;
+                    h[r] = mm3_fmix(x);
+                    ring[r][u] = mm3_kmix(w[r]);
+                }
+                // positional store (mash.go:81-84); the last step may be partial
+                my_out[i] = h[0];
+                if (i + 1 < nk) my_out[i + 1] = h[1];
+                if (i + 2 < nk) my_out[i + 2] = h[2];
+                if (i + 3 < nk) my_out[i + 3] = h[3];
+                w_cur = w_nxt;
+                raw = sw[(i >> 2) + NB + 3];
+                w_nxt = __funnelshift_r(raw_prev, raw, sh);
+                raw_prev = raw;
+            }
+        }
+    }
+
+    // hand the staged tile to the async proxy and bulk-store it
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t out_bytes = R * nk * 4u;  // multiple of 16 (R % 4 == 0)
+        bulk_s2g(out + tile * (uint64_t)(R * nk), s_out, out_bytes);
+        bulk_wait_read0();
+    }
+}
+
+// ---- generic fill path -----------------------------------------------------------
+// One warp per read.  Handles reads with n = max(len-k,0) < s (others are left to the
+// select kernel).  Also writes count / zero padding / status for those reads.
+__global__ void __launch_bounds__(256)
+sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                           uint32_t uniform_len, uint64_t n_reads, uint64_t first_read, uint32_t k,
+                           uint32_t s, uint32_t flags, uint32_t *__restrict__ out,
+                           uint64_t row_stride, uint32_t *__restrict__ count,
+                           int32_t *__restrict__ status) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_reads;
+         r += warps) {
+        const uint64_t row = first_read + r;
+        uint64_t beg, len;
+        if (offsets) {
+            beg = offsets[row];
+            len = offsets[row + 1] - beg;
+        } else {
+            beg = row * (uint64_t)uniform_len;
+            len = uniform_len;
+        }
+        const uint64_t n = len > k ? len - k : 0;  // mash.go:73
+        if (n >= s && !(n == 0 && s == 0)) continue;  // select regime (incl. s in {0,1} panics)
+        const uint8_t *seq = bases + beg;
+        uint32_t *dst = out + row * row_stride;
+        for (uint64_t i = lane; i < n; i += 32) {
+            const uint8_t *p = seq + i;
+            dst[i] = mm3_bytes([p](uint32_t j) { return __ldg(p + j); }, k);
+        }
+        if (flags & PG_SKETCH_PAD_ZERO)
+            for (uint64_t i = n + lane; i < s; i += 32) dst[i] = 0u;
+        if (lane == 0) {
+            if (count) count[row] = (uint32_t)n;
+            if (status) status[row] = PG_ITEM_OK;
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------
+template <int K, int R>
+static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
+                     uint32_t *d_out, cudaStream_t st) {
+    const size_t smem = 16 + k1_in_bytes(R, L) + (size_t)R * nk * 4;
+    static size_t configured = 0;  // per instantiation
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(sketch_fill_uniform_kernel<K, R>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, d_out, L, nk);
+    PG_LAUNCH_CHECK("sketch_fill_uniform_kernel");
+    return PG_OK;
+}
+
+template <int R>
+static int dispatch_k1(int k, const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
+                       uint32_t *d_out, cudaStream_t st, bool *handled) {
+    *handled = true;
+    switch (k) {
+#define PG_K1_CASE(KK) \
+    case KK: return launch_k1<KK, R>(d_bases, n_tiles, L, nk, d_out, st);
+        PG_K1_CASE(15) PG_K1_CASE(16) PG_K1_CASE(17) PG_K1_CASE(19) PG_K1_CASE(21) PG_K1_CASE(23)
+        PG_K1_CASE(25) PG_K1_CASE(27) PG_K1_CASE(31) PG_K1_CASE(32)
+#undef PG_K1_CASE
+    default: *handled = false; return PG_OK;
+    }
+}
+
+constexpr int K1_R = 32;  // reads per tile == threads per CTA
+
+static int launch_fill_generic(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t ulen,
+                               uint64_t n_reads, uint64_t first_read, int k, int s, uint32_t flags,
+                               uint32_t *d_out, uint64_t row_stride, uint32_t *d_count,
+                               int32_t *d_status, cudaStream_t st) {
+    if (n_reads == 0) return PG_OK;
+    const uint64_t blocks = std::min<uint64_t>((n_reads + 7) / 8, (uint64_t)sm_count() * 32);
+    sketch_fill_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(
+        d_bases, d_offsets, ulen, n_reads, first_read, (uint32_t)k, (uint32_t)s, flags, d_out,
+        row_stride, d_count, d_status);
+    PG_LAUNCH_CHECK("sketch_fill_generic_kernel");
+    return PG_OK;
+}
+
+int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, int k, int s,
+                          uint32_t flags, uint32_t *d_out, uint64_t row_stride, int32_t *d_status,
+                          cudaStream_t st) {
+    if (n_reads == 0) return PG_OK;
+    const uint64_t n = L > (uint32_t)k ? L - (uint32_t)k : 0;
+    if (n >= (uint64_t)s && !(n == 0 && s == 0))  // select regime, mash.go:87-102
+        return launch_sketch_select(d_bases, nullptr, L, n_reads, k, s, flags, d_out, row_stride,
+                                    nullptr, d_status, st);
+    // fill regime
+    const uint32_t nk = (uint32_t)n;
+    uint64_t done = 0;
+    const bool compact = row_stride == nk && !(flags & PG_SKETCH_PAD_ZERO);
+    const bool aligned = ((uintptr_t)d_bases % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
+    const size_t smem = 16 + k1_in_bytes(K1_R, L) + (size_t)K1_R * nk * 4;
+    if (compact && aligned && nk > 0 && (K1_R * (uint64_t)L) % 16 == 0 && smem <= 200 * 1024 &&
+        n_reads >= K1_R) {
+        const uint64_t tiles = n_reads / K1_R;
+        bool handled = false;
+        uint64_t t0 = 0;
+        while (t0 < tiles) {  // grid.x limit
+            const uint64_t nt = std::min<uint64_t>(tiles - t0, 0x7fffffffull);
+            int rc = dispatch_k1<K1_R>(k, d_bases + t0 * K1_R * (uint64_t)L, nt, L, nk,
+                                       d_out + t0 * K1_R * (uint64_t)nk, st, &handled);
+            if (rc != PG_OK) return rc;
+            if (!handled) break;
+            t0 += nt;
+        }
+        if (handled) {
+            done = tiles * K1_R;
+            if (d_status) PG_CUDA(cudaMemsetAsync(d_status, 0, done * sizeof(int32_t), st));
+        }
+    }
+    if (done < n_reads)
+        return launch_fill_generic(d_bases, nullptr, L, n_reads - done, done, k, s, flags, d_out,
+                                   row_stride, nullptr, d_status, st);
+    return PG_OK;
+}
+
+int launch_sketch_ragged(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
+                         uint64_t max_read_len, int k, int s, uint32_t flags, uint32_t *d_out,
+                         uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
+                         cudaStream_t st) {
+    if (n_reads == 0) return PG_OK;
+    int rc = launch_fill_generic(d_bases, d_offsets, 0, n_reads, 0, k, s, flags, d_out, row_stride,
+                                 d_count, d_status, st);
+    if (rc != PG_OK) return rc;
+    const uint64_t nmax = max_read_len > (uint64_t)k ? max_read_len - (uint64_t)k : 0;
+    if (nmax >= (uint64_t)s && nmax > 0)  // some read may be in the select regime
+        return launch_sketch_select(d_bases, d_offsets, 0, n_reads, k, s, flags, d_out, row_stride,
+                                    d_count, d_status, st);
+    return PG_OK;
+}
+
+}  // namespace pg

@@ -1,0 +1,275 @@
+// sketch_select.cu -- K2: mash.Sketch in the select regime (L-k >= s): the sketch is the
+// ascending bottom-s MULTISET of all k-mer hashes (closed form of
+// /root/reference/search/mash/mash.go:87-102: fill, sort once at i == s-1, then
+// replace-max + re-sort; duplicates are kept).
+//
+// One CTA per read.  The read is streamed through shared memory in chunks:
+//   phase 1  pre-mix K(p) of every position of the chunk, once       (shared via smem)
+//   phase 2  one k-mer per thread: body chain over K(i+4j), tail, fmix; hashes below
+//            the current admission limit are appended to the candidate buffer
+//   prune    when the buffer would overflow: exact radix-select of the s-th smallest
+//            value, keep all smaller values plus the needed number of ties
+//   final    prune to exactly s, bitonic sort in shared memory, coalesced store.
+// Nothing but the read bytes and the s output words touches HBM.
+#include <algorithm>
+
+#include "common.cuh"
+#include "murmur3.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_CHUNK = 2048;     // k-mer positions per chunk
+constexpr int SEL_MAX_S = 16384;    // largest sketch size in the select regime
+constexpr int SEL_LOOKAHEAD = 1024; // max k supported by the staged path (bytes beyond chunk)
+
+struct SelSmem {
+    uint32_t *cand;   // [cap]
+    uint32_t *keep;   // [s]
+    uint32_t *kv;     // [SEL_CHUNK + SEL_LOOKAHEAD]
+    uint32_t *bytes;  // [(SEL_CHUNK + SEL_LOOKAHEAD + 8)/4] staged read bytes (word view)
+    uint32_t *hist;   // [256]
+    uint32_t *misc;   // [8]: 0 cnt, 1 prefix, 2 want, 3 kept_lt, 4 kept_eq, 5 hmin_later
+};
+
+__device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_t p) {
+    // little-endian 4-byte window at byte position p of the staged bytes
+    const uint32_t a = bytes_w[p >> 2], b = bytes_w[(p >> 2) + 1];
+    return __funnelshift_r(a, b, (p & 3u) * 8u);
+}
+
+// exact selection: on return cand[0..s) holds the s smallest values (as a multiset) of
+// cand[0..cnt); returns the s-th smallest value.  All threads must call.
+__device__ uint32_t prune_to_s(const SelSmem &m, uint32_t cnt, uint32_t s) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t prefix = 0, mask = 0, want = s;  // want: 1-based rank inside the current bucket
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        if (tid < 256) m.hist[tid] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < cnt; i += SEL_THREADS) {
+            const uint32_t e = m.cand[i];
+            if ((e & mask) == prefix) atomicAdd(&m.hist[(e >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {  // warp 0 scans the 256 bins (8 per lane)
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = m.hist[tid * 8 + j]; sum += loc[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)tid >= d) incl += y;
+            }
+            uint32_t before = incl - sum;
+            if (before < want && want <= incl) {  // the bucket lies in my 8 bins
+                uint32_t w = want - before;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (w <= loc[j]) {
+                        m.misc[1] = prefix | ((uint32_t)(tid * 8 + j) << shift);
+                        m.misc[2] = w;
+                        break;
+                    }
+                    w -= loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = m.misc[1];
+        want = m.misc[2];
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    const uint32_t v = prefix;     // s-th smallest value
+    const uint32_t need_eq = want; // copies of v that belong to the bottom-s multiset
+    const uint32_t n_lt = s - need_eq;
+    if (tid == 0) { m.misc[3] = 0; m.misc[4] = 0; }
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < cnt; i0 += SEL_THREADS) {
+        const uint32_t i = i0 + tid;
+        const uint32_t e = i < cnt ? m.cand[i] : 0xffffffffu;
+        const bool lt = i < cnt && e < v;
+        const bool eq = i < cnt && e == v;
+        const uint32_t blt = __ballot_sync(0xffffffffu, lt), beq = __ballot_sync(0xffffffffu, eq);
+        const uint32_t lane = tid & 31u, below = (1u << lane) - 1u;
+        uint32_t base_lt = 0, base_eq = 0;
+        if (lane == 0) {
+            if (blt) base_lt = atomicAdd(&m.misc[3], __popc(blt));
+            if (beq) base_eq = atomicAdd(&m.misc[4], __popc(beq));
+        }
+        base_lt = __shfl_sync(0xffffffffu, base_lt, 0);
+        base_eq = __shfl_sync(0xffffffffu, base_eq, 0);
+        if (lt) m.keep[base_lt + __popc(blt & below)] = e;
+        if (eq) {
+            const uint32_t q = base_eq + __popc(beq & below);
+            if (q < need_eq) m.keep[n_lt + q] = e;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < s; i += SEL_THREADS) m.cand[i] = m.keep[i];
+    __syncthreads();
+    return v;
+}
+
+__device__ void bitonic_sort(uint32_t *x, uint32_t P) {
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
+        for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < (P >> 1); t += SEL_THREADS) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t ixj = i | j;
+                const bool up = (i & k2) == 0;
+                const uint32_t a = x[i], b = x[ixj];
+                if ((a > b) == up) { x[i] = b; x[ixj] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                     uint32_t uniform_len, uint64_t n_reads, uint32_t k, uint32_t s, uint32_t P,
+                     uint32_t cap, uint32_t flags, uint32_t *__restrict__ out, uint64_t row_stride,
+                     uint32_t *__restrict__ count, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    SelSmem m;
+    m.cand = smem_w;
+    m.keep = m.cand + cap;
+    m.kv = m.keep + (s ? s : 1);
+    m.bytes = m.kv + SEL_CHUNK + SEL_LOOKAHEAD;
+    m.hist = m.bytes + (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1;
+    m.misc = m.hist + 256;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nb = k >> 2, tail = k & 3u;
+    const uint32_t tailmask = tail == 1 ? 0xffu : tail == 2 ? 0xffffu : 0xffffffu;
+
+    for (uint64_t row = blockIdx.x; row < n_reads; row += gridDim.x) {
+        uint64_t beg, len;
+        if (offsets) {
+            beg = offsets[row];
+            len = offsets[row + 1] - beg;
+        } else {
+            beg = row * (uint64_t)uniform_len;
+            len = uniform_len;
+        }
+        const uint64_t n = len > k ? len - k : 0;
+        if (n < s || n == 0) continue;  // fill regime: other kernel
+        const uint8_t *seq = bases + beg;
+        uint32_t *dst = out + row * row_stride;
+        if (s == 0) {  // mash.go:96 reads Sketches[-1] on the first k-mer
+            if (tid == 0) {
+                if (status) status[row] = PG_ITEM_PANIC;
+                if (count) count[row] = 0;
+            }
+            continue;
+        }
+
+        if (tid == 0) { m.misc[0] = 0; m.misc[5] = 0xffffffffu; }
+        __syncthreads();
+        uint64_t limit = 1ull << 32;  // admit h < limit
+        uint32_t h_first = 0;
+
+        for (uint64_t c0 = 0; c0 < n; c0 += SEL_CHUNK) {
+            const uint32_t ch = (uint32_t)min((uint64_t)SEL_CHUNK, n - c0);
+            // stage bytes [c0, c0 + ch + k) (+ zero slack for the window over-read)
+            const uint32_t nbytes = ch + k;
+            uint8_t *sb = reinterpret_cast<uint8_t *>(m.bytes);
+            for (uint32_t i = tid; i < nbytes + 8; i += SEL_THREADS)
+                sb[i] = i < nbytes ? __ldg(seq + c0 + i) : (uint8_t)0;
+            // make room: candidates after this chunk must fit
+            uint32_t cnt = m.misc[0];
+            __syncthreads();
+            if (cnt + ch > cap) {
+                limit = prune_to_s(m, cnt, s);
+                if (tid == 0) m.misc[0] = s;
+                __syncthreads();
+            }
+            // phase 1: block pre-mix of every position that some k-mer of the chunk uses
+            const uint32_t npos = nb ? ch + 4 * (nb - 1) : 0;
+            for (uint32_t p = tid; p < npos; p += SEL_THREADS) m.kv[p] = mm3_kmix(smem_window(m.bytes, p));
+            __syncthreads();
+            // phase 2: one k-mer per thread
+            for (uint32_t i0 = 0; i0 < ch; i0 += SEL_THREADS) {
+                const uint32_t i = i0 + tid;
+                bool take = false;
+                uint32_t h = 0;
+                if (i < ch) {
+                    for (uint32_t j = 0; j < nb; ++j) h = mm3_round(h, m.kv[i + 4 * j]);
+                    if (tail) h ^= mm3_kmix(smem_window(m.bytes, i + 4 * nb) & tailmask);
+                    h ^= k;
+                    h = mm3_fmix(h);
+                    take = (uint64_t)h < limit;
+                    if (c0 + i == 0) h_first = h;  // thread 0 only
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, take);
+                const uint32_t lane = tid & 31u;
+                uint32_t base = 0;
+                if (lane == 0 && b) base = atomicAdd(&m.misc[0], __popc(b));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (take) m.cand[base + __popc(b & ((1u << lane) - 1u))] = h;
+                if (s == 1 && i < ch && c0 + i > 0) atomicMin(&m.misc[5], h);
+            }
+            __syncthreads();
+        }
+
+        uint32_t cnt = m.misc[0];
+        __syncthreads();
+        if (cnt > s) prune_to_s(m, cnt, s);
+        for (uint32_t i = s + tid; i < P; i += SEL_THREADS) m.cand[i] = 0xffffffffu;
+        __syncthreads();
+        bitonic_sort(m.cand, P);
+        for (uint32_t i = tid; i < s; i += SEL_THREADS) dst[i] = m.cand[i];
+        if (tid == 0) {
+            int32_t st = PG_ITEM_OK;
+            // s == 1: mash.go:96-98 indexes Sketches[-1] as soon as a later hash is
+            // strictly below Sketches[0]
+            if (s == 1 && m.misc[5] < h_first) st = PG_ITEM_PANIC;
+            if (status) status[row] = st;
+            if (count) count[row] = s;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len,
+                         uint64_t n_reads, int k, int s, uint32_t flags, uint32_t *d_out,
+                         uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
+                         cudaStream_t st) {
+    if (n_reads == 0) return PG_OK;
+    if (s > SEL_MAX_S) {
+        set_error("sketch size %d > %d is not supported when L-k >= s (select regime)", s, SEL_MAX_S);
+        return PG_ERR_UNSUPPORTED;
+    }
+    if (k > SEL_LOOKAHEAD) {
+        set_error("k = %d > %d is not supported when L-k >= s (select regime)", k, SEL_LOOKAHEAD);
+        return PG_ERR_UNSUPPORTED;
+    }
+    uint32_t P = 1;
+    while (P < (uint32_t)std::max(s, 1)) P <<= 1;
+    if (P < 2) P = 2;
+    uint32_t cap = std::max<uint32_t>(P, (uint32_t)s + 5 * SEL_CHUNK);
+    const size_t words = (size_t)cap + (s ? s : 1) + (SEL_CHUNK + SEL_LOOKAHEAD) +
+                         (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1 + 256 + 8;
+    const size_t smem = words * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(sketch_select_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 4);
+    sketch_select_kernel<<<(unsigned)blocks, SEL_THREADS, smem, st>>>(
+        d_bases, d_offsets, read_len, n_reads, (uint32_t)k, (uint32_t)s, P, cap, flags, d_out,
+        row_stride, d_count, d_status);
+    PG_LAUNCH_CHECK("sketch_select_kernel");
+    return PG_OK;
+}
+
+}  // namespace pg

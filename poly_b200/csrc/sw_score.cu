@@ -1,0 +1,281 @@
+// sw_score.cu -- K4: Smith-Waterman score of n short queries against one template,
+// /root/reference/search/align/align.go:171-203 (fill + running max; the traceback at
+// :205-231 is out of scope).  Linear gap (ADDED, align.go:193-194), arbitrary
+// substitution table addressed through two byte->index LUTs
+// (search/align/matrix/matrix.go:28-38, alphabet/alphabet.go:35-41).
+//
+// One thread per query.  The thread sweeps the template once, keeping the DP column
+// over its query (<= MAXQ cells) in registers; the template's symbol indices are
+// staged in shared memory and broadcast; the substitution table sits in shared memory
+// (a nucleotide table is <= 32 words = one word per bank).  Three DPX
+// add-max instructions per cell.  The max score does not depend on which string is
+// the outer loop; the reported error (first failing cell in row-major order,
+// align.go:188-191) does, and is resolved per orientation at the end.
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int SW_THREADS = 128;
+constexpr int SW_TCHUNK = 8192;  // template symbols staged per pass
+
+template <typename T>
+__device__ __forceinline__ T addmax(T a, T b, T c) {  // max(a + b, c)
+    const T x = a + b;
+    return x > c ? x : c;
+}
+template <>
+__device__ __forceinline__ int addmax<int>(int a, int b, int c) {
+    return __viaddmax_s32(a, b, c);
+}
+
+struct SwParams {
+    const uint8_t *q;
+    const uint64_t *qoff;
+    uint64_t nq;
+    const uint8_t *t;
+    uint64_t tlen;
+    int query_is_a;
+    int n_q, n_t;  // alphabet sizes on the query / template side
+};
+
+// lut_q/lut_t: 256-entry int16 byte->index (device), tab: n_q x n_t (row = query symbol)
+template <typename T, int MAXQ>
+__global__ void __launch_bounds__(SW_THREADS)
+sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__restrict__ lut_t,
+                const T *__restrict__ tab, T gap, int64_t *__restrict__ score,
+                int32_t *__restrict__ err, int64_t *__restrict__ errpos) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    T *s_tab = reinterpret_cast<T *>(sm);                       // [n_q * n_t]
+    int16_t *s_lut_t = reinterpret_cast<int16_t *>(s_tab + p.n_q * p.n_t);  // [256]
+    uint8_t *s_tidx = reinterpret_cast<uint8_t *>(s_lut_t + 256);           // [SW_TCHUNK]
+    __shared__ unsigned long long s_first_bad_t;
+
+    const uint32_t tid = threadIdx.x;
+    for (int i = tid; i < p.n_q * p.n_t; i += SW_THREADS) s_tab[i] = tab[i];
+    for (int i = tid; i < 256; i += SW_THREADS) s_lut_t[i] = lut_t[i];
+    if (tid == 0) s_first_bad_t = ~0ull;
+
+    const uint64_t qi = (uint64_t)blockIdx.x * SW_THREADS + tid;
+    const bool active = qi < p.nq;
+    uint64_t qbeg = 0;
+    uint32_t qlen = 0;
+    if (active) {
+        qbeg = p.qoff[qi];
+        qlen = (uint32_t)(p.qoff[qi + 1] - qbeg);
+    }
+    // per-cell row offsets into the table (symbol index * n_t); invalid symbols score 0
+    // through row 0 and are reported at the end
+    int qrow[MAXQ];
+    int64_t first_bad_q = -1;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) {
+        qrow[i] = 0;
+        if (i < (int)qlen) {
+            const int ix = lut_q[__ldg(p.q + qbeg + i)];
+            if (ix < 0) {
+                if (first_bad_q < 0) first_bad_q = i;
+            } else {
+                qrow[i] = ix * p.n_t;
+            }
+        }
+    }
+    T col[MAXQ];
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) col[i] = 0;
+    T best = 0;
+
+    for (uint64_t t0 = 0; t0 < p.tlen; t0 += SW_TCHUNK) {
+        const uint32_t tc = (uint32_t)min((uint64_t)SW_TCHUNK, p.tlen - t0);
+        __syncthreads();
+        for (uint32_t j = tid; j < tc; j += SW_THREADS) {
+            const int ix = s_lut_t[__ldg(p.t + t0 + j)];
+            if (ix < 0) atomicMin(&s_first_bad_t, (unsigned long long)(t0 + j));
+            s_tidx[j] = ix < 0 ? 0 : (uint8_t)ix;
+        }
+        __syncthreads();
+        if (active && qlen > 0) {
+            for (uint32_t j = 0; j < tc; ++j) {
+                const int tj = s_tidx[j];
+                T diag = 0, up = 0;
+#pragma unroll
+                for (int i = 0; i < MAXQ; ++i) {
+                    if (i < (int)qlen) {
+                        const T old = col[i];                 // H[i][j-1]
+                        const T sc = s_tab[qrow[i] + tj];     // align.go:188
+                        T v = addmax<T>(diag, sc, (T)0);      // align.go:192,195
+                        v = addmax<T>(old, gap, v);           // left / up by orientation
+                        v = addmax<T>(up, gap, v);
+                        best = v > best ? v : best;           // align.go:197-201
+                        diag = old;
+                        up = v;
+                        col[i] = v;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const int64_t bad_t = s_first_bad_t == ~0ull ? -1 : (int64_t)s_first_bad_t;
+    int32_t ec = 0;
+    int64_t ep = -1;
+    if (qlen > 0 && p.tlen > 0) {
+        // first failing cell in row-major order, stringA outer (align.go:186-191);
+        // Encode(a) is tried before Encode(b) (matrix.go:29-36)
+        const int64_t bad_a = p.query_is_a ? first_bad_q : bad_t;
+        const int64_t bad_b = p.query_is_a ? bad_t : first_bad_q;
+        if (bad_a == 0) { ec = 1; ep = 0; }
+        else if (bad_b >= 0) { ec = 2; ep = bad_b; }
+        else if (bad_a > 0) { ec = 1; ep = bad_a; }
+    }
+    score[qi] = ec ? 0 : (int64_t)best;
+    if (err) err[qi] = ec;
+    if (errpos) errpos[qi] = ep;
+}
+
+// Long queries: same recurrence, DP column in global scratch laid out [cell][query]
+// so that a warp's accesses coalesce.
+template <typename T>
+__global__ void __launch_bounds__(SW_THREADS)
+sw_score_long_kernel(SwParams p, uint64_t q_first, const int16_t *__restrict__ lut_q,
+                     const int16_t *__restrict__ lut_t, const T *__restrict__ tab, T gap,
+                     T *__restrict__ scratch, uint64_t n_batch, int64_t *__restrict__ score,
+                     int32_t *__restrict__ err, int64_t *__restrict__ errpos) {
+    const uint64_t b = (uint64_t)blockIdx.x * SW_THREADS + threadIdx.x;
+    if (b >= n_batch) return;
+    const uint64_t qi = q_first + b;
+    const uint64_t qbeg = p.qoff[qi];
+    const uint64_t qlen = p.qoff[qi + 1] - qbeg;
+    int64_t first_bad_q = -1, bad_t = -1;
+    for (uint64_t i = 0; i < qlen; ++i) {
+        scratch[i * n_batch + b] = 0;
+        if (first_bad_q < 0 && lut_q[__ldg(p.q + qbeg + i)] < 0) first_bad_q = (int64_t)i;
+    }
+    T best = 0;
+    for (uint64_t j = 0; j < p.tlen; ++j) {
+        const int tj = lut_t[__ldg(p.t + j)];
+        if (tj < 0 && bad_t < 0) bad_t = (int64_t)j;
+        T diag = 0, up = 0;
+        for (uint64_t i = 0; i < qlen; ++i) {
+            const int qx = lut_q[__ldg(p.q + qbeg + i)];
+            const T old = scratch[i * n_batch + b];
+            const T sc = (qx < 0 || tj < 0) ? (T)0 : tab[qx * p.n_t + tj];
+            T v = addmax<T>(diag, sc, (T)0);
+            v = addmax<T>(old, gap, v);
+            v = addmax<T>(up, gap, v);
+            best = v > best ? v : best;
+            diag = old;
+            up = v;
+            scratch[i * n_batch + b] = v;
+        }
+    }
+    int32_t ec = 0;
+    int64_t ep = -1;
+    if (qlen > 0 && p.tlen > 0) {
+        const int64_t bad_a = p.query_is_a ? first_bad_q : bad_t;
+        const int64_t bad_b = p.query_is_a ? bad_t : first_bad_q;
+        if (bad_a == 0) { ec = 1; ep = 0; }
+        else if (bad_b >= 0) { ec = 2; ep = bad_b; }
+        else if (bad_a > 0) { ec = 1; ep = bad_a; }
+    }
+    score[qi] = ec ? 0 : (int64_t)best;
+    if (err) err[qi] = ec;
+    if (errpos) errpos[qi] = ep;
+}
+
+template <typename T>
+int run_sw(const SwParams &p, uint64_t max_qlen, const int16_t *h_lut_q, const int16_t *h_lut_t,
+           const std::vector<int64_t> &tab_qt, int64_t gap, int64_t *d_score, int32_t *d_err,
+           int64_t *d_errpos, cudaStream_t st) {
+    // small parameter block: LUTs + table (query symbol major)
+    const size_t ntab = (size_t)p.n_q * p.n_t;
+    std::vector<uint8_t> blob(512 * 2 + ntab * sizeof(T));
+    memcpy(blob.data(), h_lut_q, 512);
+    memcpy(blob.data() + 512, h_lut_t, 512);
+    T *ht = reinterpret_cast<T *>(blob.data() + 1024);
+    for (size_t i = 0; i < ntab; ++i) ht[i] = (T)tab_qt[i];
+    uint8_t *d_blob = nullptr;
+    PG_CUDA(cudaMallocAsync(&d_blob, blob.size(), st));
+    PG_CUDA(cudaMemcpyAsync(d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaStreamSynchronize(st));  // blob is a stack-lifetime host buffer
+    const int16_t *d_lut_q = reinterpret_cast<const int16_t *>(d_blob);
+    const int16_t *d_lut_t = d_lut_q + 256;
+    const T *d_tab = reinterpret_cast<const T *>(d_blob + 1024);
+
+    const size_t smem = ntab * sizeof(T) + 512 + SW_TCHUNK;
+    const unsigned blocks = (unsigned)((p.nq + SW_THREADS - 1) / SW_THREADS);
+    int rc = PG_OK;
+    if (max_qlen <= 32 && smem <= 200 * 1024) {
+        cudaFuncSetAttribute(sw_score_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sw_score_kernel<T, 32><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap,
+                                                                 d_score, d_err, d_errpos);
+        note_launch("sw_score_kernel<32>");
+    } else if (max_qlen <= 64 && smem <= 200 * 1024) {
+        cudaFuncSetAttribute(sw_score_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sw_score_kernel<T, 64><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap,
+                                                                 d_score, d_err, d_errpos);
+        note_launch("sw_score_kernel<64>");
+    } else {
+        // batches bounded by a 1 GiB scratch column store
+        uint64_t per = std::max<uint64_t>(1, (1ull << 30) / (std::max<uint64_t>(max_qlen, 1) * sizeof(T)));
+        per = std::min<uint64_t>(per, p.nq);
+        T *d_scr = nullptr;
+        PG_CUDA(cudaMallocAsync(&d_scr, per * std::max<uint64_t>(max_qlen, 1) * sizeof(T), st));
+        for (uint64_t q0 = 0; q0 < p.nq; q0 += per) {
+            const uint64_t nb = std::min<uint64_t>(per, p.nq - q0);
+            sw_score_long_kernel<T><<<(unsigned)((nb + SW_THREADS - 1) / SW_THREADS), SW_THREADS, 0, st>>>(
+                p, q0, d_lut_q, d_lut_t, d_tab, (T)gap, d_scr, nb, d_score, d_err, d_errpos);
+            note_launch("sw_score_long_kernel");
+        }
+        cudaFreeAsync(d_scr, st);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "sw_score launch", __FILE__, __LINE__);
+    cudaFreeAsync(d_blob, st);
+    return rc;
+}
+
+}  // namespace
+
+int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen,
+                    const uint8_t *d_t, uint64_t tlen, int query_is_a, const int16_t *lut_a,
+                    const int16_t *lut_b, const int64_t *table, int n_a, int n_b, int64_t gap,
+                    int64_t *d_score, int32_t *d_err, int64_t *d_errpos, cudaStream_t st) {
+    if (nq == 0) return PG_OK;
+    if (n_a <= 0 || n_b <= 0 || n_a > 255 || n_b > 255) {
+        set_error("alphabet sizes must be in 1..255 (got %d, %d)", n_a, n_b);
+        return PG_ERR_ARG;
+    }
+    SwParams p;
+    p.q = d_q; p.qoff = d_qoff; p.nq = nq; p.t = d_t; p.tlen = tlen; p.query_is_a = query_is_a;
+    p.n_q = query_is_a ? n_a : n_b;
+    p.n_t = query_is_a ? n_b : n_a;
+    const int16_t *lut_q = query_is_a ? lut_a : lut_b;
+    const int16_t *lut_t = query_is_a ? lut_b : lut_a;
+    // table with the query symbol as the row: tab_qt[q][t] = S(a, b) in either orientation
+    std::vector<int64_t> tab_qt((size_t)p.n_q * p.n_t);
+    int64_t amax = 0;
+    for (int q = 0; q < p.n_q; ++q)
+        for (int t = 0; t < p.n_t; ++t) {
+            const int64_t v = query_is_a ? table[(size_t)q * n_b + t] : table[(size_t)t * n_b + q];
+            tab_qt[(size_t)q * p.n_t + t] = v;
+            amax = std::max<int64_t>(amax, v < 0 ? -v : v);
+        }
+    const int64_t agap = gap < 0 ? -gap : gap;
+    // every DP value lies in [0, min(la,lb) * max S]; operands of one add stay below
+    // that plus max(|S|,|gap|): use 32-bit DPX arithmetic when this provably fits
+    const long double bound = (long double)amax * (long double)std::min<uint64_t>(max_qlen, tlen) +
+                              (long double)std::max(amax, agap);
+    if (bound < 2.0e9L)
+        return run_sw<int>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st);
+    return run_sw<long long>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st);
+}
+
+}  // namespace pg

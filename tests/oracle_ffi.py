@@ -1,0 +1,166 @@
+"""ctypes binding for oracle/liboracle.so -- the CPU restatement of the reference.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Never imported by poly_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+_LIB = None
+
+PO_OK, PO_PANIC, PO_UNSUPPORTED = 0, -1, -2
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mash_oracle.c", "align_primers_oracle.c", "poly_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "CC=gcc"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        u8p, u32p, u64p, i64p = (C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int64))
+        L.po_murmur3_32.restype = C.c_uint32
+        L.po_murmur3_32.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
+        for f in (L.po_mash_sketch_faithful, L.po_mash_sketch_closed):
+            f.restype = C.c_int
+            f.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
+        L.po_mash_similarity.restype = C.c_int
+        L.po_mash_similarity.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, i64p, C.POINTER(C.c_double)]
+        L.po_mash_distance.restype = C.c_int
+        L.po_mash_distance.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.po_mash_sketch_batch.restype = C.c_int
+        L.po_mash_sketch_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, u64p]
+        L.po_sw_score.restype = C.c_int
+        L.po_sw_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int64, i64p, i64p, i64p, C.POINTER(C.c_int32), i64p]
+        L.po_nw_score.restype = C.c_int
+        L.po_nw_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
+        L.po_reverse_complement.restype = None
+        L.po_reverse_complement.argtypes = [C.c_char_p, C.c_int64, C.c_char_p]
+        L.po_santalucia.restype = C.c_int
+        L.po_santalucia.argtypes = [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.c_double] + [C.POINTER(C.c_double)] * 3
+        L.po_melting_temp.restype = C.c_int
+        L.po_melting_temp.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+def _b(s) -> bytes:
+    return s.encode("latin-1") if isinstance(s, str) else bytes(s)
+
+
+def murmur3_32(data, seed: int = 0) -> int:
+    d = _b(data)
+    return lib().po_murmur3_32(d, len(d), seed)
+
+
+class OracleMash:
+    """Mirror of mash.Mash (search/mash/mash.go:52-56) over the oracle."""
+
+    def __init__(self, kmer_size: int, sketch_size: int):
+        self.KmerSize, self.SketchSize = kmer_size, sketch_size
+        self.Sketches = np.zeros(sketch_size, dtype=np.uint32)
+
+    def Sketch(self, seq, faithful: bool = True) -> int:
+        d = _b(seq)
+        f = lib().po_mash_sketch_faithful if faithful else lib().po_mash_sketch_closed
+        return f(d, len(d), self.KmerSize, self.SketchSize, self.Sketches.ctypes.data)
+
+    def SimilarityCount(self, other: "OracleMash"):
+        same, sim = C.c_int64(0), C.c_double(0)
+        rc = lib().po_mash_similarity(self.Sketches.ctypes.data, self.SketchSize, other.Sketches.ctypes.data,
+                                      other.SketchSize, C.byref(same), C.byref(sim))
+        if rc != PO_OK:
+            raise IndexError("reference would panic: index out of range")
+        return same.value, sim.value
+
+    def Similarity(self, other) -> float:
+        return self.SimilarityCount(other)[1]
+
+    def Distance(self, other) -> float:
+        d = C.c_double(0)
+        rc = lib().po_mash_distance(self.Sketches.ctypes.data, self.SketchSize, other.Sketches.ctypes.data, other.SketchSize, C.byref(d))
+        if rc != PO_OK:
+            raise IndexError("reference would panic: index out of range")
+        return d.value
+
+
+def sketch_batch(bases: np.ndarray, offsets: np.ndarray, k: int, s: int, variant: int = 1, nthreads: int = 1,
+                 padded: bool = True):
+    """Returns (rc, out[n,s] uint32) -- fresh zeroed sketch per read."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    out = np.zeros((n, max(s, 0)), dtype=np.uint32)
+    rc = lib().po_mash_sketch_batch(bases.ctypes.data, offsets.ctypes.data, n, k, s, variant, nthreads, out.ctypes.data, None)
+    return rc, out
+
+
+def sketch_batch_timing(bases, offsets, k, s, variant, nthreads):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ck = C.c_uint64(0)
+    rc = lib().po_mash_sketch_batch(bases.ctypes.data, offsets.ctypes.data, len(offsets) - 1, k, s, variant, nthreads, None, C.byref(ck))
+    return rc, ck.value
+
+
+def sw_score(a, b, lut_a, lut_b, table, gap):
+    """Returns (score, max_row, max_col, err_code, err_pos)."""
+    a, b = _b(a), _b(b)
+    lut_a = np.ascontiguousarray(lut_a, dtype=np.int16)
+    lut_b = np.ascontiguousarray(lut_b, dtype=np.int16)
+    table = np.ascontiguousarray(table, dtype=np.int64)
+    sc, mr, mc, ep = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    ec = C.c_int32(0)
+    rc = lib().po_sw_score(a, len(a), b, len(b), lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[1], gap,
+                           C.byref(sc), C.byref(mr), C.byref(mc), C.byref(ec), C.byref(ep))
+    assert rc == PO_OK
+    return sc.value, mr.value, mc.value, ec.value, ep.value
+
+
+def nw_score(a, b, lut_a, lut_b, table, gap):
+    a, b = _b(a), _b(b)
+    lut_a = np.ascontiguousarray(lut_a, dtype=np.int16)
+    lut_b = np.ascontiguousarray(lut_b, dtype=np.int16)
+    table = np.ascontiguousarray(table, dtype=np.int64)
+    sc, ep, ec = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    rc = lib().po_nw_score(a, len(a), b, len(b), lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[1], gap,
+                           C.byref(sc), C.byref(ec), C.byref(ep))
+    assert rc == PO_OK
+    return sc.value, ec.value, ep.value
+
+
+def reverse_complement(seq) -> bytes:
+    d = _b(seq)
+    out = C.create_string_buffer(len(d))
+    lib().po_reverse_complement(d, len(d), out)
+    return out.raw
+
+
+def santalucia(seq, cp, na, mg):
+    d = _b(seq)
+    tm, dh, ds = C.c_double(0), C.c_double(0), C.c_double(0)
+    rc = lib().po_santalucia(d, len(d), cp, na, mg, C.byref(tm), C.byref(dh), C.byref(ds))
+    return rc, tm.value, dh.value, ds.value
+
+
+def melting_temp(seq) -> float:
+    rc, tm, _, _ = santalucia(seq, 500e-9, 50e-3, 0.0)
+    if rc == PO_PANIC:
+        raise IndexError("reference would panic: index out of range [-1]")
+    if rc != PO_OK:
+        raise ValueError("unsupported input")
+    return tm

@@ -1,0 +1,257 @@
+"""GPU parity: libpolyb200 (through the C ABI) vs the CPU oracle, bit-exact.
+
+Mirrors the reference's own tests for the path (search/mash/mash_test.go:9-62,
+example_test.go:9-22) and adds seeded batches at sizes the oracle finishes in seconds,
+the committed goldens, and size-independent properties at BASELINE scale.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from poly_b200 import mash, synth
+
+pytestmark = pytest.mark.gpu
+
+A = "ATGCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGA"
+B = "ATCGATCGATCGATCGATCGATCGATCGATCGATCGAATGCGATCGATCGATCGATCGATCG"
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_goldens.json")))
+
+
+def test_reference_TestMash(gpu):
+    """search/mash/mash_test.go:9-62, statement for statement."""
+    f1 = mash.New(17, 10); f1.Sketch(A)
+    f2 = mash.New(17, 9); f2.Sketch(A)
+    assert f1.Distance(f2) == 0
+    assert f2.Distance(f1) == 0
+    spoof = mash.New(17, 10); spoof.Sketches[0] = 0
+    assert f1.Distance(spoof) == 1
+    spoof = mash.New(17, 9)
+    assert f1.Distance(spoof) == 1
+    f1 = mash.New(17, 10); f1.Sketch(A)
+    f2 = mash.New(17, 5); f2.Sketch(B)
+    d = f1.Distance(f2)
+    assert 0.19 < d < 0.21 and d == 0.19999999999999996
+    f1 = mash.New(17, 10); f1.Sketch(B)
+    f2 = mash.New(17, 5); f2.Sketch(A)
+    assert f1.Distance(f2) == 0
+
+
+def test_reference_ExampleMash(gpu):
+    f1 = mash.New(17, 10); f1.Sketch(A)
+    f2 = mash.New(17, 9); f2.Sketch(A)
+    assert repr(f1.Distance(f2)) in ("0.0",)  # Go prints 0
+
+
+def test_survey_golden_sketches(gpu):
+    g = GOLD["mash"]
+    m = mash.New(17, 10); m.Sketch(A)
+    assert [int(x) for x in m.Sketches] == [int(x, 16) for x in g["A_k17_s10"]]
+    m = mash.New(17, 5); m.Sketch(B)
+    assert [int(x) for x in m.Sketches] == [int(x, 16) for x in g["B_k17_s5"]]
+    m = mash.New(17, 10); m.Sketch(B)
+    assert [int(x) for x in m.Sketches] == [int(x, 16) for x in g["B_k17_s10"]]
+
+
+def test_cfg1_bit_exact_and_checksums(gpu, oracle):
+    """BASELINE configs[0]: 1k x 150 bp, k=21, s=1000 (fill regime, fast TMA path)."""
+    n, L, k, s = 1000, 150, 21, 1000
+    reads = synth.independent_reads(n, L)
+    got = mash.sketch_uniform(reads, n, L, k, s)
+    rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=0)
+    assert rc == 0
+    assert got.shape == (n, L - k)
+    assert np.array_equal(got, want[:, : L - k])
+    assert not want[:, L - k:].any()
+    c = GOLD["cfg1"]
+    assert synth.fnv1a64(got) == int(c["fnv_compact"], 16)
+    padded = np.zeros((n, s), np.uint32); padded[:, : L - k] = got
+    assert synth.fnv1a64(padded) == int(c["fnv_padded"], 16)
+    assert int(got.astype(np.uint64).sum()) == int(c["sum"], 16)
+
+
+@pytest.mark.parametrize("k", [15, 16, 17, 19, 21, 23, 25, 27, 31, 32])
+@pytest.mark.parametrize("L", [64, 150, 151, 100])
+def test_uniform_fast_path_all_instantiated_k(gpu, oracle, k, L):
+    n, s = 32 * 9 + 5, 4096  # tiles + a ragged remainder that takes the generic kernel
+    reads = synth.independent_reads(n, L, first_read=7)
+    got = mash.sketch_uniform(reads, n, L, k, s)
+    rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=1)
+    assert np.array_equal(got, want[:, : max(L - k, 0)])
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4, 5, 7, 11, 13, 20, 22, 33, 40, 64])
+def test_generic_k(gpu, oracle, k):
+    n, L, s = 77, 97, 500
+    rng = np.random.default_rng(k)
+    reads = rng.integers(0, 256, n * L, dtype=np.uint8)  # arbitrary bytes are legal (mash.go:74-76)
+    got = mash.sketch_uniform(reads, n, L, k, s)
+    rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=1)
+    assert np.array_equal(got, want[:, : got.shape[1]])
+
+
+def test_ragged_batch_mixed_regimes(gpu, oracle):
+    """Empty reads, reads shorter than k, fill regime and select regime in one batch."""
+    rng = np.random.default_rng(1)
+    k, s = 21, 64
+    lens = [0, 1, 20, 21, 22, 23, 50, 84, 85, 86, 150, 300, 1000, 2500, 64 + 21, 63 + 21] + list(rng.integers(0, 400, 100))
+    seqs = [bytes(rng.choice(list(b"ACGTNacgt"), size=int(l)).astype(np.uint8)) for l in lens]
+    bases, offsets = mash.flatten(seqs)
+    out, count, status = mash.sketch_arrays(bases, offsets, k, s, pad_zero=True)
+    rc, want = oracle.sketch_batch(bases, offsets, k, s, variant=0)
+    assert rc == 0 and not status.any()
+    assert np.array_equal(out, want)
+    assert np.array_equal(count, np.minimum(np.maximum(np.array(lens) - k, 0), s))
+    # and through the object API
+    ms = mash.SketchBatch(seqs, k, s)
+    for m, w in zip(ms, want):
+        assert np.array_equal(m.Sketches, w)
+
+
+def test_select_regime_duplicates_and_ties(gpu, oracle):
+    """Bottom-s is a MULTISET (duplicates kept): low-complexity reads."""
+    rng = np.random.default_rng(2)
+    for k, s, L in [(17, 10, 62), (4, 50, 4000), (31, 2000, 10000), (8, 1000, 3000), (21, 1, 60), (5, 300, 20000)]:
+        seqs = [bytes(rng.choice(list(b"AC"), size=L).astype(np.uint8)) for _ in range(5)]
+        seqs.append(b"A" * L)
+        bases, offsets = mash.flatten(seqs)
+        out, count, status = mash.sketch_arrays(bases, offsets, k, s)
+        for i, q in enumerate(seqs):
+            o = oracle.OracleMash(k, s)
+            rc = o.Sketch(q, faithful=(L <= 4000))
+            if rc != 0:
+                assert status[i] == 1
+                continue
+            assert status[i] == 0 and count[i] == min(max(L - k, 0), s)
+            assert np.array_equal(out[i, : count[i]], o.Sketches[: count[i]]), (k, s, L, i)
+
+
+def test_cfg3_shape_sample_golden(gpu, oracle):
+    """8 family reads of the cfg3 shape (10 kbp, k=31, s=2000, R=4): SURVEY 8d goldens."""
+    n, L, k, s = 8, 10000, 31, 2000
+    reads = synth.family_reads(n, L, family=4)
+    got = mash.sketch_uniform(reads, n, L, k, s)
+    c = GOLD["cfg3_sample"]
+    assert [hex(int(x)) for x in got[0, :3]] == c["first3"]
+    assert hex(int(got[0, 1999])) == c["last"]
+    assert (np.diff(got.astype(np.int64), axis=1) >= 0).all()
+    assert synth.fnv1a64(got) == int(c["fnv"], 16)
+    same, dist = mash.distance_block(got)
+    assert [int(x) for x in same[0]] == c["row0"]
+    rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=1)
+    assert np.array_equal(got, want)
+
+
+def test_sketch_on_non_fresh_mash_keeps_tail(gpu, oracle):
+    """mash.go:81-84 only overwrites the first L-k slots when L-k < s."""
+    m = mash.New(21, 1000); o = oracle.OracleMash(21, 1000)
+    long = bytes(synth.independent_reads(1, 1500))
+    short = bytes(synth.independent_reads(1, 150, first_read=3))
+    for q in (long, short):
+        m.Sketch(q); o.Sketch(q)
+        assert np.array_equal(m.Sketches, o.Sketches)
+    assert m.Sketches[500] != 0  # tail of the previous (sorted) sketch survives
+
+
+def test_panics_small_sketch_sizes(gpu, oracle):
+    """sketchSize in {0,1}: mash.go:96-98 indexes Sketches[-1]."""
+    seq = bytes(synth.independent_reads(1, 100))
+    for s in (0, 1):
+        o = oracle.OracleMash(21, s)
+        rc = o.Sketch(seq)
+        m = mash.New(21, s)
+        if rc != 0:
+            with pytest.raises(IndexError):
+                m.Sketch(seq)
+        else:
+            m.Sketch(seq)
+            assert np.array_equal(m.Sketches, o.Sketches)
+    # s == 1 without panic: first hash is the minimum -> craft by trying reads
+    found = False
+    for r in range(400):
+        q = bytes(synth.independent_reads(1, 24, first_read=r))
+        o = oracle.OracleMash(21, 1)
+        if o.Sketch(q) == 0:
+            m = mash.New(21, 1); m.Sketch(q)
+            assert np.array_equal(m.Sketches, o.Sketches)
+            found = True
+            break
+    assert found
+    with pytest.raises(IndexError):
+        mash.New(17, 0).Distance(mash.New(17, 5))
+    with pytest.raises(IndexError):
+        mash.New(17, -1)
+
+
+def test_pairs_literal_semantics_unsorted_and_mixed_sizes(gpu, oracle):
+    """Similarity on unsorted (n < s) sketches follows the literal walk + early-out."""
+    rng = np.random.default_rng(3)
+    ms, os_ = [], []
+    specs = [(21, 1000, 150), (21, 100, 150), (21, 129, 150), (21, 130, 151), (17, 10, 62), (17, 9, 62), (17, 5, 62), (21, 50, 5000), (21, 64, 5000)]
+    for (k, s, L) in specs:
+        for rep in range(2):
+            q = bytes(synth.independent_reads(1, L, first_read=rep))
+            m = mash.New(k, s); m.Sketch(q); ms.append(m)
+            o = oracle.OracleMash(k, s); o.Sketch(q); os_.append(o)
+            assert np.array_equal(m.Sketches, o.Sketches)
+    # hand-made arrays: random unsorted, with zeros, equal values
+    for s in (1, 2, 7, 40):
+        for rep in range(3):
+            m = mash.New(5, s); m.Sketches[:] = rng.integers(0, 12, s); ms.append(m)
+            o = oracle.OracleMash(5, s); o.Sketches[:] = m.Sketches; os_.append(o)
+    n = len(ms)
+    pairs = np.array([(i, j) for i in range(n) for j in range(n)], dtype=np.uint32)
+    same, sim, dist = mash.similarity_pairs(ms, pairs)
+    for p, (i, j) in enumerate(pairs):
+        w_same, w_sim = os_[i].SimilarityCount(os_[j])
+        assert same[p] == w_same and sim[p] == w_sim and dist[p] == os_[i].Distance(os_[j]), (i, j)
+    # identical 150-bp reads have reference Distance 1.0 at k=21, s=1000 (SURVEY "READ THIS FIRST")
+    assert ms[0].Distance(ms[0]) == 1.0
+
+
+def test_distance_block_matches_pairs_and_oracle(gpu, oracle):
+    n, L, k, s = 24, 3000, 21, 256
+    reads = synth.family_reads(n, L, family=6)
+    sk = mash.sketch_uniform(reads, n, L, k, s)
+    same, dist = mash.distance_block(sk)
+    for i in range(n):
+        for j in range(n):
+            oi = oracle.OracleMash(k, s); oi.Sketches[:] = sk[i]
+            oj = oracle.OracleMash(k, s); oj.Sketches[:] = sk[j]
+            c, _ = oi.SimilarityCount(oj)
+            assert same[i, j] == c and dist[i, j] == oi.Distance(oj)
+    assert same.max() == s and (same == same.T).all()
+    # unsorted (fill-regime, zero padded) sketches through the same block kernel
+    reads = synth.independent_reads(16, 150)
+    out, _, _ = mash.sketch_arrays(reads, synth.uniform_offsets(16, 150), 21, 200, pad_zero=True)
+    out[3] = out[2]
+    same, dist = mash.distance_block(out)
+    for i in range(16):
+        for j in range(16):
+            oi = oracle.OracleMash(21, 200); oi.Sketches[:] = out[i]
+            oj = oracle.OracleMash(21, 200); oj.Sketches[:] = out[j]
+            assert same[i, j] == oi.SimilarityCount(oj)[0] and dist[i, j] == oi.Distance(oj)
+    # row block
+    s2, d2 = mash.distance_block(out, 5, 11)
+    assert np.array_equal(s2, same[5:11]) and np.array_equal(d2, dist[5:11])
+
+
+def test_full_size_properties_cfg2_slice(gpu, oracle):
+    """BASELINE cfg2 shape at 2M reads (device path via host API): spot-check rows against
+    the oracle, and a checksum-of-checksums that is independent of chunking."""
+    n, L, k, s = 2_000_000, 150, 21, 1000
+    reads = synth.independent_reads(n, L)
+    got = mash.sketch_uniform(reads, n, L, k, s)
+    idx = np.r_[0:64, n // 2 - 32: n // 2 + 32, n - 64: n, np.random.default_rng(5).integers(0, n, 512)]
+    sub = np.concatenate([reads[i * L:(i + 1) * L] for i in idx])
+    rc, want = oracle.sketch_batch(sub, synth.uniform_offsets(len(idx), L), k, s, variant=1)
+    assert np.array_equal(got[idx], want[:, : L - k])
+    # chunk-independence: the same reads sketched in two halves
+    h1 = mash.sketch_uniform(reads[: (n // 2) * L], n // 2, L, k, s)
+    assert np.array_equal(h1, got[: n // 2])
+    # shift property: read i+1 of a sliding set shares k-mer hashes with read i
+    one = reads[: L + 1]
+    a = mash.sketch_uniform(np.ascontiguousarray(one[:L]), 1, L, k, s)[0]
+    b = mash.sketch_uniform(np.ascontiguousarray(one[1:]), 1, L, k, s)[0]
+    assert np.array_equal(a[1:], b[:-1])
