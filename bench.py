@@ -58,11 +58,12 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t_load = self.t0 = self.t1 = None  # load start (warm-up), timed region start / end
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -70,7 +71,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -80,8 +81,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # samples inside the timed region; a region shorter than a few sampling periods falls
+        # back to the whole loaded window (warm-up + timed), and says so
+        rows = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        window = "timed region"
+        if len(rows) < 3 and self.t_load is not None:
+            rows = [r for (t, r) in self.rows if self.t_load <= t <= self.t1 + 0.05]
+            window = "warm-up + timed region (timed region shorter than 3 sampling periods)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
             except Exception:
@@ -90,7 +98,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_reference_leg(threads: int, budget_s: float, first_read: int = 0):
@@ -186,20 +194,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)  # let nvidia-smi start streaming
+    clocks.t_load = time.time()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # keep the device loaded for >= 100 ms before the timed region so that the clock samples
+    # describe clocks under load (untimed; same kernel)
+    barrier()
+    t_pre = time.time()
+    while time.time() - t_pre < 0.1:
+        step()
+        torch.cuda.synchronize()
+    barrier()
     launches0 = L.pg_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.t0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    clocks.t1 = time.time()
     ms = ev0.elapsed_time(ev1)
     launches = L.pg_launch_count() - launches0
     kernel_name = (L.pg_last_kernel() or b"").decode()

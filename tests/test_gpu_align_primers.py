@@ -1,0 +1,153 @@
+"""GPU parity for the secondary kernels (K4 Smith-Waterman score, K5 SantaLucia Tm)
+through the C ABI: the reference's own known answers, then seeded batches vs the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from poly_b200 import align, mash, primers, synth
+from test_oracle_align_primers import GENE, NUC_4, TEST_LUT, TEST_MAT, design_primers, lut
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_goldens.json")))
+
+
+def test_scoring():
+    a = align.NewAlphabet(["-", "A", "C", "G", "T"])
+    return align.NewScoring(align.NewSubstitutionMatrix(a, a, TEST_MAT), -2)
+
+
+SC = test_scoring()
+
+
+def test_reference_TestSmithWaterman(gpu):
+    """search/align/align_test.go:139-292 (scores)."""
+    assert align.SmithWaterman("TGTTACGG", "GGTTGACTA", SC) == 13
+    assert align.SmithWaterman("ACACACTA", "AGCACACA", SC) == 17
+    assert align.SmithWaterman("", "GAT", SC) == 0
+    assert align.SmithWaterman("", "", SC) == 0
+    assert align.SmithWaterman("G", "A", SC) == 0
+    assert align.SmithWaterman("G", "G", SC) == 3
+    assert align.SmithWaterman("G", "GATTACA", SC) == 3
+
+
+def test_reference_examples(gpu):
+    """search/align/example_test.go:49-111."""
+    a5 = align.NewAlphabet(["A", "C", "G", "T", "U"])
+    sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, 2 * np.eye(5, dtype=np.int64) - 1), -1)
+    assert align.SmithWaterman("GATTACA", "GCATGCU", sc) == 2
+    an = align.NewAlphabet(["A", "C", "G", "T", "-"])
+    sc = align.NewScoring(align.NewSubstitutionMatrix(an, an, align.NUC_4), -1)
+    assert align.SmithWaterman("GATTACA", "GCATGCT", sc) == 15  # literal index mapping, not 17
+    assert align.SmithWaterman("GATTACA", "GCATGCU", align.NewScoring(None, -1)) == 2  # matrix.Default
+
+
+def test_sw_errors_match_reference_order(gpu, oracle):
+    for a, b in [("ANA", "GAT"), ("NAA", "GXT"), ("ANA", "GXT"), ("AAN", "GAT"), ("", "X"), ("X", ""), ("ACGT", "ACGX")]:
+        w = oracle.sw_score(a, b, TEST_LUT, TEST_LUT, TEST_MAT, -2)
+        for query_is_a in (True, False):
+            q, t = (a, b) if query_is_a else (b, a)
+            scores, errs = align.SmithWatermanScores([q], t, SC, query_is_a=query_is_a)
+            if w[3] == 0:
+                assert errs[0] is None and scores[0] == w[0]
+            else:
+                bad = (a if w[3] == 1 else b)[w[4]]
+                assert scores[0] == 0 and str(errs[0]) == f"Symbol {bad} not in alphabet"
+    with pytest.raises(align.AlphabetError, match="Symbol X not in alphabet"):
+        align.SmithWaterman("ACGT", "ACGX", SC)
+
+
+@pytest.mark.parametrize("maxq,tlen", [(25, 10000), (32, 777), (33, 500), (64, 9000), (65, 300), (200, 1000)])
+def test_sw_batch_vs_oracle(gpu, oracle, maxq, tlen):
+    """All three kernel variants (<=32, <=64 register columns; long = global column), both
+    orientations, ragged query lengths, a template longer than one smem chunk."""
+    rng = np.random.default_rng(maxq)
+    nq = 300
+    qs = [bytes(rng.choice(list(b"ACGT-"), size=int(rng.integers(0, maxq + 1))).astype(np.uint8)) for _ in range(nq - 1)]
+    qs.append(bytes(rng.choice(list(b"ACGT"), size=maxq).astype(np.uint8)))
+    t = bytes(rng.choice(list(b"ACGT"), size=tlen).astype(np.uint8))
+    for query_is_a in (True, False):
+        scores, errs = align.SmithWatermanScores(qs, t, SC, query_is_a=query_is_a)
+        for i in range(0, nq, 7):
+            a, b = (qs[i], t) if query_is_a else (t, qs[i])
+            w = oracle.sw_score(a, b, TEST_LUT, TEST_LUT, TEST_MAT, -2)
+            assert errs[i] is None and scores[i] == w[0], (i, query_is_a)
+
+
+def test_sw_protein_matrix_and_wide_scores(gpu, oracle):
+    """Non-square use of Default (26 letters) and values that force the int64 kernel."""
+    rng = np.random.default_rng(9)
+    letters = [chr(65 + i) for i in range(26)]
+    qs = [bytes(rng.choice(list(range(65, 91)), size=30).astype(np.uint8)) for _ in range(40)]
+    t = bytes(rng.choice(list(range(65, 91)), size=400).astype(np.uint8))
+    sc = align.NewScoring(None, -1)
+    scores, errs = align.SmithWatermanScores(qs, t, sc)
+    l = lut(letters)
+    for i in range(40):
+        assert scores[i] == oracle.sw_score(qs[i], t, l, l, 2 * np.eye(26, dtype=np.int64) - 1, -1)[0]
+    big = np.array(TEST_MAT, dtype=np.int64) * (1 << 33)
+    a = align.NewAlphabet(["-", "A", "C", "G", "T"])
+    scb = align.NewScoring(align.NewSubstitutionMatrix(a, a, big), -(1 << 34))
+    q = [bytes(rng.choice(list(b"ACGT"), size=20).astype(np.uint8)) for _ in range(33)]
+    tt = bytes(rng.choice(list(b"ACGT"), size=300).astype(np.uint8))
+    scores, errs = align.SmithWatermanScores(q, tt, scb)
+    for i in range(33):
+        assert scores[i] == oracle.sw_score(q[i], tt, TEST_LUT, TEST_LUT, big, -(1 << 34))[0]
+
+
+def test_cfg5_goldens_and_sample(gpu, oracle):
+    """BASELINE configs[4] shape: 25-bp primers vs the 10 kb template."""
+    n = 4096
+    pr = synth.primers(n)
+    off = synth.uniform_offsets(n, 25)
+    tpl = synth.template()
+    score, ec, ep = align.sw_scores_arrays(pr, off, tpl, SC)
+    assert not ec.any()
+    assert score[:6].tolist() == GOLD["cfg5"]["sw"]
+    for i in range(0, n, 97):
+        assert score[i] == oracle.sw_score(bytes(pr[25 * i:25 * i + 25]), bytes(tpl), TEST_LUT, TEST_LUT, TEST_MAT, -2)[0]
+    tm, dh, ds, st = primers.santalucia_arrays(pr, off, primers.DEFAULT_CP, primers.DEFAULT_NA, primers.DEFAULT_MG)
+    assert not st.any()
+    assert tm[:6] == pytest.approx(GOLD["cfg5"]["tm"], rel=1e-6)  # north_star tolerance: 1e-6 relative
+    for i in range(n):
+        rc, wt, wh, ws = oracle.santalucia(bytes(pr[25 * i:25 * i + 25]), primers.DEFAULT_CP, primers.DEFAULT_NA, primers.DEFAULT_MG)
+        assert abs(tm[i] - wt) <= 1e-6 * abs(wt) and abs(dh[i] - wh) <= 1e-9 * abs(wh) and abs(ds[i] - ws) <= 1e-6 * abs(ws)
+
+
+def test_reference_tm_tests(gpu):
+    """primers/primers_test.go:29-84."""
+    tm, dh, ds = primers.SantaLucia("ACGATGGCAGTAGCATGC", 0.1e-6, 350e-3, 0.0)
+    assert abs(62.7 - tm) / 62.7 < 0.02
+    assert (tm, dh, ds) == pytest.approx(tuple(GOLD["tm"]["ACGATGGCAGTAGCATGC"]), rel=1e-6)
+    tm, dh, ds = primers.SantaLucia("ACGTAGATCTACGT", 0.1e-6, 350e-3, 0.0)
+    assert abs(47.428514 - tm) / 47.428514 < 0.02
+    assert (tm, dh, ds) == pytest.approx(tuple(GOLD["tm"]["ACGTAGATCTACGT"]), rel=1e-6)
+    tm = primers.MeltingTemp("GTAAAACGACGGCCAGT")
+    assert abs(52.8 - tm) / 52.8 < 0.02 and tm == pytest.approx(GOLD["tm"]["GTAAAACGACGGCCAGT_meltingtemp"], rel=1e-6)
+    assert primers.MeltingTemp("gtaaaacgacggccagt") == tm
+    with pytest.raises(IndexError):
+        primers.MeltingTemp("")
+    with pytest.raises(ValueError):
+        primers.MeltingTemp(b"AC\xc3\xa9")
+
+
+def test_tm_edge_symbols_vs_oracle(gpu, oracle):
+    """Unknown neighbours contribute {0,0} (primers.go:98), IUPAC palindromes, lower case."""
+    rng = np.random.default_rng(4)
+    seqs = [b"A", b"T", b"N", b"AT", b"ACGT", b"NNNN", b"RY", b"acgt", b"AcGtNnRy", b"SSSS", b"WWWW", b"A\x00T"]
+    seqs += [bytes(rng.choice(list(b"ACGTNacgtnRYSWKMBDHV\x00 "), size=int(rng.integers(1, 60))).astype(np.uint8)) for _ in range(300)]
+    bases, off = mash.flatten(seqs)
+    for (cp, na, mg) in [(500e-9, 50e-3, 0.0), (0.1e-6, 350e-3, 0.0), (1e-6, 10e-3, 2e-3)]:
+        tm, dh, ds, st = primers.santalucia_arrays(bases, off, cp, na, mg)
+        for i, q in enumerate(seqs):
+            rc, wt, wh, ws = oracle.santalucia(q, cp, na, mg)
+            assert rc == 0 and st[i] == 0
+            assert dh[i] == pytest.approx(wh, rel=1e-12, abs=1e-12) and ds[i] == pytest.approx(ws, rel=1e-9)
+            assert tm[i] == pytest.approx(wt, rel=1e-6), q
+
+
+def test_reference_design_primers_through_gpu(gpu):
+    """primers/pcr/example_test.go:36,46,54: primer strings pinned by Tm threshold crossings,
+    with every MeltingTemp evaluated on the GPU."""
+    assert design_primers(primers.MeltingTemp, GENE, 55.0) == ("AATAATTACACCGAGATAACACATCATGG", "TTAAGAAAGCGCATTTTCCAGC")
