@@ -185,9 +185,10 @@ static void *batch_worker(void *p) {
         int rc = j->variant == 0 ? po_mash_sketch_faithful(seq, len, j->k, j->s, sk)
                                  : po_mash_sketch_closed(seq, len, j->k, j->s, sk);
         if (rc != PO_OK) j->rc = rc;
-        if (!j->out) {
-            const uint8_t *b = (const uint8_t *)sk;
-            for (size_t t = 0; t < (size_t)j->s * 4; t++) { fnv ^= b[t]; fnv *= 0x100000001b3ull; }
+        if (!j->out) { /* cheap digest so the work is not optimised away (not part of the timing story) */
+            uint64_t acc = 0;
+            for (int t = 0; t < j->s; t++) acc += sk[t];
+            fnv = (fnv ^ acc) * 0x100000001b3ull;
             free(sk);
         }
     }

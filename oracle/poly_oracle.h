@@ -48,7 +48,7 @@ int po_mash_distance(const uint32_t *a, int sa, const uint32_t *b, int sb, doubl
  * read (as mash.New does, mash.go:59-65), reads in [offsets[i], offsets[i+1]).
  * variant 0 = faithful, 1 = closed form.  out is n*s words (padded layout).
  * If out == NULL the sketches are allocated, computed and freed per read (pure
- * timing mode; a 64-bit FNV-1a of all words is returned through checksum). */
+ * timing mode; a digest of the per-read word sums is returned through checksum). */
 int po_mash_sketch_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n, int k, int s,
                          int variant, int nthreads, uint32_t *out, uint64_t *checksum);
 

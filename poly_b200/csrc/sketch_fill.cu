@@ -7,8 +7,13 @@
 //   * one THREAD per read walks the read 4 bytes per step.  The murmur3 block pre-mix
 //     K(p) = rotl(w(p)*c1,15)*c2 of the 4 bytes at position p is computed ONCE and kept
 //     in a register ring shared by the k/4 k-mers that consume it, so the cost per
-//     k-mer is the body chain + fmix, not k/4 pre-mixes (integer-issue is the
-//     co-limit of this kernel);
+//     k-mer is the body chain + fmix, not k/4 pre-mixes.  The kernel is bound by the
+//     ALU pipe (SHF/LOP3 issue at one warp instruction per 2 cycles per SM sub-partition,
+//     tools/pipe_bench.cu), i.e. by ALU instruction COUNT, so everything that is not
+//     murmur3 arithmetic is kept off that pipe: for k % 4 == 1 the tail pre-mix comes from
+//     a 256-entry shared-memory table (2 LSU instructions, table address formed by IMAD on
+//     the FMA pipe), the main loop has no bounds tests or predicated stores, and raw words
+//     are fetched one step ahead (DESIGN.md "K1", profiles/);
 //   * hashes are staged in shared memory ([read][pos], stride L-k words: bank-conflict
 //     free when L-k is odd) and leave as ONE bulk store per tile (the compact output
 //     [n][L-k] of a tile is contiguous in HBM).
@@ -75,128 +80,18 @@ __device__ __forceinline__ void fence_async_smem() {
 
 // ---- K1 fast path ----------------------------------------------------------------
 // smem: [0,16) mbarrier | in tile (R*L bytes + 16 B over-read pad, 16-B rounded) | out tile
+// (+ 1 KB static table when k % 4 == 1)
 __host__ __device__ inline uint32_t k1_in_bytes(uint32_t R, uint32_t L) {
     return (R * L + 16u + 15u) & ~15u;
 }
 
-template <int K, int R>
-__global__ void __launch_bounds__(R)
-sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, uint32_t *__restrict__ out,
-                           uint32_t L, uint32_t nk) {
-    constexpr int NB = K / 4;      // 4-byte body blocks per k-mer
-    constexpr int TAIL = K % 4;    // tail bytes per k-mer
-    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
-    static_assert(NB >= 1, "fast path needs k >= 4");
-
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    uint8_t *s_in = smem + 16;
-    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_in + k1_in_bytes(R, L));
-
-    const uint32_t tid = threadIdx.x;
-    const uint64_t tile = blockIdx.x;
-    const uint32_t in_bytes = R * L;  // multiple of 16 (host guarantees)
-
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(bar, in_bytes);
-        bulk_g2s(s_in, bases + tile * in_bytes, in_bytes, bar);
-    }
-    __syncthreads();  // barrier init visible to the waiters
-    mbar_wait(bar, 0);
-
-    // my read: bytes [tid*L, tid*L+L) of the tile, realigned to words on the fly
-    const uint32_t b0 = tid * L;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_in) + (b0 >> 2);
-    const uint32_t sh = (b0 & 3u) * 8u;
-    uint32_t *my_out = s_out + tid * nk;
-
-    uint32_t raw_prev = sw[0], raw = sw[1];
-    uint32_t w_cur = __funnelshift_r(raw_prev, raw, sh);  // bytes 4Q .. 4Q+3 of the read
-    raw_prev = raw;
-    raw = sw[2];
-    uint32_t w_nxt = __funnelshift_r(raw_prev, raw, sh);  // bytes 4Q+4 .. 4Q+7
-    raw_prev = raw;
-
-    uint32_t ring[4][NB];  // ring[r][*]: pre-mixes K(4q+r) of the last NB word steps
-
-    // prologue: word steps 0 .. NB-1 only fill the ring
-#pragma unroll
-    for (int q = 0; q < NB; ++q) {
-        ring[0][q] = mm3_kmix(w_cur);
-        ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
-        ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
-        ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
-        w_cur = w_nxt;
-        raw = sw[q + 3];
-        w_nxt = __funnelshift_r(raw_prev, raw, sh);
-        raw_prev = raw;
-    }
-
-    // main loop: at word step Q = NB + i0/4 the k-mers i0+r (r = 0..3) complete: their
-    // body blocks are ring[r][oldest .. newest], their tail bytes are the low bytes of
-    // the window at position i0 + r + 4*NB, i.e. the windows formed in this very step.
-    for (uint32_t i0 = 0; i0 < nk; i0 += 4 * NB) {
-#pragma unroll
-        for (int u = 0; u < NB; ++u) {
-            const uint32_t i = i0 + 4 * u;
-            if (i < nk) {
-                uint32_t w[4];
-                w[0] = w_cur;
-                w[1] = __funnelshift_r(w_cur, w_nxt, 8);
-                w[2] = __funnelshift_r(w_cur, w_nxt, 16);
-                w[3] = __funnelshift_r(w_cur, w_nxt, 24);
-                uint32_t h[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    uint32_t x = mm3_round0(ring[r][u]);
-#pragma unroll
-                    for (int j = 1; j < NB; ++j) x = mm3_round(x, ring[r][(u + j) % NB]);
-                    if (TAIL) x ^= mm3_kmix(w[r] & TAILMASK);
-                    x ^= (uint32_t)K;
-                    h[r] = mm3_fmix(x);
-                    ring[r][u] = mm3_kmix(w[r]);
-                }
-                // positional store (mash.go:81-84); the last step may be partial
-                my_out[i] = h[0];
-                if (i + 1 < nk) my_out[i + 1] = h[1];
-                if (i + 2 < nk) my_out[i + 2] = h[2];
-                if (i + 3 < nk) my_out[i + 3] = h[3];
-                w_cur = w_nxt;
-                raw = sw[(i >> 2) + NB + 3];
-                w_nxt = __funnelshift_r(raw_prev, raw, sh);
-                raw_prev = raw;
-            }
-        }
-    }
-
-    // hand the staged tile to the async proxy and bulk-store it
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-        const uint32_t out_bytes = R * nk * 4u;  // multiple of 16 (R % 4 == 0)
-        bulk_s2g(out + tile * (uint64_t)(R * nk), s_out, out_bytes);
-        bulk_wait_read0();
-    }
-}
-
-// ---- K1 v2: same tiling, fewer ALU-pipe instructions per k-mer ----------------------
-// Measured on B200 (tools/pipe_bench.cu, profiles/r01_*): SHF/LOP3/PRMT/ISETP issue at one
-// warp instruction per 2 cycles per SM sub-partition and v1 keeps that pipe 92 % busy, so
-// the kernel is bound by ALU-pipe instruction COUNT.  v2 removes the ones that are not
-// murmur3 arithmetic:
-//   * k % 4 == 1: the tail pre-mix of the single tail byte comes from a 256-entry shared
-//     memory table (byte fetched with LDS.U8 straight from the staged read): 2 LSU
-//     instructions instead of LOP3 + IMAD + SHF + IMAD;
-//   * the main loop runs over full groups of NB word steps with no bounds tests or
-//     predicated stores; the (< NB + 1) remaining steps run once through a checked copy;
-//   * the raw shared-memory words are fetched one step ahead of their use.
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
     return v;
 }
+
+// kmix(b) for a single tail byte b, built at compile time
 struct KmixTable {
     uint32_t v[256];
 };
@@ -208,82 +103,7 @@ constexpr KmixTable make_kmix_table() {
 }
 __device__ __align__(16) const KmixTable g_kmix_byte = make_kmix_table();
 
-// right shifts of fmix done as IMAD.HI (x * 2^(32-s)) >> 32 on the FMA pipe for the first FM of
-// the three shifts; the multipliers arrive as kernel arguments so ptxas keeps the multiply
-struct K1Consts {
-    uint32_t lut_stride;  // 4
-    uint32_t m16, m19;    // 1<<16, 1<<19
-};
-template <int FM>
-__device__ __forceinline__ uint32_t mm3_fmix_v(uint32_t h, const K1Consts &c) {
-    h ^= FM >= 1 ? __umulhi(h, c.m16) : (h >> 16);
-    h *= 0x85ebca6bu;
-    h ^= FM >= 2 ? __umulhi(h, c.m19) : (h >> 13);
-    h *= 0xc2b2ae35u;
-    h ^= FM >= 3 ? __umulhi(h, c.m16) : (h >> 16);
-    return h;
-}
-
-template <int K, int R, int FM>
-__global__ void __launch_bounds__(R)
-sketch_fill_uniform_v2_kernel(const uint8_t *__restrict__ bases, uint32_t *__restrict__ out,
-                              uint32_t L, uint32_t nk, const K1Consts kc) {
-    const uint32_t lut_stride = kc.lut_stride;
-    constexpr int NB = K / 4;
-    constexpr int TAIL = K % 4;
-    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
-    constexpr bool LUT = TAIL == 1;
-    static_assert(NB >= 1, "fast path needs k >= 4");
-
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];  // static: fixed address -> LDS [R.X4+imm]
-    uint8_t *s_in = smem + 16;
-    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_in + k1_in_bytes(R, L));
-
-    const uint32_t tid = threadIdx.x;
-    const uint64_t tile = blockIdx.x;
-    const uint32_t in_bytes = R * L;
-
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(bar, in_bytes + (LUT ? 1024u : 0u));
-        bulk_g2s(s_in, bases + tile * in_bytes, in_bytes, bar);
-        if (LUT) bulk_g2s(s_lut, &g_kmix_byte, 1024u, bar);
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
-
-    const uint32_t b0 = tid * L;
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_in) + (b0 >> 2);
-    const uint8_t *sb = s_in + b0 + 4 * NB;  // tail byte of k-mer i is sb[i]
-    const uint32_t sh = (b0 & 3u) * 8u;
-    uint32_t *my_out = s_out + tid * nk;
-    // table address = byte * 4 + base.  The scale arrives as a kernel argument so that the
-    // multiply-add stays an IMAD (FMA pipe) instead of being strength-reduced to LEA (ALU pipe).
-    const uint32_t lut_base = smem_u32(s_lut);
-
-    uint32_t raw_a = sw[0], raw_b = sw[1];
-    uint32_t w_cur = __funnelshift_r(raw_a, raw_b, sh);
-    raw_a = raw_b; raw_b = sw[2];
-    uint32_t w_nxt = __funnelshift_r(raw_a, raw_b, sh);
-    raw_a = raw_b; raw_b = sw[3];   // one word ahead
-    const uint32_t *swp = sw + 4;   // next raw word to fetch
-
-    uint32_t ring[4][NB];
-#pragma unroll
-    for (int q = 0; q < NB; ++q) {
-        ring[0][q] = mm3_kmix(w_cur);
-        ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
-        ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
-        ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
-        w_cur = w_nxt;
-        w_nxt = __funnelshift_r(raw_a, raw_b, sh);
-        raw_a = raw_b;
-        raw_b = *swp++;
-    }
-
+// One word step = 4 k-mers (ring slot U).  Uses the locals of the enclosing kernel.
 #define PG_K1_STEP(U, CHECKED)                                                                 \
     {                                                                                          \
         uint32_t w[4];                                                                         \
@@ -298,7 +118,7 @@ sketch_fill_uniform_v2_kernel(const uint8_t *__restrict__ bases, uint32_t *__res
             if (LUT) x ^= lds_u32(sb[i + r] * lut_stride + lut_base);                          \
             else if (TAIL) x ^= mm3_kmix(w[r] & TAILMASK);                                     \
             x ^= (uint32_t)K;                                                                  \
-            h[r] = mm3_fmix_v<FM>(x, kc);                                                      \
+            h[r] = mm3_fmix(x);                                                                \
             ring[r][U] = mm3_kmix(w[r]);                                                       \
         }                                                                                      \
         my_out[i] = h[0];                                                                      \
@@ -312,27 +132,89 @@ sketch_fill_uniform_v2_kernel(const uint8_t *__restrict__ bases, uint32_t *__res
         i += 4;                                                                                \
     }
 
+// lut_stride == 4 arrives as a kernel argument so that the table address byte*4 + base
+// stays an IMAD (FMA pipe) instead of being strength-reduced to LEA (ALU pipe).
+template <int K, int R>
+__global__ void __launch_bounds__(R)
+sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, uint32_t *__restrict__ out,
+                           uint32_t L, uint32_t nk, uint32_t lut_stride) {
+    constexpr int NB = K / 4;    // 4-byte body blocks per k-mer
+    constexpr int TAIL = K % 4;  // tail bytes per k-mer
+    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
+    constexpr bool LUT = TAIL == 1;
+    static_assert(NB >= 1, "fast path needs k >= 4");
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
+    uint8_t *s_in = smem + 16;
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_in + k1_in_bytes(R, L));
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t tile = blockIdx.x;
+    const uint32_t in_bytes = R * L;  // multiple of 16 (host guarantees)
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, in_bytes + (LUT ? 1024u : 0u));
+        bulk_g2s(s_in, bases + tile * in_bytes, in_bytes, bar);
+        if (LUT) bulk_g2s(s_lut, &g_kmix_byte, 1024u, bar);
+    }
+    __syncthreads();  // barrier init visible to the waiters
+    mbar_wait(bar, 0);
+
+    // my read: bytes [tid*L, tid*L+L) of the tile, realigned to words on the fly
+    const uint32_t b0 = tid * L;
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_in) + (b0 >> 2);
+    const uint8_t *sb = s_in + b0 + 4 * NB;  // tail byte of k-mer i is sb[i]
+    const uint32_t sh = (b0 & 3u) * 8u;
+    uint32_t *my_out = s_out + tid * nk;
+    const uint32_t lut_base = smem_u32(s_lut);
+
+    uint32_t raw_a = sw[0], raw_b = sw[1];
+    uint32_t w_cur = __funnelshift_r(raw_a, raw_b, sh);  // bytes 4Q .. 4Q+3 of the read
+    raw_a = raw_b; raw_b = sw[2];
+    uint32_t w_nxt = __funnelshift_r(raw_a, raw_b, sh);  // bytes 4Q+4 .. 4Q+7
+    raw_a = raw_b; raw_b = sw[3];                        // one word ahead of its use
+    const uint32_t *swp = sw + 4;
+
+    uint32_t ring[4][NB];  // ring[r][*]: pre-mixes K(4q+r) of the last NB word steps
+    // prologue: word steps 0 .. NB-1 only fill the ring
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+        ring[0][q] = mm3_kmix(w_cur);
+        ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
+        ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
+        ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
+        w_cur = w_nxt;
+        w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+        raw_a = raw_b;
+        raw_b = *swp++;
+    }
+
+    // At word step Q = NB + i/4 the k-mers i+r (r = 0..3) complete: their body blocks are
+    // ring[r][oldest .. newest], their tail bytes start at position i + r + 4*NB.
     uint32_t i = 0;
-    // full groups: NB word steps = 4*NB k-mers, no bounds tests
     const uint32_t n_main = (nk / (4 * NB)) * (4 * NB);
-    while (i < n_main) {
+    while (i < n_main) {  // full groups of NB word steps: no bounds tests
 #pragma unroll
         for (int u = 0; u < NB; ++u) PG_K1_STEP(u, false)
     }
-    // remainder: < NB full steps plus possibly one partial step
 #pragma unroll
-    for (int u = 0; u < NB; ++u) {
+    for (int u = 0; u < NB; ++u) {  // remainder: < NB full steps plus possibly a partial one
         if (i < nk) PG_K1_STEP(u, true)
     }
-#undef PG_K1_STEP
 
+    // hand the staged tile to the async proxy and bulk-store it (positional, mash.go:81-84)
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        bulk_s2g(out + tile * (uint64_t)(R * nk), s_out, R * nk * 4u);
+        bulk_s2g(out + tile * (uint64_t)(R * nk), s_out, R * nk * 4u);  // multiple of 16 (R % 4 == 0)
         bulk_wait_read0();
     }
 }
+#undef PG_K1_STEP
 
 // ---- generic fill path -----------------------------------------------------------
 // One warp per read.  Handles reads with n = max(len-k,0) < s (others are left to the
@@ -374,56 +256,19 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
 }
 
 // ---- launchers -------------------------------------------------------------------
-static int k1_env(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-// A/B knobs (tuning runs): PG_K1_VARIANT=1 first-generation kernel; PG_K1_FM=0..3 number of
-// fmix shifts issued on the FMA pipe; PG_K1_R=32|64 reads per CTA.
-static int k1_variant() { static int v = k1_env("PG_K1_VARIANT", 2); return v; }
-static int k1_fm() { static int v = k1_env("PG_K1_FM", 0); return v; }
-static int k1_r() { static int v = k1_env("PG_K1_R", 32); return v; }
-
-template <int K, int R, int FM>
-static int launch_k1v2(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
-                       uint32_t *d_out, cudaStream_t st) {
-    const size_t smem = 16 + k1_in_bytes(R, L) + (size_t)R * nk * 4;
-    static size_t configured2 = 0;
-    if (smem > configured2) {
-        PG_CUDA(cudaFuncSetAttribute(sketch_fill_uniform_v2_kernel<K, R, FM>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured2 = smem;
-    }
-    const K1Consts kc{4u, 1u << 16, 1u << 19};
-    sketch_fill_uniform_v2_kernel<K, R, FM><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, d_out, L, nk, kc);
-    PG_LAUNCH_CHECK("sketch_fill_uniform_v2_kernel");
-    return PG_OK;
-}
-
 template <int K, int R>
 static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
                      uint32_t *d_out, cudaStream_t st) {
-    if (k1_variant() == 1) {
-        const size_t smem = 16 + k1_in_bytes(R, L) + (size_t)R * nk * 4;
-        static size_t configured = 0;  // per instantiation
-        if (smem > configured) {
-            PG_CUDA(cudaFuncSetAttribute(sketch_fill_uniform_kernel<K, R>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
-        sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, d_out, L, nk);
-        PG_LAUNCH_CHECK("sketch_fill_uniform_kernel");
-        return PG_OK;
+    const size_t smem = 16 + k1_in_bytes(R, L) + (size_t)R * nk * 4;
+    static size_t configured = 0;  // per instantiation (one process = one device)
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(sketch_fill_uniform_kernel<K, R>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
     }
-    if (K == 21) {  // tuning variants are only instantiated for the headline k
-        switch (k1_fm()) {
-            case 1: return launch_k1v2<K == 21 ? K : 21, R, 1>(d_bases, n_tiles, L, nk, d_out, st);
-            case 2: return launch_k1v2<K == 21 ? K : 21, R, 2>(d_bases, n_tiles, L, nk, d_out, st);
-            case 3: return launch_k1v2<K == 21 ? K : 21, R, 3>(d_bases, n_tiles, L, nk, d_out, st);
-            default: break;
-        }
-    }
-    return launch_k1v2<K, R, 0>(d_bases, n_tiles, L, nk, d_out, st);
+    sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, d_out, L, nk, 4u);
+    PG_LAUNCH_CHECK("sketch_fill_uniform_kernel");
+    return PG_OK;
 }
 
 template <int R>
@@ -433,14 +278,17 @@ static int dispatch_k1(int k, const uint8_t *d_bases, uint64_t n_tiles, uint32_t
     switch (k) {
 #define PG_K1_CASE(KK) \
     case KK: return launch_k1<KK, R>(d_bases, n_tiles, L, nk, d_out, st);
-        PG_K1_CASE(15) PG_K1_CASE(16) PG_K1_CASE(17) PG_K1_CASE(19) PG_K1_CASE(21) PG_K1_CASE(23)
-        PG_K1_CASE(25) PG_K1_CASE(27) PG_K1_CASE(31) PG_K1_CASE(32)
+        PG_K1_CASE(11) PG_K1_CASE(13) PG_K1_CASE(15) PG_K1_CASE(16) PG_K1_CASE(17) PG_K1_CASE(19)
+        PG_K1_CASE(21) PG_K1_CASE(23) PG_K1_CASE(24) PG_K1_CASE(25) PG_K1_CASE(27) PG_K1_CASE(29)
+        PG_K1_CASE(31) PG_K1_CASE(32)
 #undef PG_K1_CASE
     default: *handled = false; return PG_OK;
     }
 }
 
-constexpr int K1_R = 32;  // reads per tile == threads per CTA
+// reads per tile == threads per CTA.  32 (one warp per CTA, ~10 CTAs per SM at L=150, k=21)
+// measured fastest: 64 loses ~9 % (profiles/r01_k1_tuning.md).
+constexpr int K1_R = 32;
 
 static int launch_fill_generic(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t ulen,
                                uint64_t n_reads, uint64_t first_read, int k, int s, uint32_t flags,
@@ -476,15 +324,8 @@ int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, 
         uint64_t t0 = 0;
         while (t0 < tiles) {  // grid.x limit
             const uint64_t nt = std::min<uint64_t>(tiles - t0, 0x7fffffffull);
-            int rc;
-            if (k == 21 && k1_r() == 64 && nt % 2 == 0 && smem * 2 <= 200 * 1024) {
-                handled = true;
-                rc = launch_k1<21, 64>(d_bases + t0 * K1_R * (uint64_t)L, nt / 2, L, nk,
-                                       d_out + t0 * K1_R * (uint64_t)nk, st);
-            } else {
-                rc = dispatch_k1<K1_R>(k, d_bases + t0 * K1_R * (uint64_t)L, nt, L, nk,
+            int rc = dispatch_k1<K1_R>(k, d_bases + t0 * K1_R * (uint64_t)L, nt, L, nk,
                                        d_out + t0 * K1_R * (uint64_t)nk, st, &handled);
-            }
             if (rc != PG_OK) return rc;
             if (!handled) break;
             t0 += nt;

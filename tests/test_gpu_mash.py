@@ -71,7 +71,7 @@ def test_cfg1_bit_exact_and_checksums(gpu, oracle):
     assert int(got.astype(np.uint64).sum()) == int(c["sum"], 16)
 
 
-@pytest.mark.parametrize("k", [15, 16, 17, 19, 21, 23, 25, 27, 31, 32])
+@pytest.mark.parametrize("k", [11, 13, 15, 16, 17, 19, 21, 23, 24, 25, 27, 29, 31, 32])
 @pytest.mark.parametrize("L", [64, 150, 151, 100])
 def test_uniform_fast_path_all_instantiated_k(gpu, oracle, k, L):
     n, s = 32 * 9 + 5, 4096  # tiles + a ragged remainder that takes the generic kernel
