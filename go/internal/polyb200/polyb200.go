@@ -1,0 +1,119 @@
+// Package polyb200 is the cgo binding of libpolyb200.so (include/poly_b200.h): the thin
+// shim the mash / align / primers drop-in packages call.  NOT COMPILED IN THIS REPOSITORY'S
+// CI: the build image has no Go toolchain (DESIGN.md); the same C ABI is exercised by the
+// C++ and Python host mirrors.  Build with:
+//
+//	CGO_CFLAGS="-I${POLYB200}/include" CGO_LDFLAGS="-L${POLYB200}/poly_b200/lib -lpolyb200" go build ./...
+package polyb200
+
+/*
+#include <stdlib.h>
+#include "poly_b200.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"unsafe"
+)
+
+// ErrPanic is returned where the pure-Go reference would panic (index out of range).
+var ErrPanic = errors.New("poly: reference panics on this input (index out of range)")
+
+func check(rc C.int) error {
+	switch rc {
+	case C.PG_OK:
+		return nil
+	case C.PG_ERR_PANIC:
+		return ErrPanic
+	default:
+		return fmt.Errorf("libpolyb200 error %d: %s", int(rc), C.GoString(C.pg_last_error()))
+	}
+}
+
+// Flatten copies []string into the bytes+offsets layout of the C ABI.  The copy is what
+// makes the call legal under the cgo pointer rules (no Go pointer to Go pointers crosses;
+// nothing is retained by C after return).
+func Flatten(seqs []string) ([]byte, []uint64) {
+	total := 0
+	for _, s := range seqs {
+		total += len(s)
+	}
+	bases := make([]byte, 0, total+1)
+	offsets := make([]uint64, len(seqs)+1)
+	for i, s := range seqs {
+		bases = append(bases, s...)
+		offsets[i+1] = uint64(len(bases))
+	}
+	if len(bases) == 0 {
+		bases = bases[:1] // keep &bases[0] valid
+	}
+	return bases, offsets
+}
+
+// SketchBatch wraps pg_mash_sketch_batch: compact rows of rowStride words, count[i] informative words.
+func SketchBatch(bases []byte, offsets []uint64, k, s int, rowStride int) (out []uint32, count []uint32, status []int32, err error) {
+	n := len(offsets) - 1
+	out = make([]uint32, n*rowStride+1)
+	count = make([]uint32, n+1)
+	status = make([]int32, n+1)
+	rc := C.pg_mash_sketch_batch((*C.uint8_t)(unsafe.Pointer(&bases[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n),
+		C.int32_t(k), C.int32_t(s), 0, (*C.uint32_t)(unsafe.Pointer(&out[0])), C.uint64_t(rowStride),
+		(*C.uint32_t)(unsafe.Pointer(&count[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
+	return out, count, status, check(rc)
+}
+
+// SimilarityPairs wraps pg_mash_similarity_pairs.
+func SimilarityPairs(sketches []uint32, skOffsets []uint64, pairA, pairB []uint32) (same []int64, sim, dist []float64, err error) {
+	np := len(pairA)
+	same, sim, dist = make([]int64, np+1), make([]float64, np+1), make([]float64, np+1)
+	status := make([]int32, np+1)
+	if len(sketches) == 0 {
+		sketches = make([]uint32, 1)
+	}
+	rc := C.pg_mash_similarity_pairs((*C.uint32_t)(unsafe.Pointer(&sketches[0])), (*C.uint64_t)(unsafe.Pointer(&skOffsets[0])),
+		C.uint64_t(len(skOffsets)-1), (*C.uint32_t)(unsafe.Pointer(&pairA[0])), (*C.uint32_t)(unsafe.Pointer(&pairB[0])), C.uint64_t(np),
+		(*C.int64_t)(unsafe.Pointer(&same[0])), (*C.double)(unsafe.Pointer(&sim[0])), (*C.double)(unsafe.Pointer(&dist[0])),
+		(*C.int32_t)(unsafe.Pointer(&status[0])))
+	return same[:np], sim[:np], dist[:np], check(rc)
+}
+
+// DistanceBlock wraps pg_mash_distance_block (rows [rowBegin,rowEnd) x all n columns).
+func DistanceBlock(sketches []uint32, n, s int, rowBegin, rowEnd int) (same []uint32, dist []float64, err error) {
+	rows := rowEnd - rowBegin
+	same, dist = make([]uint32, rows*n+1), make([]float64, rows*n+1)
+	rc := C.pg_mash_distance_block((*C.uint32_t)(unsafe.Pointer(&sketches[0])), C.uint64_t(n), C.int32_t(s), C.uint64_t(rowBegin),
+		C.uint64_t(rowEnd), (*C.uint32_t)(unsafe.Pointer(&same[0])), (*C.double)(unsafe.Pointer(&dist[0])))
+	return same[:rows*n], dist[:rows*n], check(rc)
+}
+
+// SWScoreBatch wraps pg_sw_score_batch.
+func SWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
+	nA, nB int, gap int64) (score []int64, errCode []int32, errPos []int64, err error) {
+	n := len(qOffsets) - 1
+	score, errCode, errPos = make([]int64, n+1), make([]int32, n+1), make([]int64, n+1)
+	t := []byte(template)
+	if len(t) == 0 {
+		t = make([]byte, 1)
+	}
+	qa := C.int32_t(0)
+	if queryIsA {
+		qa = 1
+	}
+	rc := C.pg_sw_score_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
+		(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
+		(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
+		(*C.int64_t)(unsafe.Pointer(&score[0])), (*C.int32_t)(unsafe.Pointer(&errCode[0])), (*C.int64_t)(unsafe.Pointer(&errPos[0])))
+	return score[:n], errCode[:n], errPos[:n], check(rc)
+}
+
+// TmBatch wraps pg_tm_batch.
+func TmBatch(bases []byte, offsets []uint64, cp, na, mg float64) (tm, dH, dS []float64, status []int32, err error) {
+	n := len(offsets) - 1
+	tm, dH, dS, status = make([]float64, n+1), make([]float64, n+1), make([]float64, n+1), make([]int32, n+1)
+	rc := C.pg_tm_batch((*C.uint8_t)(unsafe.Pointer(&bases[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n),
+		C.double(cp), C.double(na), C.double(mg), (*C.double)(unsafe.Pointer(&tm[0])), (*C.double)(unsafe.Pointer(&dH[0])),
+		(*C.double)(unsafe.Pointer(&dS[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
+	return tm[:n], dH[:n], dS[:n], status[:n], check(rc)
+}

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Timings of the non-headline kernels on their BASELINE configs (device-resident, CUDA events):
+cfg3 (100k x 10 kbp, k=31, s=2000: K2 sketch + K3 all-pairs on a row block) and cfg5
+(1M x 25 bp primers vs a 10 kb template: K4 SW score, K5 Tm).  Prints one JSON line per kernel;
+copy into profiles/.  Not the driver's bench (that is bench.py)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from poly_b200 import _lib, align, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--reads", type=int, default=100_000)
+ap.add_argument("--rows", type=int, default=512, help="row block of the all-pairs matrix to time")
+ap.add_argument("--primers", type=int, default=1_000_000)
+ap.add_argument("--iters", type=int, default=3)
+args = ap.parse_args()
+
+L = _lib.lib()
+_lib.check(L.pg_init(0))
+dev = torch.device("cuda", 0)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def timed(fn, iters=args.iters, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+# ---- cfg3: K2 + K3 ---------------------------------------------------------------------
+n, RL, k, s = args.reads, 10_000, 31, 2000
+d_reads = torch.empty(n * RL, dtype=torch.uint8, device=dev)
+_lib.check(L.pg_synth_reads_dev(d_reads.data_ptr(), 0, n, RL, synth.SEED_READS, 1, 100, st))
+d_sk = torch.empty((n, s), dtype=torch.int32, device=dev)
+ms = timed(lambda: _lib.check(L.pg_mash_sketch_uniform_dev(d_reads.data_ptr(), n, RL, k, s, 0, d_sk.data_ptr(), s, None, st)))
+alg = n * (RL + 4 * s)
+print(json.dumps({"kernel": "K2 sketch_select (cfg3)", "reads": n, "read_len": RL, "k": k, "s": s, "ms": ms,
+                  "gbases_per_s": n * RL / ms / 1e6, "algorithmic_GBps": alg / ms / 1e6, "kernel_name": L.pg_last_kernel().decode()}))
+rows = min(args.rows, n)
+d_same = torch.empty((rows, n), dtype=torch.int32, device=dev)
+ms = timed(lambda: _lib.check(L.pg_mash_distance_block_dev(d_sk.data_ptr(), n, s, 0, rows, d_same.data_ptr(), None, st)), iters=1, warm=1)
+pairs = rows * n
+same = d_same.cpu().numpy()
+print(json.dumps({"kernel": "K3 distance_block (cfg3 row block)", "rows": rows, "cols": n, "pairs": pairs, "ms": ms,
+                  "gpairs_per_s": pairs / ms / 1e6, "full_allpairs_estimate_s": (n * (n - 1) / 2) / (pairs / ms * 1e3),
+                  "diag_ok": bool((np.diag(same[:, :rows]) == s).all()), "row0_family_mean": float(same[0, 1:100].mean()),
+                  "row0_other_max": int(same[0, 100:].max()), "kernel_name": L.pg_last_kernel().decode()}))
+del d_same, d_sk, d_reads
+
+# ---- cfg5: K4 + K5 ---------------------------------------------------------------------
+m, PL, TL = args.primers, 25, 10_000
+pr = torch.from_numpy(synth.primers(m)).to(dev)
+off = torch.arange(m + 1, dtype=torch.int64, device=dev) * PL
+tpl = torch.from_numpy(synth.template(TL)).to(dev)
+alpha = align.NewAlphabet(["-", "A", "C", "G", "T"])
+mat = np.array([[0, 0, 0, 0, 0], [0, 3, -3, -3, -3], [0, -3, 3, -3, -3], [0, -3, -3, 3, -3], [0, -3, -3, -3, 3]], dtype=np.int64)
+lut = alpha.byte_lut()
+score = torch.empty(m, dtype=torch.int64, device=dev)
+ec = torch.empty(m, dtype=torch.int32, device=dev)
+ep = torch.empty(m, dtype=torch.int64, device=dev)
+ms = timed(lambda: _lib.check(L.pg_sw_score_batch_dev(pr.data_ptr(), off.data_ptr(), m, PL, tpl.data_ptr(), TL, 1, lut.ctypes.data, lut.ctypes.data,
+                                                     mat.ctypes.data, 5, 5, -2, score.data_ptr(), ec.data_ptr(), ep.data_ptr(), st)), iters=2)
+cells = m * PL * TL
+print(json.dumps({"kernel": "K4 sw_score (cfg5)", "queries": m, "qlen": PL, "tlen": TL, "ms": ms, "gcups": cells / ms / 1e6,
+                  "first6": score[:6].cpu().tolist(), "kernel_name": L.pg_last_kernel().decode()}))
+tm = torch.empty(m, dtype=torch.float64, device=dev)
+ms = timed(lambda: _lib.check(L.pg_tm_batch_dev(pr.data_ptr(), off.data_ptr(), m, 500e-9, 50e-3, 0.0, tm.data_ptr(), None, None, None, st)), iters=10)
+print(json.dumps({"kernel": "K5 tm (cfg5)", "primers": m, "ms": ms, "mprimers_per_s": m / ms / 1e3, "first3": tm[:3].cpu().tolist()}))
