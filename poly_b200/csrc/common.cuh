@@ -47,6 +47,9 @@ int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_
                             cudaStream_t st);
 int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin,
                           uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st);
+// distance_join.cu (ascending sketches only; *done == false -> caller falls back to the pairwise kernel)
+int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin, uint64_t row_end,
+                         uint32_t *d_same, double *d_dist, cudaStream_t st, bool *done);
 // sw_score.cu
 int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen,
                     const uint8_t *d_t, uint64_t tlen, int query_is_a, const int16_t *lut_a,

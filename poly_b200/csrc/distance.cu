@@ -10,6 +10,7 @@
 //                           owns a TILE x TILE block of pairs with both sketch tiles
 //                           staged in shared memory.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -158,7 +159,7 @@ distance_block_kernel(const uint32_t *__restrict__ sk, uint64_t n, uint32_t s, u
 }
 
 __global__ void sorted_flag_kernel(const uint32_t *__restrict__ sk, uint64_t n, uint32_t s,
-                                   uint8_t *__restrict__ flag) {
+                                   uint8_t *__restrict__ flag, uint32_t *__restrict__ n_unsorted) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
@@ -166,7 +167,10 @@ __global__ void sorted_flag_kernel(const uint32_t *__restrict__ sk, uint64_t n, 
         bool ok = true;
         for (uint32_t i = lane + 1; i < s; i += 32) ok &= __ldg(x + i - 1) <= __ldg(x + i);
         ok = __all_sync(0xffffffffu, ok);
-        if (lane == 0) flag[r] = ok ? 1 : 0;
+        if (lane == 0) {
+            flag[r] = ok ? 1 : 0;
+            if (!ok) atomicAdd(n_unsorted, 1u);
+        }
     }
 }
 
@@ -197,9 +201,25 @@ int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_
         return PG_ERR_UNSUPPORTED;
     }
     uint8_t *d_flag = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_flag, n, st));
-    sorted_flag_kernel<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 4096), 256, 0, st>>>(d_sk, n, s, d_flag);
+    PG_CUDA(cudaMallocAsync(&d_flag, n + 8, st));
+    uint32_t *d_unsorted = reinterpret_cast<uint32_t *>(d_flag + ((n + 3) & ~3ull));
+    PG_CUDA(cudaMemsetAsync(d_unsorted, 0, 4, st));
+    sorted_flag_kernel<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 4096), 256, 0, st>>>(d_sk, n, s, d_flag, d_unsorted);
     PG_LAUNCH_CHECK("sorted_flag_kernel");
+    // every sketch ascending (the select regime, L-k >= s): inverted-index join, output-sensitive
+    if (d_same) {
+        uint32_t n_unsorted = 1;
+        PG_CUDA(cudaMemcpyAsync(&n_unsorted, d_unsorted, 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        if (n_unsorted == 0 && !getenv("PG_K3_PAIRWISE")) {
+            bool done = false;
+            int rc = launch_distance_join(d_sk, n, s, row_begin, row_end, d_same, d_dist, st, &done);
+            if (rc != PG_OK || done) {
+                cudaFreeAsync(d_flag, st);
+                return rc;
+            }
+        }
+    }
     static size_t configured = 0;
     if (smem > configured) {
         PG_CUDA(cudaFuncSetAttribute(distance_block_kernel,

@@ -1,0 +1,226 @@
+// distance_join.cu -- K3 fast path: all-pairs matching counts over ASCENDING sketches as an
+// inverted-index join instead of N^2 pairwise merges.
+//
+// For two ascending sketches the reference's walk (/root/reference/search/mash/mash.go:121-132)
+// counts sum over values v of min(cnt_A(v), cnt_B(v)), and its early-out
+// (mash.go:117-119) only fires when that sum is 0 anyway.  So
+//     same[i][j] = sum over values v present in both i and j of min(c_i(v), c_j(v))
+// and the whole matrix is the sum over values of the outer product of that value's posting
+// list.  Work is N*s + (number of matching pairs), not N^2*s:
+//   1. histogram of value buckets over all N*s (value, sketch id) entries
+//   2. exclusive scan of the bucket counts
+//   3. scatter of the entries into their buckets
+//   4. one CTA per bucket: sort the bucket's entries by (value, id) in shared memory, collapse
+//      duplicates into (id, count), and for every run of one value add min(count_a, count_b)
+//      to same[a][b] for all a in the row block, b in the run (global atomics).
+// Buckets are value ranges scaled to the largest value present, sized for ~2k entries.  If the
+// data is so skewed that a bucket cannot fit shared memory even with the finest bucketing, the
+// caller falls back to the pairwise kernel (distance.cu).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int JOIN_CAP = 8192;      // entries a bucket CTA can hold (64 KB of keys)
+constexpr int JOIN_THREADS = 256;
+
+__device__ __forceinline__ uint32_t bucket_of(uint32_t v, uint64_t scale /* = B * 2^32 / (vmax+1) */) {
+    return (uint32_t)(((uint64_t)v * scale) >> 32);
+}
+
+__global__ void max_value_kernel(const uint32_t *__restrict__ sk, uint64_t n, uint32_t s,
+                                 uint32_t *__restrict__ vmax) {
+    // ascending rows: the maximum of a row is its last element
+    uint32_t m = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, __ldg(sk + r * s + (s - 1)));
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0) atomicMax(vmax, m);
+}
+
+__global__ void hist_kernel(const uint32_t *__restrict__ sk, uint64_t total, const uint32_t *__restrict__ vmax,
+                            uint32_t nbuckets, uint32_t *__restrict__ hist) {
+    const uint64_t scale = (((uint64_t)nbuckets) << 32) / ((uint64_t)(*vmax) + 1);
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = min(bucket_of(__ldg(sk + e), scale), nbuckets - 1);
+        // consecutive elements of an ascending row mostly share a bucket: aggregate per warp
+        const uint32_t peers = __match_any_sync(__activemask(), b);
+        if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[b], __popc(peers));
+    }
+}
+
+// single-CTA exclusive scan (nbuckets <= 2^22); also reports the largest bucket
+__global__ void scan_kernel(const uint32_t *__restrict__ hist, uint32_t nbuckets, uint64_t *__restrict__ start,
+                            uint32_t *__restrict__ largest) {
+    __shared__ uint64_t s_part[1024];
+    __shared__ uint32_t s_max[1024];
+    const uint32_t tid = threadIdx.x, per = (nbuckets + 1023) / 1024;
+    const uint32_t lo = min(tid * per, nbuckets), hi = min(lo + per, nbuckets);
+    uint64_t sum = 0;
+    uint32_t mx = 0;
+    for (uint32_t i = lo; i < hi; ++i) { sum += hist[i]; mx = max(mx, hist[i]); }
+    s_part[tid] = sum;
+    s_max[tid] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t run = 0;
+        uint32_t m = 0;
+        for (int i = 0; i < 1024; ++i) { const uint64_t t = s_part[i]; s_part[i] = run; run += t; m = max(m, s_max[i]); }
+        *largest = m;
+        start[nbuckets] = run;
+    }
+    __syncthreads();
+    uint64_t run = s_part[tid];
+    for (uint32_t i = lo; i < hi; ++i) { start[i] = run; run += hist[i]; }
+}
+
+__global__ void scatter_kernel(const uint32_t *__restrict__ sk, uint64_t total, uint32_t s,
+                               const uint32_t *__restrict__ vmax, uint32_t nbuckets,
+                               const uint64_t *__restrict__ start, uint32_t *__restrict__ cursor,
+                               uint64_t *__restrict__ entries) {
+    const uint64_t scale = (((uint64_t)nbuckets) << 32) / ((uint64_t)(*vmax) + 1);
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(sk + e);
+        const uint32_t id = (uint32_t)(e / s);
+        const uint32_t b = min(bucket_of(v, scale), nbuckets - 1);
+        const uint32_t peers = __match_any_sync(__activemask(), b);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&cursor[b], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+        entries[start[b] + base + rank] = ((uint64_t)v << 32) | id;
+    }
+}
+
+__global__ void __launch_bounds__(JOIN_THREADS)
+bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restrict__ start, uint32_t nbuckets,
+                   uint64_t n, uint64_t row_begin, uint64_t row_end, uint32_t *__restrict__ same) {
+    extern __shared__ __align__(16) uint64_t key[];  // [JOIN_CAP]
+    __shared__ uint32_t s_cnt;
+    for (uint32_t b = blockIdx.x; b < nbuckets; b += gridDim.x) {
+        const uint64_t lo = start[b];
+        const uint32_t m = (uint32_t)(start[b + 1] - lo);
+        if (m == 0) continue;
+        uint32_t P = 1;
+        while (P < m) P <<= 1;
+        for (uint32_t i = threadIdx.x; i < P; i += JOIN_THREADS) key[i] = i < m ? entries[lo + i] : ~0ull;
+        __syncthreads();
+        for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
+            for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = threadIdx.x; t < (P >> 1); t += JOIN_THREADS) {
+                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+                    const bool up = (i & k2) == 0;
+                    const uint64_t a = key[i], c = key[ixj];
+                    if ((a > c) == up) { key[i] = c; key[ixj] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        // entry i heads a (value, id) group if it differs from its predecessor; its multiplicity is
+        // the group length.  Each group head a adds min(c_a, c_b) to same[a][b] for every group b of
+        // the same value (including itself: the diagonal gets c_a).
+        for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) {
+            const uint64_t ka = key[i];
+            if (i > 0 && key[i - 1] == ka) continue;
+            const uint32_t ida = (uint32_t)ka, va = (uint32_t)(ka >> 32);
+            if (ida < row_begin || ida >= row_end) continue;
+            uint32_t ca = 1;
+            while (i + ca < m && key[i + ca] == ka) ++ca;
+            // walk left to the start of the value run, then right over the whole run
+            uint32_t j = i;
+            while (j > 0 && (uint32_t)(key[j - 1] >> 32) == va) --j;
+            uint32_t *row = same + (ida - row_begin) * n;
+            while (j < m && (uint32_t)(key[j] >> 32) == va) {
+                const uint64_t kb = key[j];
+                uint32_t cb = 1;
+                while (j + cb < m && key[j + cb] == kb) ++cb;
+                atomicAdd(row + (uint32_t)kb, min(ca, cb));
+                j += cb;
+            }
+        }
+        __syncthreads();
+    }
+    (void)s_cnt;
+}
+
+__global__ void same_to_distance_kernel(const uint32_t *__restrict__ same, uint64_t count, uint32_t s,
+                                        double *__restrict__ dist) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        dist[i] = 1 - (double)same[i] / (double)s;  // mash.go:134,139
+}
+
+}  // namespace
+
+// Returns PG_OK and sets *done = true if the join ran; *done = false means "not applicable"
+// (skewed data) and the caller must use the pairwise kernel.  All sketches must be ascending.
+int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin, uint64_t row_end,
+                         uint32_t *d_same, double *d_dist, cudaStream_t st, bool *done) {
+    *done = false;
+    const uint64_t total = n * (uint64_t)s;
+    const uint64_t rows = row_end - row_begin;
+    if (total == 0 || n > 0xffffffffull) return PG_OK;
+    uint32_t *d_scalars = nullptr;  // [0] vmax, [1] largest bucket
+    PG_CUDA(cudaMallocAsync(&d_scalars, 8, st));
+    PG_CUDA(cudaMemsetAsync(d_scalars, 0, 8, st));
+    const unsigned sms = (unsigned)sm_count();
+    max_value_kernel<<<sms * 4, 256, 0, st>>>(d_sk, n, (uint32_t)s, d_scalars);
+    note_launch("max_value_kernel");
+
+    uint64_t nb = 1;
+    while (nb * 2048 < total) nb <<= 1;
+    nb = std::min<uint64_t>(std::max<uint64_t>(nb, 1), 1u << 22);
+    uint32_t *d_hist = nullptr, *d_cursor = nullptr;
+    uint64_t *d_start = nullptr, *d_entries = nullptr;
+    int rc = PG_OK;
+    for (int attempt = 0; attempt < 3 && !*done; ++attempt) {
+        PG_CUDA(cudaMallocAsync(&d_hist, nb * 4, st));
+        PG_CUDA(cudaMallocAsync(&d_cursor, nb * 4, st));
+        PG_CUDA(cudaMallocAsync(&d_start, (nb + 1) * 8, st));
+        PG_CUDA(cudaMemsetAsync(d_hist, 0, nb * 4, st));
+        PG_CUDA(cudaMemsetAsync(d_cursor, 0, nb * 4, st));
+        hist_kernel<<<sms * 16, 256, 0, st>>>(d_sk, total, d_scalars, (uint32_t)nb, d_hist);
+        note_launch("hist_kernel");
+        scan_kernel<<<1, 1024, 0, st>>>(d_hist, (uint32_t)nb, d_start, d_scalars + 1);
+        note_launch("scan_kernel");
+        uint32_t largest = 0;
+        PG_CUDA(cudaMemcpyAsync(&largest, d_scalars + 1, 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        if (largest <= JOIN_CAP) {
+            PG_CUDA(cudaMallocAsync(&d_entries, total * 8, st));
+            scatter_kernel<<<sms * 16, 256, 0, st>>>(d_sk, total, (uint32_t)s, d_scalars, (uint32_t)nb, d_start, d_cursor, d_entries);
+            note_launch("scatter_kernel");
+            PG_CUDA(cudaMemsetAsync(d_same, 0, rows * n * 4, st));
+            static bool configured = false;
+            if (!configured) {
+                PG_CUDA(cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JOIN_CAP * 8));
+                configured = true;
+            }
+            bucket_join_kernel<<<(unsigned)std::min<uint64_t>(nb, (uint64_t)sms * 12), JOIN_THREADS, JOIN_CAP * 8, st>>>(
+                d_entries, d_start, (uint32_t)nb, n, row_begin, row_end, d_same);
+            note_launch("bucket_join_kernel");
+            if (d_dist) {
+                same_to_distance_kernel<<<sms * 8, 256, 0, st>>>(d_same, rows * n, (uint32_t)s, d_dist);
+                note_launch("same_to_distance_kernel");
+            }
+            cudaFreeAsync(d_entries, st);
+            *done = true;
+        }
+        cudaFreeAsync(d_hist, st);
+        cudaFreeAsync(d_cursor, st);
+        cudaFreeAsync(d_start, st);
+        if (!*done) {
+            if (nb >= (1u << 22)) break;
+            nb = std::min<uint64_t>(nb * 8, 1u << 22);
+        }
+    }
+    cudaFreeAsync(d_scalars, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = cuda_fail(e, "distance join", __FILE__, __LINE__);
+    return rc;
+}
+
+}  // namespace pg

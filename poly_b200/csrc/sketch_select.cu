@@ -9,7 +9,12 @@
 //            the current admission limit are appended to the candidate buffer
 //   prune    when the buffer would overflow: exact radix-select of the s-th smallest
 //            value, keep all smaller values plus the needed number of ties
-//   final    prune to exactly s, bitonic sort in shared memory, coalesced store.
+//   final    bucket sort-select: histogram of the candidates over 2048 value buckets, scan,
+//            scatter of the buckets below the one holding the s-th smallest value, rank inside
+//            each (tiny) bucket -> the sorted bottom-s directly (O(candidates), exact for
+//            ties).  Degenerate value distributions (a bucket that does not fit the scratch
+//            area, e.g. a homopolymer read) take the general path: exact radix select to s,
+//            bitonic sort in shared memory.
 // Nothing but the read bytes and the s output words touches HBM.
 #include <algorithm>
 
@@ -24,14 +29,17 @@ constexpr int SEL_THREADS = 512;
 constexpr int SEL_CHUNK = 2048;     // k-mer positions per chunk
 constexpr int SEL_MAX_S = 16384;    // largest sketch size in the select regime
 constexpr int SEL_LOOKAHEAD = 1024; // max k supported by the staged path (bytes beyond chunk)
+constexpr int SEL_NBK = 2048;       // value buckets of the final sort-select (v >> 21)
+constexpr int SEL_BSHIFT = 21;
 
 struct SelSmem {
     uint32_t *cand;   // [cap]
     uint32_t *keep;   // [s]
     uint32_t *kv;     // [SEL_CHUNK + SEL_LOOKAHEAD]
     uint32_t *bytes;  // [(SEL_CHUNK + SEL_LOOKAHEAD + 8)/4] staged read bytes (word view)
-    uint32_t *hist;   // [256]
-    uint32_t *misc;   // [8]: 0 cnt, 1 prefix, 2 want, 3 kept_lt, 4 kept_eq, 5 hmin_later
+    uint32_t *hist;   // [SEL_NBK + 1] (radix select uses the first 256 words)
+    uint32_t *misc;   // [8]: 0 cnt, 1 prefix, 2 want, 3 kept_lt, 4 kept_eq, 5 hmin_later, 6 bt, 7 need
+    uint32_t tmpcap;  // words available at keep[] for the final scatter (keep+kv+bytes are contiguous)
 };
 
 __device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_t p) {
@@ -130,6 +138,71 @@ __device__ void bitonic_sort(uint32_t *x, uint32_t P) {
     }
 }
 
+// Final stage, fast path.  cand[0..cnt) holds a superset of the bottom-s multiset (cnt >= s).
+// Writes the ascending bottom-s to dst and returns true, or returns false (nothing written) if
+// the buckets up to the threshold bucket do not fit the scratch area.  All threads must call.
+__device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, uint32_t *__restrict__ dst) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t *bstart = m.hist;  // counts, then exclusive starts; [SEL_NBK] = total
+    uint32_t *tmp = m.keep;
+    for (uint32_t i = tid; i <= SEL_NBK; i += SEL_THREADS) bstart[i] = 0;
+    if (tid == 0) { m.misc[6] = 0xffffffffu; m.misc[7] = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += SEL_THREADS) atomicAdd(&bstart[m.cand[i] >> SEL_BSHIFT], 1u);
+    __syncthreads();
+    // exclusive scan: 4 buckets per thread, warp scan, then the 16 warp totals
+    constexpr int PER = SEL_NBK / SEL_THREADS;
+    uint32_t c[PER], sum = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { c[j] = bstart[tid * PER + j]; sum += c[j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)(tid & 31u) >= d) incl += y;
+    }
+    __shared__ uint32_t s_warp[SEL_THREADS / 32];
+    if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t w = 0; w < (tid >> 5); ++w) base += s_warp[w];
+    uint32_t run = base + incl - sum;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        bstart[tid * PER + j] = run;
+        if (run < s && run + c[j] >= s) { m.misc[6] = tid * PER + j; m.misc[7] = run + c[j]; }  // threshold bucket
+        run += c[j];
+    }
+    if (tid == SEL_THREADS - 1) bstart[SEL_NBK] = run;
+    __syncthreads();
+    const uint32_t bt = m.misc[6], need = m.misc[7];
+    if (bt == 0xffffffffu || need > m.tmpcap) return false;
+    // scatter buckets <= bt (slot order inside a bucket is arbitrary); the per-bucket cursors
+    // sit right behind the scattered elements in the scratch area
+    uint32_t *cursor = tmp + need;  // [bt + 1]
+    if (need + bt + 1 > m.tmpcap) return false;
+    for (uint32_t i = tid; i <= bt; i += SEL_THREADS) cursor[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += SEL_THREADS) {
+        const uint32_t e = m.cand[i], b = e >> SEL_BSHIFT;
+        if (b <= bt) tmp[bstart[b] + atomicAdd(&cursor[b], 1u)] = e;
+    }
+    __syncthreads();
+    // rank inside the bucket -> final position (ties keep distinct slots via the index tie-break)
+    for (uint32_t p = tid; p < need; p += SEL_THREADS) {
+        const uint32_t e = tmp[p], b = e >> SEL_BSHIFT;
+        const uint32_t lo = bstart[b], hi = bstart[b + 1];
+        uint32_t r = 0;
+        for (uint32_t q = lo; q < hi; ++q) {
+            const uint32_t x = tmp[q];
+            r += (x < e) || (x == e && q < p);
+        }
+        if (lo + r < s) dst[lo + r] = e;
+    }
+    __syncthreads();
+    return true;
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
                      uint32_t uniform_len, uint64_t n_reads, uint32_t k, uint32_t s, uint32_t P,
@@ -142,7 +215,8 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
     m.kv = m.keep + (s ? s : 1);
     m.bytes = m.kv + SEL_CHUNK + SEL_LOOKAHEAD;
     m.hist = m.bytes + (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1;
-    m.misc = m.hist + 256;
+    m.misc = m.hist + SEL_NBK + 1;
+    m.tmpcap = (uint32_t)(m.hist - m.keep);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t nb = k >> 2, tail = k & 3u;
@@ -219,11 +293,13 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
 
         uint32_t cnt = m.misc[0];
         __syncthreads();
-        if (cnt > s) prune_to_s(m, cnt, s);
-        for (uint32_t i = s + tid; i < P; i += SEL_THREADS) m.cand[i] = 0xffffffffu;
-        __syncthreads();
-        bitonic_sort(m.cand, P);
-        for (uint32_t i = tid; i < s; i += SEL_THREADS) dst[i] = m.cand[i];
+        if (!final_bucket_sort(m, cnt, s, dst)) {
+            if (cnt > s) prune_to_s(m, cnt, s);
+            for (uint32_t i = s + tid; i < P; i += SEL_THREADS) m.cand[i] = 0xffffffffu;
+            __syncthreads();
+            bitonic_sort(m.cand, P);
+            for (uint32_t i = tid; i < s; i += SEL_THREADS) dst[i] = m.cand[i];
+        }
         if (tid == 0) {
             int32_t st = PG_ITEM_OK;
             // s == 1: mash.go:96-98 indexes Sketches[-1] as soon as a later hash is
@@ -254,9 +330,9 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     uint32_t P = 1;
     while (P < (uint32_t)std::max(s, 1)) P <<= 1;
     if (P < 2) P = 2;
-    uint32_t cap = std::max<uint32_t>(P, (uint32_t)s + 5 * SEL_CHUNK);
+    uint32_t cap = std::max<uint32_t>(P, (uint32_t)s + 4 * SEL_CHUNK);
     const size_t words = (size_t)cap + (s ? s : 1) + (SEL_CHUNK + SEL_LOOKAHEAD) +
-                         (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1 + 256 + 8;
+                         (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1 + (SEL_NBK + 1) + 8;
     const size_t smem = words * 4;
     static size_t configured = 0;
     if (smem > configured) {

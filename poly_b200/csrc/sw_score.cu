@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstring>
 #include <limits>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -45,22 +46,38 @@ struct SwParams {
     int n_q, n_t;  // alphabet sizes on the query / template side
 };
 
-// lut_q/lut_t: 256-entry int16 byte->index (device), tab: n_q x n_t (row = query symbol)
-template <typename T, int MAXQ>
+// Short queries (<= ROWS cells): one thread per query, DP column in registers, no branches in
+// the cell loop.  Rows at or beyond the query length read a score of -BIG, so (for gap <= 0)
+// they can never exceed a valid cell and need no masking; a positive "gap" takes the MASK
+// variant.  PROFILE: the per-thread query profile prof[t][i] = S(q_i, t) is expanded into
+// shared memory ([n_t][ROWS][threads], conflict-free, immediate offsets) so a cell is
+// 1 LDS + 3 add-max + 1 max; otherwise (large alphabets) the score comes from the shared
+// table through a per-row offset.
+template <typename T>
+struct SwBig {
+    static constexpr T value = (T)1 << (sizeof(T) * 8 - 3);  // 2^29 / 2^61: no overflow in diag + sc
+};
+
+template <typename T, int ROWS, bool PROFILE, bool MASK>
 __global__ void __launch_bounds__(SW_THREADS)
 sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__restrict__ lut_t,
                 const T *__restrict__ tab, T gap, int64_t *__restrict__ score,
                 int32_t *__restrict__ err, int64_t *__restrict__ errpos) {
     extern __shared__ __align__(16) uint8_t sm[];
-    T *s_tab = reinterpret_cast<T *>(sm);                       // [n_q * n_t]
-    int16_t *s_lut_t = reinterpret_cast<int16_t *>(s_tab + p.n_q * p.n_t);  // [256]
-    uint8_t *s_tidx = reinterpret_cast<uint8_t *>(s_lut_t + 256);           // [SW_TCHUNK]
+    // layout: [s_tidx: SW_TCHUNK bytes][s_lut_t: 256 int16][s_tab: (n_q+1)*n_t T][prof: n_t*ROWS*threads T]
+    uint8_t *s_tidx = sm;
+    int16_t *s_lut_t = reinterpret_cast<int16_t *>(sm + SW_TCHUNK);
+    T *s_tab = reinterpret_cast<T *>(sm + SW_TCHUNK + 512);
+    T *s_prof = s_tab + (p.n_q + 1) * p.n_t;
     __shared__ unsigned long long s_first_bad_t;
 
     const uint32_t tid = threadIdx.x;
+    const T NEG = (T)0 - SwBig<T>::value;
     for (int i = tid; i < p.n_q * p.n_t; i += SW_THREADS) s_tab[i] = tab[i];
+    for (int i = tid; i < p.n_t; i += SW_THREADS) s_tab[p.n_q * p.n_t + i] = NEG;  // row n_q: "beyond the query"
     for (int i = tid; i < 256; i += SW_THREADS) s_lut_t[i] = lut_t[i];
     if (tid == 0) s_first_bad_t = ~0ull;
+    __syncthreads();
 
     const uint64_t qi = (uint64_t)blockIdx.x * SW_THREADS + tid;
     const bool active = qi < p.nq;
@@ -70,25 +87,31 @@ sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__
         qbeg = p.qoff[qi];
         qlen = (uint32_t)(p.qoff[qi + 1] - qbeg);
     }
-    // per-cell row offsets into the table (symbol index * n_t); invalid symbols score 0
-    // through row 0 and are reported at the end
-    int qrow[MAXQ];
+    // per-row table offsets; invalid symbols score through row 0 and are reported at the end
+    int qrow[ROWS];
     int64_t first_bad_q = -1;
 #pragma unroll
-    for (int i = 0; i < MAXQ; ++i) {
-        qrow[i] = 0;
+    for (int i = 0; i < ROWS; ++i) {
+        qrow[i] = p.n_q * p.n_t;
         if (i < (int)qlen) {
             const int ix = lut_q[__ldg(p.q + qbeg + i)];
             if (ix < 0) {
                 if (first_bad_q < 0) first_bad_q = i;
+                qrow[i] = 0;
             } else {
                 qrow[i] = ix * p.n_t;
             }
         }
     }
-    T col[MAXQ];
+    if (PROFILE) {
+        for (int t = 0; t < p.n_t; ++t) {
 #pragma unroll
-    for (int i = 0; i < MAXQ; ++i) col[i] = 0;
+            for (int i = 0; i < ROWS; ++i) s_prof[(t * ROWS + i) * SW_THREADS + tid] = s_tab[qrow[i] + t];
+        }
+    }
+    T col[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) col[i] = 0;
     T best = 0;
 
     for (uint64_t t0 = 0; t0 < p.tlen; t0 += SW_TCHUNK) {
@@ -103,20 +126,20 @@ sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__
         if (active && qlen > 0) {
             for (uint32_t j = 0; j < tc; ++j) {
                 const int tj = s_tidx[j];
+                const T *pcol = s_prof + (size_t)tj * ROWS * SW_THREADS + tid;
                 T diag = 0, up = 0;
 #pragma unroll
-                for (int i = 0; i < MAXQ; ++i) {
-                    if (i < (int)qlen) {
-                        const T old = col[i];                 // H[i][j-1]
-                        const T sc = s_tab[qrow[i] + tj];     // align.go:188
-                        T v = addmax<T>(diag, sc, (T)0);      // align.go:192,195
-                        v = addmax<T>(old, gap, v);           // left / up by orientation
-                        v = addmax<T>(up, gap, v);
-                        best = v > best ? v : best;           // align.go:197-201
-                        diag = old;
-                        up = v;
-                        col[i] = v;
-                    }
+                for (int i = 0; i < ROWS; ++i) {
+                    const T old = col[i];                                    // H[i][j-1]
+                    const T sc = PROFILE ? pcol[i * SW_THREADS] : s_tab[qrow[i] + tj];  // align.go:188
+                    T v = addmax<T>(diag, sc, (T)0);                         // align.go:192,195
+                    v = addmax<T>(old, gap, v);                              // left / up by orientation
+                    v = addmax<T>(up, gap, v);
+                    if (MASK) { if (i < (int)qlen) best = v > best ? v : best; }
+                    else best = v > best ? v : best;                         // align.go:197-201
+                    diag = old;
+                    up = v;
+                    col[i] = v;
                 }
             }
         }
@@ -209,19 +232,48 @@ int run_sw(const SwParams &p, uint64_t max_qlen, const int16_t *h_lut_q, const i
     const int16_t *d_lut_t = d_lut_q + 256;
     const T *d_tab = reinterpret_cast<const T *>(d_blob + 1024);
 
-    const size_t smem = ntab * sizeof(T) + 512 + SW_TCHUNK;
+    const size_t base_smem = SW_TCHUNK + 512 + (ntab + p.n_t) * sizeof(T);
     const unsigned blocks = (unsigned)((p.nq + SW_THREADS - 1) / SW_THREADS);
     int rc = PG_OK;
-    if (max_qlen <= 32 && smem <= 200 * 1024) {
-        cudaFuncSetAttribute(sw_score_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sw_score_kernel<T, 32><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap,
-                                                                 d_score, d_err, d_errpos);
-        note_launch("sw_score_kernel<32>");
-    } else if (max_qlen <= 64 && smem <= 200 * 1024) {
-        cudaFuncSetAttribute(sw_score_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sw_score_kernel<T, 64><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap,
-                                                                 d_score, d_err, d_errpos);
-        note_launch("sw_score_kernel<64>");
+    const bool mask = gap > 0;
+    bool launched = false;
+    // smallest instantiated row count that covers the longest query
+    auto try_rows = [&](auto rows_tag) -> bool {
+        constexpr int ROWS = decltype(rows_tag)::value;
+        if (launched || max_qlen > (uint64_t)ROWS) return false;
+        const size_t prof = (size_t)p.n_t * ROWS * SW_THREADS * sizeof(T);
+        const bool profile = base_smem + prof <= 100 * 1024;
+        const size_t smem = base_smem + (profile ? prof : 0);
+        if (smem > 200 * 1024) return false;
+#define PG_SW_LAUNCH(PROF, MSK)                                                                          \
+        do {                                                                                                 \
+            cudaFuncSetAttribute(sw_score_kernel<T, ROWS, PROF, MSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            sw_score_kernel<T, ROWS, PROF, MSK><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap, d_score, d_err, d_errpos); \
+        } while (0)
+        if (profile && !mask) PG_SW_LAUNCH(true, false);
+        else if (profile && mask) PG_SW_LAUNCH(true, true);
+        else if (!profile && !mask) PG_SW_LAUNCH(false, false);
+        else PG_SW_LAUNCH(false, true);
+#undef PG_SW_LAUNCH
+        note_launch("sw_score_kernel");
+        launched = true;
+        return true;
+    };
+    if (sizeof(T) == 4) {
+        try_rows(std::integral_constant<int, 8>{});
+        try_rows(std::integral_constant<int, 16>{});
+        try_rows(std::integral_constant<int, 20>{});
+        try_rows(std::integral_constant<int, 24>{});
+        try_rows(std::integral_constant<int, 28>{});
+        try_rows(std::integral_constant<int, 32>{});
+        try_rows(std::integral_constant<int, 40>{});
+        try_rows(std::integral_constant<int, 48>{});
+        try_rows(std::integral_constant<int, 64>{});
+    } else {
+        try_rows(std::integral_constant<int, 32>{});
+        try_rows(std::integral_constant<int, 64>{});
+    }
+    if (launched) {
     } else {
         // batches bounded by a 1 GiB scratch column store
         uint64_t per = std::max<uint64_t>(1, (1ull << 30) / (std::max<uint64_t>(max_qlen, 1) * sizeof(T)));

@@ -255,3 +255,64 @@ def test_full_size_properties_cfg2_slice(gpu, oracle):
     a = mash.sketch_uniform(np.ascontiguousarray(one[:L]), 1, L, k, s)[0]
     b = mash.sketch_uniform(np.ascontiguousarray(one[1:]), 1, L, k, s)[0]
     assert np.array_equal(a[1:], b[:-1])
+
+
+def _oracle_same_matrix(oracle, sk, rows):
+    n, s = sk.shape
+    out = np.zeros((len(rows), n), np.uint32)
+    for a, i in enumerate(rows):
+        oi = oracle.OracleMash(0, s); oi.Sketches[:] = sk[i]
+        for j in range(n):
+            oj = oracle.OracleMash(0, s); oj.Sketches[:] = sk[j]
+            out[a, j] = oi.SimilarityCount(oj)[0]
+    return out
+
+
+def test_distance_join_multiset_and_skew(gpu, oracle, monkeypatch):
+    """All-ascending inputs take the inverted-index join (distance_join.cu): duplicates inside a
+    sketch (multiset min-count), identical sketches, values piled into one bucket, row blocks;
+    and the pairwise kernel (PG_K3_PAIRWISE=1) must agree with it."""
+    rng = np.random.default_rng(21)
+    cases = []
+    # (a) low-complexity reads: many repeated k-mers -> duplicate hashes inside each sketch
+    seqs = [bytes(rng.choice(list(b"AC"), size=600).astype(np.uint8)) for _ in range(20)] + [b"A" * 600, b"AC" * 300]
+    bases, off = mash.flatten(seqs)
+    out, cnt, st = mash.sketch_arrays(bases, off, 6, 128)
+    assert (cnt == 128).all()
+    cases.append(out)
+    # (b) hand-made ascending multisets over a tiny value range (heavy ties, one hot bucket)
+    cases.append(np.sort(rng.integers(0, 9, (40, 33)), axis=1).astype(np.uint32))
+    # (c) identical sketches + values at both ends of the 32-bit range
+    x = np.sort(rng.integers(0, 2 ** 32, (1, 64), dtype=np.uint64), axis=1).astype(np.uint32)
+    y = np.concatenate([np.repeat(x, 30, 0), np.sort(rng.integers(0, 2 ** 32, (10, 64), dtype=np.uint64), axis=1).astype(np.uint32)])
+    y[5, 0] = 0; y[6, -1] = 0xFFFFFFFF
+    cases.append(np.sort(y, axis=1))
+    for sk in cases:
+        n = len(sk)
+        want = _oracle_same_matrix(oracle, sk, range(n))
+        same, dist = mash.distance_block(sk)
+        assert np.array_equal(same, want)
+        assert np.array_equal(dist, 1 - want / float(sk.shape[1]))
+        s2, _ = mash.distance_block(sk, 3, n - 2)
+        assert np.array_equal(s2, want[3:n - 2])
+    monkeypatch.setenv("PG_K3_PAIRWISE", "1")
+    for sk in cases:
+        same, _ = mash.distance_block(sk)
+        assert np.array_equal(same, _oracle_same_matrix(oracle, sk, range(len(sk))))
+
+
+def test_distance_join_larger_family_set(gpu, oracle):
+    """2k sketches of the cfg3 family shape at reduced size: spot-check rows against the oracle and
+    check the structural properties of the full matrix (symmetry, diagonal, family blocks)."""
+    n, L, k, s, fam = 2000, 2500, 31, 256, 20
+    reads = synth.family_reads(n, L, family=fam)
+    sk = mash.sketch_uniform(reads, n, L, k, s)
+    same, _ = mash.distance_block(sk, want_distance=False)
+    assert (np.diag(same) == s).all() and (same == same.T).all()
+    rows = [0, 1, 19, 20, 777, 1999]
+    assert np.array_equal(same[rows], _oracle_same_matrix(oracle, sk, rows))
+    blocks = same.reshape(n // fam, fam, n // fam, fam)
+    off_family = blocks.copy()
+    for f in range(n // fam):
+        off_family[f, :, f, :] = 0
+    assert off_family.max() <= 2 and blocks[3, :, 3, :].min() > 20
