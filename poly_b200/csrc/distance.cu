@@ -119,6 +119,22 @@ distance_block_kernel(const uint32_t *__restrict__ sk, uint64_t n, uint32_t s, u
     const uint64_t c0 = (uint64_t)blockIdx.x * BT;
     const uint32_t nr = (uint32_t)min((uint64_t)BT, row_end - r0);
     const uint32_t nc = (uint32_t)min((uint64_t)BT, n - c0);
+    // mash.go:117-119 needs only the first and last word of each sketch: if every pair of the
+    // tile early-outs (always the case for zero-padded fill-regime sketches) skip the staging
+    {
+        bool work = false;
+        if (threadIdx.x < nr * nc) {
+            const uint32_t ri = threadIdx.x / nc, ci = threadIdx.x % nc;
+            const uint32_t *L = sk + (r0 + ri) * s, *S = sk + (c0 + ci) * s;
+            work = !(__ldg(L + s - 1) < __ldg(S) || __ldg(S + s - 1) < __ldg(L));
+            if (!work) {
+                const uint64_t o = (r0 + ri - row_begin) * n + (c0 + ci);
+                if (same_out) same_out[o] = 0;
+                if (dist_out) dist_out[o] = 1 - (double)0 / (double)s;
+            }
+        }
+        if (!__syncthreads_or(work)) return;
+    }
     for (uint32_t i = threadIdx.x; i < nr * s; i += blockDim.x) srow[i] = __ldg(sk + r0 * s + i);
     for (uint32_t i = threadIdx.x; i < nc * s; i += blockDim.x) scol[i] = __ldg(sk + c0 * s + i);
     __syncthreads();

@@ -26,5 +26,5 @@ def gpu():
     """The CUDA library bound to device 0; fails (does not skip) if it cannot run."""
     from poly_b200 import _lib
 
-    _lib.check(_lib.lib().pg_init(0))
+    _lib.check(_lib.lib().pg_init(int(os.environ.get("LOCAL_RANK", "0"))))  # one process per GPU under torchrun
     return _lib
