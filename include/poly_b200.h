@@ -95,6 +95,23 @@ int pg_mash_sketch_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, 
 int pg_mash_sketch_uniform_dev(const uint8_t *d_bases, uint64_t n_reads, uint32_t read_len,
                                int32_t k, int32_t s, uint32_t flags, uint32_t *d_out,
                                uint64_t row_stride, int32_t *d_status, void *stream);
+/* Fused sketch + all-gather over NVLink peer memory (one process per GPU).  Every rank owns a
+ * "gathered" buffer of world*n_local rows; gathered_ptrs[p] is that buffer on rank p as seen from
+ * THIS process (own pointer for p == rank, pg_ipc_import()ed peer mappings otherwise).  The
+ * sketch kernel stores each finished tile / row straight into all of them at row offset
+ * rank*n_local (TMA bulk stores to peer addresses in the fill regime), so the transfer overlaps
+ * the hashing tile by tile and no separate collective pass runs.  Rows are compact
+ * (row stride = min(max(read_len-k,0), s) words).  The caller must synchronise the stream and
+ * barrier across ranks before reading its gathered buffer.  n_local must be the same on all
+ * ranks; world <= 8. */
+#define PG_MAX_PEERS 8
+#define PG_IPC_HANDLE_BYTES 64
+int pg_ipc_export(void *dptr, uint8_t handle[PG_IPC_HANDLE_BYTES]);
+int pg_ipc_import(const uint8_t handle[PG_IPC_HANDLE_BYTES], void **dptr);
+int pg_ipc_close(void *dptr);
+int pg_mash_sketch_uniform_gather_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len,
+                                      int32_t k, int32_t s, void *const *gathered_ptrs,
+                                      int32_t world, int32_t rank, void *stream);
 /* Name of the kernel the last uniform call on this thread dispatched to and how many
  * kernels it launched (bench.py's gpu_launches evidence). */
 const char *pg_last_kernel(void);

@@ -263,6 +263,49 @@ int pg_mash_sketch_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, 
                                 row_stride, d_count, d_status, (cudaStream_t)stream);
 }
 
+int pg_ipc_export(void *dptr, uint8_t handle[PG_IPC_HANDLE_BYTES]) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == PG_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    PG_CUDA(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle, &h, sizeof h);
+    return PG_OK;
+}
+int pg_ipc_import(const uint8_t handle[PG_IPC_HANDLE_BYTES], void **dptr) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    PG_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PG_OK;
+}
+int pg_ipc_close(void *dptr) {
+    if (dptr) PG_CUDA(cudaIpcCloseMemHandle(dptr));
+    return PG_OK;
+}
+
+int pg_mash_sketch_uniform_gather_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len,
+                                      int32_t k, int32_t s, void *const *gathered_ptrs,
+                                      int32_t world, int32_t rank, void *stream) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if ((rc = check_ks(k, s)) != PG_OK) return rc;
+    if (world < 1 || world > PG_MAX_PEERS || rank < 0 || rank >= world || !gathered_ptrs) {
+        set_error("bad world/rank (%d/%d)", world, rank);
+        return PG_ERR_ARG;
+    }
+    const uint64_t cnt = std::min<uint64_t>(kmers_of(read_len, k), (uint64_t)s);
+    SketchDst dst;
+    dst.n = world;
+    for (int p = 0; p < world; ++p) {
+        if (!gathered_ptrs[p]) { set_error("null gathered pointer for rank %d", p); return PG_ERR_ARG; }
+        dst.ptr[p] = (uint32_t *)gathered_ptrs[p] + (uint64_t)rank * n_local * cnt;  // this rank's row block
+    }
+    return launch_sketch_uniform(d_bases, n_local, read_len, k, s, 0, dst.ptr[rank], cnt, nullptr,
+                                 (cudaStream_t)stream, &dst);
+}
+
 // Pipelined host path shared by the uniform and ragged entry points: chunks of reads
 // cycle through 3 stream/buffer slots (H2D, kernel, D2H overlap across slots).
 static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t ulen, uint64_t n_reads,

@@ -28,18 +28,25 @@ void note_launch(const char *kernel_name);
 
 int sm_count();
 
+// destinations of a sketch row block: the local buffer, or the gathered buffers of all ranks
+struct SketchDst {
+    uint32_t *ptr[PG_MAX_PEERS];
+    int n;
+};
+
 // ---- kernel launchers (one per .cu) -------------------------------------------
 // sketch_fill.cu
 int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t read_len, int k, int s,
                           uint32_t flags, uint32_t *d_out, uint64_t row_stride, int32_t *d_status,
-                          cudaStream_t st);
+                          cudaStream_t st, const SketchDst *extra = nullptr);
 int launch_sketch_ragged(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                          uint64_t max_read_len, int k, int s, uint32_t flags, uint32_t *d_out,
                          uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st);
 // sketch_select.cu  (reads with n >= s; uniform: read_len != 0 and d_offsets == nullptr)
 int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len,
                          uint64_t n_reads, int k, int s, uint32_t flags, uint32_t *d_out,
-                         uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st);
+                         uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st,
+                         const SketchDst *extra = nullptr);
 // distance.cu
 int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_t n_sk,
                             const uint32_t *d_a, const uint32_t *d_b, uint64_t n_pairs,

@@ -136,7 +136,7 @@ __device__ __align__(16) const KmixTable g_kmix_byte = make_kmix_table();
 // stays an IMAD (FMA pipe) instead of being strength-reduced to LEA (ALU pipe).
 template <int K, int R>
 __global__ void __launch_bounds__(R)
-sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, uint32_t *__restrict__ out,
+sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, const SketchDst dst,
                            uint32_t L, uint32_t nk, uint32_t lut_stride) {
     constexpr int NB = K / 4;    // 4-byte body blocks per k-mer
     constexpr int TAIL = K % 4;  // tail bytes per k-mer
@@ -210,7 +210,10 @@ sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, uint32_t *__restri
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        bulk_s2g(out + tile * (uint64_t)(R * nk), s_out, R * nk * 4u);  // multiple of 16 (R % 4 == 0)
+        // one bulk store per destination: the local buffer, or (fused all-gather) the gathered
+        // buffer of every rank, peers reached through their NVLink-mapped addresses
+        for (int p = 0; p < dst.n; ++p)
+            bulk_s2g(dst.ptr[p] + tile * (uint64_t)(R * nk), s_out, R * nk * 4u);  // multiple of 16 (R % 4 == 0)
         bulk_wait_read0();
     }
 }
@@ -258,7 +261,7 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
 // ---- launchers -------------------------------------------------------------------
 template <int K, int R>
 static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
-                     uint32_t *d_out, cudaStream_t st) {
+                     const SketchDst &dst, cudaStream_t st) {
     const size_t smem = 16 + k1_in_bytes(R, L) + (size_t)R * nk * 4;
     static size_t configured = 0;  // per instantiation (one process = one device)
     if (smem > configured) {
@@ -266,18 +269,18 @@ static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint3
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, d_out, L, nk, 4u);
+    sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, dst, L, nk, 4u);
     PG_LAUNCH_CHECK("sketch_fill_uniform_kernel");
     return PG_OK;
 }
 
 template <int R>
 static int dispatch_k1(int k, const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
-                       uint32_t *d_out, cudaStream_t st, bool *handled) {
+                       const SketchDst &dst, cudaStream_t st, bool *handled) {
     *handled = true;
     switch (k) {
 #define PG_K1_CASE(KK) \
-    case KK: return launch_k1<KK, R>(d_bases, n_tiles, L, nk, d_out, st);
+    case KK: return launch_k1<KK, R>(d_bases, n_tiles, L, nk, dst, st);
         PG_K1_CASE(11) PG_K1_CASE(13) PG_K1_CASE(15) PG_K1_CASE(16) PG_K1_CASE(17) PG_K1_CASE(19)
         PG_K1_CASE(21) PG_K1_CASE(23) PG_K1_CASE(24) PG_K1_CASE(25) PG_K1_CASE(27) PG_K1_CASE(29)
         PG_K1_CASE(31) PG_K1_CASE(32)
@@ -305,17 +308,19 @@ static int launch_fill_generic(const uint8_t *d_bases, const uint64_t *d_offsets
 
 int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, int k, int s,
                           uint32_t flags, uint32_t *d_out, uint64_t row_stride, int32_t *d_status,
-                          cudaStream_t st) {
+                          cudaStream_t st, const SketchDst *extra) {
     if (n_reads == 0) return PG_OK;
     const uint64_t n = L > (uint32_t)k ? L - (uint32_t)k : 0;
     if (n >= (uint64_t)s && !(n == 0 && s == 0))  // select regime, mash.go:87-102
         return launch_sketch_select(d_bases, nullptr, L, n_reads, k, s, flags, d_out, row_stride,
-                                    nullptr, d_status, st);
+                                    nullptr, d_status, st, extra);
     // fill regime
     const uint32_t nk = (uint32_t)n;
     uint64_t done = 0;
     const bool compact = row_stride == nk && !(flags & PG_SKETCH_PAD_ZERO);
-    const bool aligned = ((uintptr_t)d_bases % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
+    bool aligned = ((uintptr_t)d_bases % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
+    if (extra)
+        for (int p = 0; p < extra->n; ++p) aligned = aligned && ((uintptr_t)extra->ptr[p] % 16 == 0);
     const size_t smem = 16 + k1_in_bytes(K1_R, L) + (size_t)K1_R * nk * 4;
     if (compact && aligned && nk > 0 && (K1_R * (uint64_t)L) % 16 == 0 && smem <= 200 * 1024 &&
         n_reads >= K1_R) {
@@ -324,8 +329,11 @@ int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, 
         uint64_t t0 = 0;
         while (t0 < tiles) {  // grid.x limit
             const uint64_t nt = std::min<uint64_t>(tiles - t0, 0x7fffffffull);
-            int rc = dispatch_k1<K1_R>(k, d_bases + t0 * K1_R * (uint64_t)L, nt, L, nk,
-                                       d_out + t0 * K1_R * (uint64_t)nk, st, &handled);
+            SketchDst dst;
+            dst.n = extra ? extra->n : 1;
+            for (int p = 0; p < dst.n; ++p)
+                dst.ptr[p] = (extra ? extra->ptr[p] : d_out) + t0 * K1_R * (uint64_t)nk;
+            int rc = dispatch_k1<K1_R>(k, d_bases + t0 * K1_R * (uint64_t)L, nt, L, nk, dst, st, &handled);
             if (rc != PG_OK) return rc;
             if (!handled) break;
             t0 += nt;
@@ -335,9 +343,14 @@ int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, 
             if (d_status) PG_CUDA(cudaMemsetAsync(d_status, 0, done * sizeof(int32_t), st));
         }
     }
-    if (done < n_reads)
+    if (done < n_reads) {
+        if (extra) {
+            set_error("fused sketch+gather needs the TMA fast path (k instantiated, n_local %% 32 == 0, 16-byte aligned buffers)");
+            return PG_ERR_UNSUPPORTED;
+        }
         return launch_fill_generic(d_bases, nullptr, L, n_reads - done, done, k, s, flags, d_out,
                                    row_stride, nullptr, d_status, st);
+    }
     return PG_OK;
 }
 

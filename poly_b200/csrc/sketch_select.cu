@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(SEL_THREADS)
 sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
                      uint32_t uniform_len, uint64_t n_reads, uint32_t k, uint32_t s, uint32_t P,
                      uint32_t cap, uint32_t flags, uint32_t *__restrict__ out, uint64_t row_stride,
-                     uint32_t *__restrict__ count, int32_t *__restrict__ status) {
+                     uint32_t *__restrict__ count, int32_t *__restrict__ status, const SketchDst extra) {
     extern __shared__ __align__(16) uint32_t smem_w[];
     SelSmem m;
     m.cand = smem_w;
@@ -300,6 +300,15 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
             bitonic_sort(m.cand, P);
             for (uint32_t i = tid; i < s; i += SEL_THREADS) dst[i] = m.cand[i];
         }
+        // fused all-gather: replicate the finished row into the gathered buffer of every rank
+        if (extra.n > 0) {
+            __syncthreads();
+            for (int pr = 0; pr < extra.n; ++pr) {
+                uint32_t *peer = extra.ptr[pr] + row * row_stride;
+                if (peer == dst) continue;
+                for (uint32_t i = tid; i < s; i += SEL_THREADS) peer[i] = dst[i];
+            }
+        }
         if (tid == 0) {
             int32_t st = PG_ITEM_OK;
             // s == 1: mash.go:96-98 indexes Sketches[-1] as soon as a later hash is
@@ -317,8 +326,11 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
 int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len,
                          uint64_t n_reads, int k, int s, uint32_t flags, uint32_t *d_out,
                          uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
-                         cudaStream_t st) {
+                         cudaStream_t st, const SketchDst *extra) {
     if (n_reads == 0) return PG_OK;
+    SketchDst ex;
+    ex.n = 0;
+    if (extra) ex = *extra;
     if (s > SEL_MAX_S) {
         set_error("sketch size %d > %d is not supported when L-k >= s (select regime)", s, SEL_MAX_S);
         return PG_ERR_UNSUPPORTED;
@@ -343,7 +355,7 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 4);
     sketch_select_kernel<<<(unsigned)blocks, SEL_THREADS, smem, st>>>(
         d_bases, d_offsets, read_len, n_reads, (uint32_t)k, (uint32_t)s, P, cap, flags, d_out,
-        row_stride, d_count, d_status);
+        row_stride, d_count, d_status, ex);
     PG_LAUNCH_CHECK("sketch_select_kernel");
     return PG_OK;
 }

@@ -7,8 +7,8 @@ rank r computes row block r of the pair matrix against the gathered set (receive
 
 The communication pattern is independent of who computes: `sharded_sketch_distance` takes
 the two compute callables, and defaults to the CUDA entry points of libpolyb200.so.  (The
-CPU-tier test drives the same function over gloo with the oracle injected as the compute,
-to check the partition / gather / row-block bookkeeping without a GPU.)
+CPU-tier test drives the same function over gloo with a CPU stand-in injected by the test
+itself, to check the partition / gather / row-block bookkeeping without a GPU.)
 """
 from __future__ import annotations
 
@@ -110,3 +110,71 @@ def sharded_sketch_distance(local_reads: torch.Tensor, plan: ShardPlan, read_len
         gathered = full
     same = distance_fn(gathered, plan.lo, plan.hi)
     return local, gathered, same
+
+
+# ---- fused sketch + all-gather over NVLink peer memory ------------------------------------
+class GatheredBuffer:
+    """A cudaMalloc'ed [world*n_local, cnt] uint32 buffer on this rank, exported to / mapped from
+    every peer process through CUDA IPC handles exchanged over torch.distributed."""
+
+    def __init__(self, n_local: int, cnt: int, plan: ShardPlan, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._lib, self.plan, self.n_local, self.cnt = _lib, plan, n_local, cnt
+        L = _lib.lib()
+        self.nbytes = plan.world * n_local * max(cnt, 1) * 4
+        p = C.c_void_p()
+        _lib.check(L.pg_dev_alloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        handle = (C.c_uint8 * 64)()
+        _lib.check(L.pg_ipc_export(self.ptr, handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        allh = torch.empty((plan.world, 64), dtype=torch.uint8, device=mine.device)
+        if plan.world > 1:
+            dist.all_gather_into_tensor(allh, mine, group=group)
+        else:
+            allh[0] = mine
+        allh = allh.cpu().numpy()
+        self.peer_ptrs = []
+        for r in range(plan.world):
+            if r == plan.rank:
+                self.peer_ptrs.append(self.ptr)
+            else:
+                q = C.c_void_p()
+                h = (C.c_uint8 * 64)(*allh[r].tolist())
+                _lib.check(L.pg_ipc_import(h, C.byref(q)))
+                self.peer_ptrs.append(q.value)
+        self._arr = (C.c_void_p * plan.world)(*self.peer_ptrs)
+
+    def to_numpy(self) -> np.ndarray:
+        out = np.empty((self.plan.world * self.n_local, max(self.cnt, 1)), dtype=np.uint32)
+        self._lib.check(self._lib.lib().pg_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, None))
+        self._lib.check(self._lib.lib().pg_stream_sync(None))
+        return out[:, : self.cnt]
+
+    def close(self, group=None):
+        L = self._lib.lib()
+        torch.cuda.synchronize()
+        if self.plan.world > 1:
+            dist.barrier(group=group)  # nobody may still be storing into a buffer that is about to go
+        for r, q in enumerate(self.peer_ptrs):
+            if r != self.plan.rank:
+                L.pg_ipc_close(q)
+        L.pg_dev_free(self.ptr)
+
+
+def fused_sketch_gather(d_bases: torch.Tensor, n_local: int, read_len: int, k: int, s: int, gathered: GatheredBuffer, group=None):
+    """ONE kernel sketches the local reads and stores every finished tile into the gathered
+    buffer of every rank (TMA bulk stores to peer-mapped addresses): the all-gather overlaps
+    the hashing tile by tile.  Returns after a stream sync + barrier, i.e. when this rank's
+    gathered buffer is complete."""
+    from . import _lib
+
+    plan = gathered.plan
+    _lib.check(_lib.lib().pg_mash_sketch_uniform_gather_dev(d_bases.data_ptr(), n_local, read_len, k, s, gathered._arr, plan.world, plan.rank,
+                                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    if plan.world > 1:
+        dist.barrier(group=group)
