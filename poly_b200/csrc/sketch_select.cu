@@ -4,6 +4,8 @@
 // replace-max + re-sort; duplicates are kept).
 //
 // One CTA per read.  The read is streamed through shared memory in chunks:
+//   stage    the chunk's bytes arrive by a 1-D TMA bulk copy (16-byte aligned body; the few
+//            unaligned tail bytes by plain loads), double-buffered one chunk ahead
 //   phase 1  pre-mix K(p) of every position of the chunk, once       (shared via smem)
 //   phase 2  one k-mer per thread: body chain over K(i+4j), tail, fmix; hashes below
 //            the current admission limit are appended to the candidate buffer
@@ -20,6 +22,7 @@
 
 #include "common.cuh"
 #include "murmur3.cuh"
+#include "tma.cuh"
 
 namespace pg {
 
@@ -31,12 +34,13 @@ constexpr int SEL_MAX_S = 16384;    // largest sketch size in the select regime
 constexpr int SEL_LOOKAHEAD = 1024; // max k supported by the staged path (bytes beyond chunk)
 constexpr int SEL_NBK = 2048;       // value buckets of the final sort-select (v >> 21)
 constexpr int SEL_BSHIFT = 21;
+constexpr int SEL_STAGE_WORDS = (SEL_CHUNK + SEL_LOOKAHEAD + 16 + 16) / 4;  // 15 B head + 8 B slack, 16-B multiple
 
 struct SelSmem {
     uint32_t *cand;   // [cap]
     uint32_t *keep;   // [s]
     uint32_t *kv;     // [SEL_CHUNK + SEL_LOOKAHEAD]
-    uint32_t *bytes;  // [(SEL_CHUNK + SEL_LOOKAHEAD + 8)/4] staged read bytes (word view)
+    uint32_t *bytes;  // 2 x [SEL_STAGE_WORDS] staged read bytes (word view), double-buffered
     uint32_t *hist;   // [SEL_NBK + 1] (radix select uses the first 256 words)
     uint32_t *misc;   // [8]: 0 cnt, 1 prefix, 2 want, 3 kept_lt, 4 kept_eq, 5 hmin_later, 6 bt, 7 need
     uint32_t tmpcap;  // words available at keep[] for the final scatter (keep+kv+bytes are contiguous)
@@ -214,11 +218,19 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
     m.keep = m.cand + cap;
     m.kv = m.keep + (s ? s : 1);
     m.bytes = m.kv + SEL_CHUNK + SEL_LOOKAHEAD;
-    m.hist = m.bytes + (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1;
+    m.hist = m.bytes + 2 * SEL_STAGE_WORDS;
     m.misc = m.hist + SEL_NBK + 1;
     m.tmpcap = (uint32_t)(m.hist - m.keep);
 
+    __shared__ __align__(8) uint64_t s_bar[2];
+    uint32_t par0 = 0u, par1 = 0u;  // barrier parities (uniform across the CTA)
     const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
     const uint32_t nb = k >> 2, tail = k & 3u;
     const uint32_t tailmask = tail == 1 ? 0xffu : tail == 2 ? 0xffffu : 0xffffffu;
 
@@ -248,13 +260,37 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
         uint64_t limit = 1ull << 32;  // admit h < limit
         uint32_t h_first = 0;
 
-        for (uint64_t c0 = 0; c0 < n; c0 += SEL_CHUNK) {
+        // chunk c lives in stage buffer c & 1; its copy is issued one iteration ahead
+        auto issue_stage = [&](uint64_t c0, uint32_t buf) {
+            // bytes [c0, c0 + ch + k) of the read -> sb[head ..): 16-byte aligned body by TMA,
+            // the (< 16) trailing bytes and 8 bytes of zero slack by plain stores
             const uint32_t ch = (uint32_t)min((uint64_t)SEL_CHUNK, n - c0);
-            // stage bytes [c0, c0 + ch + k) (+ zero slack for the window over-read)
             const uint32_t nbytes = ch + k;
-            uint8_t *sb = reinterpret_cast<uint8_t *>(m.bytes);
-            for (uint32_t i = tid; i < nbytes + 8; i += SEL_THREADS)
-                sb[i] = i < nbytes ? __ldg(seq + c0 + i) : (uint8_t)0;
+            const uint8_t *src = seq + c0;
+            const uint32_t head = (uint32_t)((uintptr_t)src & 15u);
+            const uint32_t body = (head + nbytes) & ~15u;
+            uint8_t *sb = reinterpret_cast<uint8_t *>(m.bytes + buf * SEL_STAGE_WORDS);
+            if (tid == 0) {
+                if (body) {
+                    mbar_expect_tx(&s_bar[buf], body);
+                    bulk_g2s(sb, src - head, body, &s_bar[buf]);
+                } else {
+                    mbar_expect_tx(&s_bar[buf], 0);
+                }
+            }
+            for (uint32_t i = body + tid; i < head + nbytes + 8; i += SEL_THREADS)
+                sb[i] = i < head + nbytes ? __ldg(src - head + i) : (uint8_t)0;
+        };
+        issue_stage(0, 0);
+        uint32_t chunk_idx = 0;
+        for (uint64_t c0 = 0; c0 < n; c0 += SEL_CHUNK, ++chunk_idx) {
+            const uint32_t ch = (uint32_t)min((uint64_t)SEL_CHUNK, n - c0);
+            const uint32_t buf = chunk_idx & 1u;
+            if (c0 + SEL_CHUNK < n) issue_stage(c0 + SEL_CHUNK, buf ^ 1u);  // previous user of that buffer finished last iteration
+            const uint32_t head = (uint32_t)((uintptr_t)(seq + c0) & 15u);
+            const uint32_t *stage = m.bytes + buf * SEL_STAGE_WORDS;
+            if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1u; }
+            else          { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
             // make room: candidates after this chunk must fit
             uint32_t cnt = m.misc[0];
             __syncthreads();
@@ -265,7 +301,7 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
             }
             // phase 1: block pre-mix of every position that some k-mer of the chunk uses
             const uint32_t npos = nb ? ch + 4 * (nb - 1) : 0;
-            for (uint32_t p = tid; p < npos; p += SEL_THREADS) m.kv[p] = mm3_kmix(smem_window(m.bytes, p));
+            for (uint32_t p = tid; p < npos; p += SEL_THREADS) m.kv[p] = mm3_kmix(smem_window(stage, head + p));
             __syncthreads();
             // phase 2: one k-mer per thread
             for (uint32_t i0 = 0; i0 < ch; i0 += SEL_THREADS) {
@@ -274,7 +310,7 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
                 uint32_t h = 0;
                 if (i < ch) {
                     for (uint32_t j = 0; j < nb; ++j) h = mm3_round(h, m.kv[i + 4 * j]);
-                    if (tail) h ^= mm3_kmix(smem_window(m.bytes, i + 4 * nb) & tailmask);
+                    if (tail) h ^= mm3_kmix(smem_window(stage, head + i + 4 * nb) & tailmask);
                     h ^= k;
                     h = mm3_fmix(h);
                     take = (uint64_t)h < limit;
@@ -344,7 +380,7 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     if (P < 2) P = 2;
     uint32_t cap = std::max<uint32_t>(P, (uint32_t)s + 4 * SEL_CHUNK);
     const size_t words = (size_t)cap + (s ? s : 1) + (SEL_CHUNK + SEL_LOOKAHEAD) +
-                         (SEL_CHUNK + SEL_LOOKAHEAD + 8) / 4 + 1 + (SEL_NBK + 1) + 8;
+                         2 * SEL_STAGE_WORDS + (SEL_NBK + 1) + 8;
     const size_t smem = words * 4;
     static size_t configured = 0;
     if (smem > configured) {
