@@ -216,7 +216,7 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
     SelSmem m;
     m.cand = smem_w;
     m.keep = m.cand + cap;
-    m.kv = m.keep + (s ? s : 1);
+    m.kv = m.keep + ((s + 3u) & ~3u) + 4u;  // 16-byte granules keep the TMA stage buffers aligned
     m.bytes = m.kv + SEL_CHUNK + SEL_LOOKAHEAD;
     m.hist = m.bytes + 2 * SEL_STAGE_WORDS;
     m.misc = m.hist + SEL_NBK + 1;
@@ -378,8 +378,8 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     uint32_t P = 1;
     while (P < (uint32_t)std::max(s, 1)) P <<= 1;
     if (P < 2) P = 2;
-    uint32_t cap = std::max<uint32_t>(P, (uint32_t)s + 4 * SEL_CHUNK);
-    const size_t words = (size_t)cap + (s ? s : 1) + (SEL_CHUNK + SEL_LOOKAHEAD) +
+    uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + 4 * SEL_CHUNK) + 3u) & ~3u;
+    const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + (SEL_CHUNK + SEL_LOOKAHEAD) +
                          2 * SEL_STAGE_WORDS + (SEL_NBK + 1) + 8;
     const size_t smem = words * 4;
     static size_t configured = 0;
