@@ -24,11 +24,20 @@ def splitmix64(x: np.ndarray) -> np.ndarray:
 
 
 def codes(seed: int, g0: int, count: int) -> np.ndarray:
-    """2-bit codes for global base indices [g0, g0+count)."""
-    g = np.arange(g0, g0 + count, dtype=np.uint64)
-    with np.errstate(over="ignore"):
-        w = splitmix64(np.uint64(seed) + (g >> np.uint64(5)))
-    return ((w >> (np.uint64(2) * (g & np.uint64(31)))) & np.uint64(3)).astype(np.uint8)
+    """2-bit codes for global base indices [g0, g0+count): one splitmix64 word per 32 bases."""
+    if count <= 0:
+        return np.zeros(0, dtype=np.uint8)
+    w0, w1 = g0 >> 5, (g0 + count - 1) >> 5
+    out = np.empty((w1 - w0 + 1) * 32, dtype=np.uint8)
+    shifts = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+    step = 1 << 19  # words per chunk (bounded temporaries)
+    for a in range(w0, w1 + 1, step):
+        b = min(a + step, w1 + 1)
+        with np.errstate(over="ignore"):
+            w = splitmix64(np.uint64(seed) + np.arange(a, b, dtype=np.uint64))
+        out[(a - w0) * 32:(b - w0) * 32] = ((w[:, None] >> shifts) & np.uint64(3)).astype(np.uint8).reshape(-1)
+    lo = g0 & 31
+    return out[lo:lo + count]
 
 
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
