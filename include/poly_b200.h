@@ -167,6 +167,21 @@ int pg_sw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets,
                           const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
                           int64_t *d_score, int32_t *d_err_code, int64_t *d_err_pos, void *stream);
 
+/* ---- align.NeedlemanWunsch score -- search/align/align.go:100-134 (fill) and :166 --------
+ * (a "next" row of SURVEY.md 8f).  Same arguments and error semantics as the Smith-Waterman
+ * entry points; score = matrix[len(a)][len(b)] of the global alignment (gap ramps on the first
+ * row and column, no zero floor). */
+int pg_nw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table,
+                      int32_t n_a, int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code,
+                      int64_t *err_pos);
+int pg_nw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets, uint64_t n_queries,
+                          uint64_t max_query_len, const uint8_t *d_templ, uint64_t templ_len,
+                          int32_t query_is_a, const int16_t *lut_a_host, const int16_t *lut_b_host,
+                          const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
+                          int64_t *d_score, int32_t *d_err_code, int64_t *d_err_pos, void *stream);
+
 /* ---- primers.SantaLucia / MeltingTemp -- primers/primers.go:70-105,121-128 --------
  * tm/dh/ds may each be NULL.  status: PG_ITEM_PANIC for an empty primer
  * (primers.go:89), PG_ITEM_UNSUPPORTED for a byte >= 0x80 (strings.ToUpper would

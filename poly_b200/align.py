@@ -87,8 +87,9 @@ def NewScoring(substitution_matrix: Optional[SubstitutionMatrix], gap_penalty: i
 
 
 def sw_scores_arrays(q_bases: np.ndarray, q_offsets: np.ndarray, template: BytesLike, scoring: Scoring,
-                     query_is_a: bool = True) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """(score, err_code, err_pos) for every query against one template."""
+                     query_is_a: bool = True, global_alignment: bool = False) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(score, err_code, err_pos) for every query against one template (Smith-Waterman, or the
+    Needleman-Wunsch score with global_alignment=True)."""
     m = scoring.SubstitutionMatrix
     lut_a, lut_b = m.FirstAlphabet.byte_lut(), m.SecondAlphabet.byte_lut()
     table = np.ascontiguousarray(m.scores, dtype=np.int64)
@@ -97,7 +98,8 @@ def sw_scores_arrays(q_bases: np.ndarray, q_offsets: np.ndarray, template: Bytes
     q_offsets = np.ascontiguousarray(q_offsets, dtype=np.uint64)
     n = len(q_offsets) - 1
     score, ec, ep = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int64)
-    rc = _lib.lib().pg_sw_score_batch(q_bases.ctypes.data, q_offsets.ctypes.data, n, t.ctypes.data, len(t), int(query_is_a),
+    fn = _lib.lib().pg_nw_score_batch if global_alignment else _lib.lib().pg_sw_score_batch
+    rc = fn(q_bases.ctypes.data, q_offsets.ctypes.data, n, t.ctypes.data, len(t), int(query_is_a),
                                       lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[0], table.shape[1],
                                       scoring.GapPenalty, score.ctypes.data, ec.ctypes.data, ep.ctypes.data)
     _lib.check(rc)
@@ -110,11 +112,11 @@ def _error_for(ec: int, ep: int, a: np.ndarray, b: np.ndarray) -> AlphabetError:
 
 
 def SmithWatermanScores(queries: Sequence[BytesLike], template: BytesLike, scoring: Scoring,
-                        query_is_a: bool = True) -> Tuple[List[int], List[Optional[AlphabetError]]]:
+                        query_is_a: bool = True, global_alignment: bool = False) -> Tuple[List[int], List[Optional[AlphabetError]]]:
     """Batched addition: score (and error) of SmithWaterman(query, template) per query
     (or SmithWaterman(template, query) with query_is_a=False)."""
     bases, offsets = flatten(queries)
-    score, ec, ep = sw_scores_arrays(bases, offsets, template, scoring, query_is_a)
+    score, ec, ep = sw_scores_arrays(bases, offsets, template, scoring, query_is_a, global_alignment)
     t = _as_bytes(template)
     errs: List[Optional[AlphabetError]] = []
     for i in range(len(queries)):
@@ -130,6 +132,19 @@ def SmithWaterman(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> i
     """Score of align.SmithWaterman(stringA, stringB, scoring) (align.go:171-203).
     Raises AlphabetError where the reference returns (0, "", "", err)."""
     scores, errs = SmithWatermanScores([stringA], stringB, scoring, query_is_a=True)
+    if errs[0] is not None:
+        raise errs[0]
+    return scores[0]
+
+
+def NeedlemanWunschScores(queries: Sequence[BytesLike], template: BytesLike, scoring: Scoring, query_is_a: bool = True):
+    """Batched score of align.NeedlemanWunsch(query, template) (align.go:100-134,166)."""
+    return SmithWatermanScores(queries, template, scoring, query_is_a, global_alignment=True)
+
+
+def NeedlemanWunsch(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> int:
+    """Score of align.NeedlemanWunsch(stringA, stringB, scoring); the aligned strings are not built."""
+    scores, errs = NeedlemanWunschScores([stringA], stringB, scoring)
     if errs[0] is not None:
         raise errs[0]
     return scores[0]

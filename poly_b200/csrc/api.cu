@@ -530,7 +530,7 @@ int pg_mash_distance_block(const uint32_t *sketches, uint64_t n, int32_t s, uint
 // ---------------------------------------------------------------------------------
 // Smith-Waterman score
 // ---------------------------------------------------------------------------------
-int pg_sw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets, uint64_t n_queries,
+static int align_score_dev(int global, const uint8_t *d_queries, const uint64_t *d_q_offsets, uint64_t n_queries,
                           uint64_t max_query_len, const uint8_t *d_templ, uint64_t templ_len,
                           int32_t query_is_a, const int16_t *lut_a_host, const int16_t *lut_b_host,
                           const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
@@ -540,10 +540,10 @@ int pg_sw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets,
     if (!lut_a_host || !lut_b_host || !table_host || (n_queries && (!d_q_offsets || !d_score))) { set_error("null buffer"); return PG_ERR_ARG; }
     return launch_sw_score(d_queries, d_q_offsets, n_queries, max_query_len, d_templ, templ_len,
                            query_is_a, lut_a_host, lut_b_host, table_host, n_a, n_b, gap, d_score,
-                           d_err_code, d_err_pos, (cudaStream_t)stream);
+                           d_err_code, d_err_pos, (cudaStream_t)stream, global);
 }
 
-int pg_sw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+static int align_score_host(int global, const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
                       const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
                       const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
                       int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos) {
@@ -565,13 +565,44 @@ int pg_sw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_
     if (templ_len) PG_CUDA(cudaMemcpyAsync(d_t.p, templ, templ_len, cudaMemcpyHostToDevice, st));
     rc = launch_sw_score(d_q.as<uint8_t>() - q0, d_off.as<uint64_t>(), n_queries, maxq, d_t.as<uint8_t>(), templ_len,
                          query_is_a, lut_a, lut_b, table, n_a, n_b, gap, d_sc.as<int64_t>(), d_ec.as<int32_t>(),
-                         d_ep.as<int64_t>(), st);
+                         d_ep.as<int64_t>(), st, global);
     if (rc != PG_OK) return rc;
     PG_CUDA(cudaMemcpyAsync(score, d_sc.p, n_queries * 8, cudaMemcpyDeviceToHost, st));
     if (err_code) PG_CUDA(cudaMemcpyAsync(err_code, d_ec.p, n_queries * 4, cudaMemcpyDeviceToHost, st));
     if (err_pos) PG_CUDA(cudaMemcpyAsync(err_pos, d_ep.p, n_queries * 8, cudaMemcpyDeviceToHost, st));
     PG_CUDA(cudaStreamSynchronize(st));
     return PG_OK;
+}
+
+int pg_sw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets, uint64_t n_queries,
+                          uint64_t max_query_len, const uint8_t *d_templ, uint64_t templ_len,
+                          int32_t query_is_a, const int16_t *lut_a_host, const int16_t *lut_b_host,
+                          const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
+                          int64_t *d_score, int32_t *d_err_code, int64_t *d_err_pos, void *stream) {
+    return align_score_dev(0, d_queries, d_q_offsets, n_queries, max_query_len, d_templ, templ_len, query_is_a, lut_a_host,
+                           lut_b_host, table_host, n_a, n_b, gap, d_score, d_err_code, d_err_pos, stream);
+}
+int pg_nw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets, uint64_t n_queries,
+                          uint64_t max_query_len, const uint8_t *d_templ, uint64_t templ_len,
+                          int32_t query_is_a, const int16_t *lut_a_host, const int16_t *lut_b_host,
+                          const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
+                          int64_t *d_score, int32_t *d_err_code, int64_t *d_err_pos, void *stream) {
+    return align_score_dev(1, d_queries, d_q_offsets, n_queries, max_query_len, d_templ, templ_len, query_is_a, lut_a_host,
+                           lut_b_host, table_host, n_a, n_b, gap, d_score, d_err_code, d_err_pos, stream);
+}
+int pg_sw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
+                      int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos) {
+    return align_score_host(0, queries, q_offsets, n_queries, templ, templ_len, query_is_a, lut_a, lut_b, table, n_a, n_b, gap,
+                            score, err_code, err_pos);
+}
+int pg_nw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
+                      int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos) {
+    return align_score_host(1, queries, q_offsets, n_queries, templ, templ_len, query_is_a, lut_a, lut_b, table, n_a, n_b, gap,
+                            score, err_code, err_pos);
 }
 
 // ---------------------------------------------------------------------------------

@@ -61,7 +61,7 @@ int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_b
 int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen,
                     const uint8_t *d_t, uint64_t tlen, int query_is_a, const int16_t *lut_a,
                     const int16_t *lut_b, const int64_t *table, int n_a, int n_b, int64_t gap,
-                    int64_t *d_score, int32_t *d_err, int64_t *d_errpos, cudaStream_t st);
+                    int64_t *d_score, int32_t *d_err, int64_t *d_errpos, cudaStream_t st, int global = 0);
 // tm.cu
 int launch_tm(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double cp, double na,
               double mg, double *d_tm, double *d_dh, double *d_ds, int32_t *d_status,

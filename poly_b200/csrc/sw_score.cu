@@ -1,4 +1,5 @@
-// sw_score.cu -- K4: Smith-Waterman score of n short queries against one template,
+// sw_score.cu -- K4: Smith-Waterman (and Needleman-Wunsch, align.go:100-134,166) score of n short
+// queries against one template,
 // /root/reference/search/align/align.go:171-203 (fill + running max; the traceback at
 // :205-231 is out of scope).  Linear gap (ADDED, align.go:193-194), arbitrary
 // substitution table addressed through two byte->index LUTs
@@ -44,6 +45,7 @@ struct SwParams {
     uint64_t tlen;
     int query_is_a;
     int n_q, n_t;  // alphabet sizes on the query / template side
+    int global;    // 0: Smith-Waterman (local), 1: Needleman-Wunsch (global) score
 };
 
 // Short queries (<= ROWS cells): one thread per query, DP column in registers, no branches in
@@ -58,7 +60,7 @@ struct SwBig {
     static constexpr T value = (T)1 << (sizeof(T) * 8 - 3);  // 2^29 / 2^61: no overflow in diag + sc
 };
 
-template <typename T, int ROWS, bool PROFILE, bool MASK>
+template <typename T, int ROWS, bool PROFILE, bool MASK, bool GLOBAL>
 __global__ void __launch_bounds__(SW_THREADS)
 sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__restrict__ lut_t,
                 const T *__restrict__ tab, T gap, int64_t *__restrict__ score,
@@ -111,8 +113,9 @@ sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__
     }
     T col[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) col[i] = 0;
+    for (int i = 0; i < ROWS; ++i) col[i] = GLOBAL ? (T)(i + 1) * gap : (T)0;  // NW: first column, align.go:115-117
     T best = 0;
+    T edge = 0;  // NW: H[0][j-1], the first-row gap ramp (align.go:120-122)
 
     for (uint64_t t0 = 0; t0 < p.tlen; t0 += SW_TCHUNK) {
         const uint32_t tc = (uint32_t)min((uint64_t)SW_TCHUNK, p.tlen - t0);
@@ -127,22 +130,35 @@ sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__
             for (uint32_t j = 0; j < tc; ++j) {
                 const int tj = s_tidx[j];
                 const T *pcol = s_prof + (size_t)tj * ROWS * SW_THREADS + tid;
-                T diag = 0, up = 0;
+                T diag = GLOBAL ? edge : (T)0, up = GLOBAL ? edge + gap : (T)0;
+                if (GLOBAL) edge += gap;
 #pragma unroll
                 for (int i = 0; i < ROWS; ++i) {
                     const T old = col[i];                                    // H[i][j-1]
-                    const T sc = PROFILE ? pcol[i * SW_THREADS] : s_tab[qrow[i] + tj];  // align.go:188
-                    T v = addmax<T>(diag, sc, (T)0);                         // align.go:192,195
-                    v = addmax<T>(old, gap, v);                              // left / up by orientation
-                    v = addmax<T>(up, gap, v);
-                    if (MASK) { if (i < (int)qlen) best = v > best ? v : best; }
-                    else best = v > best ? v : best;                         // align.go:197-201
+                    const T sc = PROFILE ? pcol[i * SW_THREADS] : s_tab[qrow[i] + tj];  // align.go:188 / :126
+                    T v;
+                    if (GLOBAL) {
+                        v = addmax<T>(diag, sc, old + gap);                  // align.go:132-135 (no zero floor)
+                        v = addmax<T>(up, gap, v);
+                    } else {
+                        v = addmax<T>(diag, sc, (T)0);                       // align.go:192,195
+                        v = addmax<T>(old, gap, v);                          // left / up by orientation
+                        v = addmax<T>(up, gap, v);
+                        if (MASK) { if (i < (int)qlen) best = v > best ? v : best; }
+                        else best = v > best ? v : best;                     // align.go:197-201
+                    }
                     diag = old;
                     up = v;
                     col[i] = v;
                 }
             }
         }
+    }
+    if (GLOBAL) {  // matrix[la][lb] (align.go:166); la == 0 or lb == 0: a pure gap ramp
+        best = (T)p.tlen * gap;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i)
+            if (i + 1 == (int)qlen) best = p.tlen ? col[i] : (T)qlen * gap;
     }
     __syncthreads();
     if (!active) return;
@@ -178,27 +194,35 @@ sw_score_long_kernel(SwParams p, uint64_t q_first, const int16_t *__restrict__ l
     const uint64_t qlen = p.qoff[qi + 1] - qbeg;
     int64_t first_bad_q = -1, bad_t = -1;
     for (uint64_t i = 0; i < qlen; ++i) {
-        scratch[i * n_batch + b] = 0;
+        scratch[i * n_batch + b] = p.global ? (T)(i + 1) * gap : (T)0;
         if (first_bad_q < 0 && lut_q[__ldg(p.q + qbeg + i)] < 0) first_bad_q = (int64_t)i;
     }
-    T best = 0;
+    T best = 0, edge = 0;
     for (uint64_t j = 0; j < p.tlen; ++j) {
         const int tj = lut_t[__ldg(p.t + j)];
         if (tj < 0 && bad_t < 0) bad_t = (int64_t)j;
-        T diag = 0, up = 0;
+        T diag = p.global ? edge : (T)0, up = p.global ? edge + gap : (T)0;
+        edge += gap;
         for (uint64_t i = 0; i < qlen; ++i) {
             const int qx = lut_q[__ldg(p.q + qbeg + i)];
             const T old = scratch[i * n_batch + b];
             const T sc = (qx < 0 || tj < 0) ? (T)0 : tab[qx * p.n_t + tj];
-            T v = addmax<T>(diag, sc, (T)0);
-            v = addmax<T>(old, gap, v);
-            v = addmax<T>(up, gap, v);
-            best = v > best ? v : best;
+            T v;
+            if (p.global) {
+                v = addmax<T>(diag, sc, old + gap);
+                v = addmax<T>(up, gap, v);
+            } else {
+                v = addmax<T>(diag, sc, (T)0);
+                v = addmax<T>(old, gap, v);
+                v = addmax<T>(up, gap, v);
+                best = v > best ? v : best;
+            }
             diag = old;
             up = v;
             scratch[i * n_batch + b] = v;
         }
     }
+    if (p.global) best = qlen == 0 ? (T)p.tlen * gap : (p.tlen == 0 ? (T)qlen * gap : scratch[(qlen - 1) * n_batch + b]);
     int32_t ec = 0;
     int64_t ep = -1;
     if (qlen > 0 && p.tlen > 0) {
@@ -245,17 +269,18 @@ int run_sw(const SwParams &p, uint64_t max_qlen, const int16_t *h_lut_q, const i
         const bool profile = base_smem + prof <= 100 * 1024;
         const size_t smem = base_smem + (profile ? prof : 0);
         if (smem > 200 * 1024) return false;
-#define PG_SW_LAUNCH(PROF, MSK)                                                                          \
+#define PG_SW_LAUNCH(PROF, MSK, GLB)                                                                     \
         do {                                                                                                 \
-            cudaFuncSetAttribute(sw_score_kernel<T, ROWS, PROF, MSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            sw_score_kernel<T, ROWS, PROF, MSK><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap, d_score, d_err, d_errpos); \
+            cudaFuncSetAttribute(sw_score_kernel<T, ROWS, PROF, MSK, GLB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            sw_score_kernel<T, ROWS, PROF, MSK, GLB><<<blocks, SW_THREADS, smem, st>>>(p, d_lut_q, d_lut_t, d_tab, (T)gap, d_score, d_err, d_errpos); \
         } while (0)
-        if (profile && !mask) PG_SW_LAUNCH(true, false);
-        else if (profile && mask) PG_SW_LAUNCH(true, true);
-        else if (!profile && !mask) PG_SW_LAUNCH(false, false);
-        else PG_SW_LAUNCH(false, true);
+        if (p.global) { if (profile) PG_SW_LAUNCH(true, false, true); else PG_SW_LAUNCH(false, false, true); }
+        else if (profile && !mask) PG_SW_LAUNCH(true, false, false);
+        else if (profile && mask) PG_SW_LAUNCH(true, true, false);
+        else if (!profile && !mask) PG_SW_LAUNCH(false, false, false);
+        else PG_SW_LAUNCH(false, true, false);
 #undef PG_SW_LAUNCH
-        note_launch("sw_score_kernel");
+        note_launch(p.global ? "nw_score_kernel" : "sw_score_kernel");
         launched = true;
         return true;
     };
@@ -299,7 +324,7 @@ int run_sw(const SwParams &p, uint64_t max_qlen, const int16_t *h_lut_q, const i
 int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen,
                     const uint8_t *d_t, uint64_t tlen, int query_is_a, const int16_t *lut_a,
                     const int16_t *lut_b, const int64_t *table, int n_a, int n_b, int64_t gap,
-                    int64_t *d_score, int32_t *d_err, int64_t *d_errpos, cudaStream_t st) {
+                    int64_t *d_score, int32_t *d_err, int64_t *d_errpos, cudaStream_t st, int global) {
     if (nq == 0) return PG_OK;
     if (n_a <= 0 || n_b <= 0 || n_a > 255 || n_b > 255) {
         set_error("alphabet sizes must be in 1..255 (got %d, %d)", n_a, n_b);
@@ -307,6 +332,7 @@ int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
     }
     SwParams p;
     p.q = d_q; p.qoff = d_qoff; p.nq = nq; p.t = d_t; p.tlen = tlen; p.query_is_a = query_is_a;
+    p.global = global;
     p.n_q = query_is_a ? n_a : n_b;
     p.n_t = query_is_a ? n_b : n_a;
     const int16_t *lut_q = query_is_a ? lut_a : lut_b;
@@ -323,8 +349,10 @@ int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
     const int64_t agap = gap < 0 ? -gap : gap;
     // every DP value lies in [0, min(la,lb) * max S]; operands of one add stay below
     // that plus max(|S|,|gap|): use 32-bit DPX arithmetic when this provably fits
-    const long double bound = (long double)amax * (long double)std::min<uint64_t>(max_qlen, tlen) +
-                              (long double)std::max(amax, agap);
+    // (NW: every value lies within (la + lb) * max(|S|, |gap|))
+    const long double bound = global ? (long double)std::max(amax, agap) * (long double)(max_qlen + tlen + 2)
+                                     : (long double)amax * (long double)std::min<uint64_t>(max_qlen, tlen) +
+                                           (long double)std::max(amax, agap);
     if (bound < 2.0e9L)
         return run_sw<int>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st);
     return run_sw<long long>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st);

@@ -151,3 +151,54 @@ def test_reference_design_primers_through_gpu(gpu):
     """primers/pcr/example_test.go:36,46,54: primer strings pinned by Tm threshold crossings,
     with every MeltingTemp evaluated on the GPU."""
     assert design_primers(primers.MeltingTemp, GENE, 55.0) == ("AATAATTACACCGAGATAACACATCATGG", "TTAAGAAAGCGCATTTTCCAGC")
+
+
+def test_reference_TestNeedlemanWunsch(gpu):
+    """search/align/align_test.go:11-137 and example_test.go:10-47 (scores)."""
+    a5 = align.NewAlphabet(["A", "C", "G", "T", "U"])
+    sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, 2 * np.eye(5, dtype=np.int64) - 1), -1)
+    for a, b, want in [("GATTACA", "GCATGCU", 0), ("GATTACA", "GATTACA", 7), ("GATTACA", "GAT", -1), ("", "GAT", -3), ("", "", 0),
+                       ("G", "A", -1), ("G", "G", 1), ("G", "GATTACA", -5), ("GAT", "", -3)]:
+        assert align.NeedlemanWunsch(a, b, sc) == want, (a, b)
+    with pytest.raises(align.AlphabetError, match="Symbol X not in alphabet"):
+        align.NeedlemanWunsch("GATX", "GAT", sc)
+
+
+@pytest.mark.parametrize("maxq,tlen", [(25, 3000), (40, 9000), (64, 500), (150, 400)])
+def test_nw_batch_vs_oracle(gpu, oracle, maxq, tlen):
+    rng = np.random.default_rng(maxq + 1)
+    nq = 200
+    qs = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, maxq + 1))).astype(np.uint8)) for _ in range(nq - 1)]
+    qs.append(bytes(rng.choice(list(b"ACGT"), size=maxq).astype(np.uint8)))
+    t = bytes(rng.choice(list(b"ACGT"), size=tlen).astype(np.uint8))
+    for query_is_a in (True, False):
+        scores, errs = align.NeedlemanWunschScores(qs, t, SC, query_is_a=query_is_a)
+        for i in range(0, nq, 5):
+            a, b = (qs[i], t) if query_is_a else (t, qs[i])
+            w = oracle.nw_score(a, b, TEST_LUT, TEST_LUT, TEST_MAT, -2)
+            assert errs[i] is None and scores[i] == w[0], (i, query_is_a, len(qs[i]))
+    # positive "gap" (a reward) exercises the masked Smith-Waterman variant
+    scp = align.NewScoring(SC.SubstitutionMatrix, 1)
+    scores, errs = align.SmithWatermanScores(qs[:60], t[:300], scp)
+    for i in range(60):
+        assert scores[i] == oracle.sw_score(qs[i], t[:300], TEST_LUT, TEST_LUT, TEST_MAT, 1)[0]
+
+
+def test_cfg5_full_size_properties(gpu, oracle):
+    """BASELINE configs[4] at full size: 1M x 25 bp primers vs the 10 kb template."""
+    n = 1_000_000
+    pr = synth.primers(n)
+    off = synth.uniform_offsets(n, 25)
+    tpl = synth.template()
+    score, ec, ep = align.sw_scores_arrays(pr, off, tpl, SC)
+    assert not ec.any() and score.min() >= 0 and score.max() <= 75        # 25 matches x 3
+    idx = np.random.default_rng(8).integers(0, n, 200)
+    for i in idx:
+        assert score[i] == oracle.sw_score(bytes(pr[25 * i:25 * i + 25]), bytes(tpl), TEST_LUT, TEST_LUT, TEST_MAT, -2)[0]
+    # the same primers in two halves give the same scores (chunk independence)
+    s2, _, _ = align.sw_scores_arrays(pr[: 25 * 1000], off[:1001], tpl, SC)
+    assert np.array_equal(s2, score[:1000])
+    tm, dh, ds, st = primers.santalucia_arrays(pr, off, primers.DEFAULT_CP, primers.DEFAULT_NA, primers.DEFAULT_MG)
+    assert not st.any() and np.isfinite(tm).all() and 20 < tm.min() and tm.max() < 90
+    for i in idx:
+        assert tm[i] == pytest.approx(oracle.melting_temp(bytes(pr[25 * i:25 * i + 25])), rel=1e-6)

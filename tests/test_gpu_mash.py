@@ -316,3 +316,40 @@ def test_distance_join_larger_family_set(gpu, oracle):
     for f in range(n // fam):
         off_family[f, :, f, :] = 0
     assert off_family.max() <= 2 and blocks[3, :, 3, :].min() > 20
+
+
+def test_cfg3_full_size_properties(gpu, oracle):
+    """BASELINE configs[2] sketching at full size (100k x 10 kbp, k=31, s=2000): every row
+    ascending, spot rows bit-exact vs the oracle, and an all-pairs row block whose structure
+    matches the family construction."""
+    import torch
+    from poly_b200 import _lib
+
+    n, L, k, s = 100_000, 10_000, 31, 2000
+    L_ = _lib.lib()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    d_reads = torch.empty(n * L, dtype=torch.uint8, device=dev)
+    _lib.check(L_.pg_synth_reads_dev(d_reads.data_ptr(), 0, n, L, synth.SEED_READS, 1, 100, st))
+    d_sk = torch.empty((n, s), dtype=torch.int32, device=dev)
+    _lib.check(L_.pg_mash_sketch_uniform_dev(d_reads.data_ptr(), n, L, k, s, 0, d_sk.data_ptr(), s, None, st))
+    sk64 = d_sk.to(torch.int64) & 0xFFFFFFFF
+    assert bool((sk64[:, 1:] >= sk64[:, :-1]).all())                          # sortedness of all 100k rows
+    idx = [0, 1, 99, 100, 54_321, n - 1]
+    got = d_sk[idx].cpu().numpy().view(np.uint32)
+    host_reads = np.concatenate([synth.family_reads(1, L, family=100, first_read=i) for i in idx])
+    dev_reads = np.concatenate([d_reads[i * L:(i + 1) * L].cpu().numpy() for i in idx])
+    assert np.array_equal(host_reads, dev_reads)                               # device generator == numpy generator
+    rc, want = oracle.sketch_batch(host_reads, synth.uniform_offsets(len(idx), L), k, s, variant=1)
+    assert rc == 0 and np.array_equal(got, want)
+    rows = 512
+    d_same = torch.empty((rows, n), dtype=torch.int32, device=dev)
+    _lib.check(L_.pg_mash_distance_block_dev(d_sk.data_ptr(), n, s, 0, rows, d_same.data_ptr(), None, st))
+    same = d_same.cpu().numpy()
+    assert (np.diag(same[:, :rows]) == s).all() and (same[:, :rows] == same[:, :rows].T).all()
+    fam = same[:100, :100]
+    assert fam[~np.eye(100, dtype=bool)].min() > 500 and same[:100, 100:].max() <= 3
+    a = oracle.OracleMash(k, s); a.Sketches[:] = got[0]
+    b = oracle.OracleMash(k, s); b.Sketches[:] = got[1]
+    assert same[0, 1] == a.SimilarityCount(b)[0]
