@@ -167,6 +167,20 @@ int pg_sw_score_batch_dev(const uint8_t *d_queries, const uint64_t *d_q_offsets,
                           const int64_t *table_host, int32_t n_a, int32_t n_b, int64_t gap,
                           int64_t *d_score, int32_t *d_err_code, int64_t *d_err_pos, void *stream);
 
+/* ---- align.SmithWaterman with the aligned strings -- search/align/align.go:171-232 in full ----
+ * (SURVEY.md 8f.1).  As pg_sw_score_batch, plus for every query the two aligned strings of the
+ * reference's traceback (first maximum in row-major order, diagonal > up > left, align.go:205-229):
+ * align_a / align_b hold n_queries rows of out_stride bytes, align_len[i] the common length.
+ * status[i]: PG_ITEM_OK, or PG_ITEM_UNSUPPORTED if the alignment is longer than out_stride
+ * (align_len[i] then reports the needed length).  Limits: queries of <= 64 symbols and scores
+ * that fit 32 bits (PG_ERR_UNSUPPORTED otherwise). */
+int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table,
+                      int32_t n_a, int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code,
+                      int64_t *err_pos, uint8_t *align_a, uint8_t *align_b, uint64_t out_stride,
+                      uint32_t *align_len, int32_t *status);
+
 /* ---- align.NeedlemanWunsch score -- search/align/align.go:100-134 (fill) and :166 --------
  * (a "next" row of SURVEY.md 8f).  Same arguments and error semantics as the Smith-Waterman
  * entry points; score = matrix[len(a)][len(b)] of the global alignment (gap ramps on the first

@@ -184,3 +184,47 @@ int po_santalucia(const uint8_t *seq_in, int64_t len, double cp, double na, doub
 int po_melting_temp(const uint8_t *seq, int64_t len, double *tm) {
     return po_santalucia(seq, len, 500e-9, 50e-3, 0.0, tm, NULL, NULL);
 }
+
+/* search/align/align.go:171-232 in full: fill, first-max position, traceback (diag > up > left
+ * preference, strings built by prepending).  out_a/out_b receive the aligned strings (no NUL),
+ * *out_len their common length; cap = capacity of each buffer (la + lb always suffices).
+ * Only used to pin the traceback kernel; O(la*lb) memory. */
+int po_sw_align(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb, const int16_t *lut_a,
+                const int16_t *lut_b, const int64_t *table, int n_b, int64_t gap, int64_t *score,
+                uint8_t *out_a, uint8_t *out_b, int64_t cap, int64_t *out_len, int32_t *err_code,
+                int64_t *err_pos) {
+    const int64_t W = lb + 1;
+    int64_t *m = (int64_t *)calloc((size_t)((la + 1) * W), sizeof(int64_t)); /* align.go:175-178 */
+    if (!m) return -100;
+    int64_t best = 0, br = 0, bc = 0;
+    *err_code = 0; *err_pos = -1; *out_len = 0;
+    for (int64_t i = 1; i <= la; i++)
+        for (int64_t j = 1; j <= lb; j++) {
+            int64_t s = 0;
+            int e = cell_score(a[i - 1], b[j - 1], lut_a, lut_b, table, n_b, &s);
+            if (e) { *err_code = e; *err_pos = e == 1 ? i - 1 : j - 1; *score = 0; free(m); return PO_OK; }
+            int64_t v = max64(0, max64(m[(i - 1) * W + j - 1] + s, max64(m[(i - 1) * W + j] + gap, m[i * W + j - 1] + gap)));
+            m[i * W + j] = v;
+            if (v > best) { best = v; br = i; bc = j; }            /* align.go:197-201 */
+        }
+    /* traceback, align.go:205-229: build reversed, then reverse (== prepending) */
+    int64_t n = 0, i = br, j = bc;
+    while (m[i * W + j] > 0) {
+        int64_t s = 0;
+        cell_score(a[i - 1], b[j - 1], lut_a, lut_b, table, n_b, &s);
+        if (n >= cap) { free(m); return -101; }
+        if (m[i * W + j] == m[(i - 1) * W + j - 1] + s) { out_a[n] = a[i - 1]; out_b[n] = b[j - 1]; i--; j--; }
+        else if (m[i * W + j] == m[(i - 1) * W + j] + gap) { out_a[n] = a[i - 1]; out_b[n] = '-'; i--; }
+        else if (m[i * W + j] == m[i * W + j - 1] + gap) { out_a[n] = '-'; out_b[n] = b[j - 1]; j--; }
+        else { free(m); return -102; } /* the reference would spin forever; cannot happen for a max of the three */
+        n++;
+    }
+    for (int64_t t = 0; t < n / 2; t++) {
+        uint8_t x = out_a[t]; out_a[t] = out_a[n - 1 - t]; out_a[n - 1 - t] = x;
+        x = out_b[t]; out_b[t] = out_b[n - 1 - t]; out_b[n - 1 - t] = x;
+    }
+    *out_len = n;
+    *score = best;
+    free(m);
+    return PO_OK;
+}

@@ -4,10 +4,10 @@ search/align/matrix packages over libpolyb200.so.
 Mirrors /root/reference/alphabet/alphabet.go:25-61 (`NewAlphabet`, `Encode`, `Error`),
 search/align/matrix/matrix.go:13-38 (`NewSubstitutionMatrix`, `Score`, `Default`),
 search/align/matrix/matrices.go:33-40 (`NUC_4`) and search/align/align.go:73-95,171-203
-(`Scoring`, `NewScoring`, the fill + running max of `SmithWaterman`).  The traceback
-strings (align.go:205-231) are a "next" row of SURVEY.md 8f: `SmithWaterman` here
-returns the score and raises the reference's `alphabet.Error`; it does not build the
-aligned strings.  All DP cells are computed on the GPU.
+(`Scoring`, `NewScoring`, `SmithWaterman`).  `SmithWaterman` returns the score (raising the
+reference's `alphabet.Error`); `SmithWatermanAlign` additionally returns the two aligned strings
+of the reference's traceback (align.go:205-231; queries of <= 64 symbols); `NeedlemanWunsch`
+returns the global score.  All DP cells and the traceback are computed on the GPU.
 """
 from __future__ import annotations
 
@@ -148,3 +148,51 @@ def NeedlemanWunsch(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) ->
     if errs[0] is not None:
         raise errs[0]
     return scores[0]
+
+
+def SmithWatermanAligns(queries: Sequence[BytesLike], template: BytesLike, scoring: Scoring, query_is_a: bool = True):
+    """Batched full align.SmithWaterman: [(score, alignA, alignB, err)] per query (stringA = query
+    when query_is_a, else stringA = template)."""
+    m = scoring.SubstitutionMatrix
+    lut_a, lut_b = m.FirstAlphabet.byte_lut(), m.SecondAlphabet.byte_lut()
+    table = np.ascontiguousarray(m.scores, dtype=np.int64)
+    t = _as_bytes(template)
+    bases, offsets = flatten(queries)
+    n = len(queries)
+    maxq = max((len(_as_bytes(q)) for q in queries), default=0)
+    stride = max(2 * maxq + 64, 64)
+    while True:
+        score, ec, ep = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int64)
+        oa, ob = np.zeros((n, stride), np.uint8), np.zeros((n, stride), np.uint8)
+        ln, st = np.zeros(n, np.uint32), np.zeros(n, np.int32)
+        rc = _lib.lib().pg_sw_align_batch(bases.ctypes.data, offsets.ctypes.data, n, t.ctypes.data, len(t), int(query_is_a),
+                                          lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[0], table.shape[1],
+                                          scoring.GapPenalty, score.ctypes.data, ec.ctypes.data, ep.ctypes.data, oa.ctypes.data,
+                                          ob.ctypes.data, stride, ln.ctypes.data, st.ctypes.data)
+        _lib.check(rc)
+        if (st == _lib.PG_ITEM_UNSUPPORTED).any():  # an alignment longer than the row: grow and retry
+            stride = int(ln.max()) + 8
+            continue
+        break
+    res = []
+    for i in range(n):
+        if ec[i]:
+            q = bases[int(offsets[i]): int(offsets[i + 1])]
+            res.append((0, "", "", _error_for(int(ec[i]), int(ep[i]), q if query_is_a else t, t if query_is_a else q)))
+        else:
+            res.append((int(score[i]), bytes(oa[i, : ln[i]]).decode("latin-1"), bytes(ob[i, : ln[i]]).decode("latin-1"), None))
+    return res
+
+
+def SmithWatermanAlign(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> Tuple[int, str, str]:
+    """align.SmithWaterman(stringA, stringB, scoring) -> (score, alignA, alignB); raises
+    AlphabetError where the reference returns (0, "", "", err).  Needs len(stringA) <= 64 or
+    len(stringB) <= 64 (the shorter string rides in registers)."""
+    a, b = _as_bytes(stringA), _as_bytes(stringB)
+    if len(a) <= 64:
+        score, sa, sb, err = SmithWatermanAligns([a], b, scoring, query_is_a=True)[0]
+    else:
+        score, sa, sb, err = SmithWatermanAligns([b], a, scoring, query_is_a=False)[0]
+    if err is not None:
+        raise err
+    return score, sa, sb

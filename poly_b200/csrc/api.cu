@@ -605,6 +605,50 @@ int pg_nw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_
                             score, err_code, err_pos);
 }
 
+int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
+                      int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos,
+                      uint8_t *align_a, uint8_t *align_b, uint64_t out_stride, uint32_t *align_len,
+                      int32_t *status) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (n_queries == 0) return PG_OK;
+    if (!q_offsets || !score || !lut_a || !lut_b || !table || !align_a || !align_b || !align_len || n_a <= 0 || n_b <= 0) {
+        set_error("null buffer");
+        return PG_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g_streams[0];
+    const uint64_t q0 = q_offsets[0], qbytes = q_offsets[n_queries] - q0;
+    uint64_t maxq = 0;
+    for (uint64_t i = 0; i < n_queries; ++i) maxq = std::max(maxq, q_offsets[i + 1] - q_offsets[i]);
+    Tmp d_q(st), d_off(st), d_t(st), d_sc(st), d_ec(st), d_ep(st), d_a(st), d_b(st), d_len(st), d_st(st);
+    if ((rc = d_q.alloc(qbytes)) || (rc = d_off.alloc((n_queries + 1) * 8)) || (rc = d_t.alloc(templ_len)) ||
+        (rc = d_sc.alloc(n_queries * 8)) || (rc = d_ec.alloc(n_queries * 4)) || (rc = d_ep.alloc(n_queries * 8)) ||
+        (rc = d_a.alloc(n_queries * out_stride)) || (rc = d_b.alloc(n_queries * out_stride)) ||
+        (rc = d_len.alloc(n_queries * 4)) || (rc = d_st.alloc(n_queries * 4)))
+        return rc;
+    if (qbytes) PG_CUDA(cudaMemcpyAsync(d_q.p, queries + q0, qbytes, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_off.p, q_offsets, (n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (templ_len) PG_CUDA(cudaMemcpyAsync(d_t.p, templ, templ_len, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemsetAsync(d_len.p, 0, n_queries * 4, st));
+    PG_CUDA(cudaMemsetAsync(d_st.p, 0, n_queries * 4, st));
+    rc = launch_sw_align(d_q.as<uint8_t>() - q0, d_off.as<uint64_t>(), n_queries, maxq, d_t.as<uint8_t>(), templ_len, query_is_a,
+                         lut_a, lut_b, table, n_a, n_b, gap, d_sc.as<int64_t>(), d_ec.as<int32_t>(), d_ep.as<int64_t>(),
+                         d_a.as<uint8_t>(), d_b.as<uint8_t>(), out_stride, d_len.as<uint32_t>(), d_st.as<int32_t>(), st);
+    if (rc != PG_OK) return rc;
+    PG_CUDA(cudaMemcpyAsync(score, d_sc.p, n_queries * 8, cudaMemcpyDeviceToHost, st));
+    if (err_code) PG_CUDA(cudaMemcpyAsync(err_code, d_ec.p, n_queries * 4, cudaMemcpyDeviceToHost, st));
+    if (err_pos) PG_CUDA(cudaMemcpyAsync(err_pos, d_ep.p, n_queries * 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(align_a, d_a.p, n_queries * out_stride, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(align_b, d_b.p, n_queries * out_stride, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(align_len, d_len.p, n_queries * 4, cudaMemcpyDeviceToHost, st));
+    if (status) PG_CUDA(cudaMemcpyAsync(status, d_st.p, n_queries * 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // SantaLucia Tm
 // ---------------------------------------------------------------------------------

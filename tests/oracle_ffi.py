@@ -45,6 +45,9 @@ def lib():
         L.po_sw_score.restype = C.c_int
         L.po_sw_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int64, i64p, i64p, i64p, C.POINTER(C.c_int32), i64p]
+        L.po_sw_align.restype = C.c_int
+        L.po_sw_align.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int64, i64p, C.c_char_p, C.c_char_p, C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
         L.po_nw_score.restype = C.c_int
         L.po_nw_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
@@ -129,6 +132,21 @@ def sw_score(a, b, lut_a, lut_b, table, gap):
                            C.byref(sc), C.byref(mr), C.byref(mc), C.byref(ec), C.byref(ep))
     assert rc == PO_OK
     return sc.value, mr.value, mc.value, ec.value, ep.value
+
+
+def sw_align(a, b, lut_a, lut_b, table, gap):
+    """Returns (score, alignA, alignB, err_code, err_pos) of the full align.SmithWaterman."""
+    a, b = _b(a), _b(b)
+    lut_a = np.ascontiguousarray(lut_a, dtype=np.int16)
+    lut_b = np.ascontiguousarray(lut_b, dtype=np.int16)
+    table = np.ascontiguousarray(table, dtype=np.int64)
+    cap = len(a) + len(b) + 1
+    oa, ob = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    sc, n, ep, ec = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    rc = lib().po_sw_align(a, len(a), b, len(b), lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[1], gap,
+                           C.byref(sc), oa, ob, cap, C.byref(n), C.byref(ec), C.byref(ep))
+    assert rc == PO_OK, rc
+    return sc.value, oa.raw[: n.value], ob.raw[: n.value], ec.value, ep.value
 
 
 def nw_score(a, b, lut_a, lut_b, table, gap):

@@ -202,3 +202,51 @@ def test_cfg5_full_size_properties(gpu, oracle):
     assert not st.any() and np.isfinite(tm).all() and 20 < tm.min() and tm.max() < 90
     for i in idx:
         assert tm[i] == pytest.approx(oracle.melting_temp(bytes(pr[25 * i:25 * i + 25])), rel=1e-6)
+
+
+def test_reference_alignment_strings(gpu):
+    """The aligned strings of align.SmithWaterman: search/align/align_test.go:157-291 and
+    search/align/example_test.go:82,110."""
+    assert align.SmithWatermanAlign("TGTTACGG", "GGTTGACTA", SC) == (13, "GTT-AC", "GTTGAC")
+    assert align.SmithWatermanAlign("ACACACTA", "AGCACACA", SC) == (17, "A-CACACTA", "AGCACAC-A")
+    assert align.SmithWatermanAlign("", "GAT", SC) == (0, "", "")
+    assert align.SmithWatermanAlign("", "", SC) == (0, "", "")
+    assert align.SmithWatermanAlign("G", "A", SC) == (0, "", "")
+    assert align.SmithWatermanAlign("G", "G", SC) == (3, "G", "G")
+    assert align.SmithWatermanAlign("G", "GATTACA", SC) == (3, "G", "G")
+    a5 = align.NewAlphabet(["A", "C", "G", "T", "U"])
+    sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, 2 * np.eye(5, dtype=np.int64) - 1), -1)
+    assert align.SmithWatermanAlign("GATTACA", "GCATGCU", sc) == (2, "AT", "AT")
+    an = align.NewAlphabet(["A", "C", "G", "T", "-"])
+    sc = align.NewScoring(align.NewSubstitutionMatrix(an, an, align.NUC_4), -1)
+    assert align.SmithWatermanAlign("GATTACA", "GCATGCT", sc) == (15, "GATTAC", "GCATGC")
+    with pytest.raises(align.AlphabetError, match="Symbol X not in alphabet"):
+        align.SmithWatermanAlign("ACGT", "ACGX", SC)
+
+
+@pytest.mark.parametrize("maxq,tlen,gap", [(25, 10000, -2), (32, 700, -1), (33, 500, -2), (64, 3000, -3), (20, 400, 0), (12, 300, 1)])
+def test_sw_align_batch_vs_oracle(gpu, oracle, maxq, tlen, gap):
+    """Tie-breaking of the first maximum and of the traceback, both orientations, ragged
+    queries, gap 0 / positive gap (long gap runs leave the default window: full-window retry)."""
+    rng = np.random.default_rng(maxq * 7 + tlen)
+    nq = 150
+    qs = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, maxq + 1))).astype(np.uint8)) for _ in range(nq - 1)]
+    qs.append(bytes(rng.choice(list(b"ACGT"), size=maxq).astype(np.uint8)))
+    t = bytes(rng.choice(list(b"ACGT"), size=tlen).astype(np.uint8))
+    # plant near-copies of some queries (with an indel) so that real gapped alignments occur
+    tl = bytearray(t)
+    for k_, q in enumerate(qs[:40]):
+        if len(q) > 8:
+            pos = 50 + k_ * (tlen - 200) // 40
+            ins = q[: len(q) // 2] + b"T" + q[len(q) // 2:]
+            tl[pos: pos + len(ins)] = ins[: max(0, min(len(ins), tlen - pos))]
+    t = bytes(tl[:tlen])
+    sc = align.NewScoring(SC.SubstitutionMatrix, gap)
+    for query_is_a in (True, False):
+        res = align.SmithWatermanAligns(qs, t, sc, query_is_a=query_is_a)
+        step = 1 if tlen <= 1000 else 3
+        for i in range(0, nq, step):
+            a, b = (qs[i], t) if query_is_a else (t, qs[i])
+            w = oracle.sw_align(a, b, TEST_LUT, TEST_LUT, TEST_MAT, gap)
+            assert res[i][3] is None
+            assert (res[i][0], res[i][1].encode(), res[i][2].encode()) == (w[0], w[1], w[2]), (i, query_is_a, qs[i])
