@@ -13,12 +13,12 @@ pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "survey_goldens.json")))
 
 
-def test_scoring():
+def _make_scoring():
     a = align.NewAlphabet(["-", "A", "C", "G", "T"])
     return align.NewScoring(align.NewSubstitutionMatrix(a, a, TEST_MAT), -2)
 
 
-SC = test_scoring()
+SC = _make_scoring()
 
 
 def test_reference_TestSmithWaterman(gpu):
