@@ -108,6 +108,71 @@ func SWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA b
 	return score[:n], errCode[:n], errPos[:n], check(rc)
 }
 
+// NWScoreBatch wraps pg_nw_score_batch (same arguments as SWScoreBatch).
+func NWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
+	nA, nB int, gap int64) (score []int64, errCode []int32, errPos []int64, err error) {
+	n := len(qOffsets) - 1
+	score, errCode, errPos = make([]int64, n+1), make([]int32, n+1), make([]int64, n+1)
+	t := []byte(template)
+	if len(t) == 0 {
+		t = make([]byte, 1)
+	}
+	qa := C.int32_t(0)
+	if queryIsA {
+		qa = 1
+	}
+	rc := C.pg_nw_score_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
+		(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
+		(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
+		(*C.int64_t)(unsafe.Pointer(&score[0])), (*C.int32_t)(unsafe.Pointer(&errCode[0])), (*C.int64_t)(unsafe.Pointer(&errPos[0])))
+	return score[:n], errCode[:n], errPos[:n], check(rc)
+}
+
+// SWAlignBatch wraps pg_sw_align_batch: scores plus the two aligned strings per query.  Rows that
+// do not fit `stride` bytes are retried with the reported length.
+func SWAlignBatch(queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
+	nA, nB int, gap int64, stride int) (score []int64, errCode []int32, errPos []int64, alignA, alignB []string, err error) {
+	n := len(qOffsets) - 1
+	t := []byte(template)
+	if len(t) == 0 {
+		t = make([]byte, 1)
+	}
+	qa := C.int32_t(0)
+	if queryIsA {
+		qa = 1
+	}
+	for {
+		score, errCode, errPos = make([]int64, n+1), make([]int32, n+1), make([]int64, n+1)
+		oa, ob := make([]byte, n*stride+1), make([]byte, n*stride+1)
+		ln, st := make([]uint32, n+1), make([]int32, n+1)
+		rc := C.pg_sw_align_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
+			(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
+			(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
+			(*C.int64_t)(unsafe.Pointer(&score[0])), (*C.int32_t)(unsafe.Pointer(&errCode[0])), (*C.int64_t)(unsafe.Pointer(&errPos[0])),
+			(*C.uint8_t)(unsafe.Pointer(&oa[0])), (*C.uint8_t)(unsafe.Pointer(&ob[0])), C.uint64_t(stride),
+			(*C.uint32_t)(unsafe.Pointer(&ln[0])), (*C.int32_t)(unsafe.Pointer(&st[0])))
+		if e := check(rc); e != nil {
+			return nil, nil, nil, nil, nil, e
+		}
+		grow := 0
+		for i := 0; i < n; i++ {
+			if st[i] == 2 && int(ln[i]) > grow {
+				grow = int(ln[i])
+			}
+		}
+		if grow > 0 {
+			stride = grow + 8
+			continue
+		}
+		alignA, alignB = make([]string, n), make([]string, n)
+		for i := 0; i < n; i++ {
+			alignA[i] = string(oa[i*stride : i*stride+int(ln[i])])
+			alignB[i] = string(ob[i*stride : i*stride+int(ln[i])])
+		}
+		return score[:n], errCode[:n], errPos[:n], alignA, alignB, nil
+	}
+}
+
 // TmBatch wraps pg_tm_batch.
 func TmBatch(bases []byte, offsets []uint64, cp, na, mg float64) (tm, dH, dS []float64, status []int32, err error) {
 	n := len(offsets) - 1

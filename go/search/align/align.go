@@ -1,6 +1,7 @@
-// Package align: drop-in for the SCORE of github.com/bebop/poly/search/align.SmithWaterman
-// (search/align/align.go:171-203) backed by libpolyb200.so.  NOT COMPILED HERE.
-// The traceback strings (align.go:205-231) stay with the pure-Go implementation ("next" row).
+// Package align: drop-in for github.com/bebop/poly/search/align.SmithWaterman
+// (search/align/align.go:171-232: score, aligned strings, error) and for the score of
+// NeedlemanWunsch (align.go:100-134,166), backed by libpolyb200.so.  NOT COMPILED HERE.
+// The NeedlemanWunsch traceback strings stay with the pure-Go implementation.
 package align
 
 import (
@@ -75,6 +76,50 @@ func SmithWatermanScore(stringA, stringB string, scoring Scoring) (int, error) {
 		return 0, e[0]
 	}
 	return s[0], nil
+}
+
+// SmithWaterman keeps the reference signature (align.go:171): score, aligned strings, error.
+// The shorter of the two strings must have <= 64 symbols (it rides in registers on the GPU);
+// longer pairs should keep using the pure-Go implementation.
+func SmithWaterman(stringA string, stringB string, scoring Scoring) (int, string, string, error) {
+	lutA, lutB, table, nA, nB := flatten(scoring.SubstitutionMatrix)
+	queryIsA := len(stringA) <= 64
+	q, t := stringA, stringB
+	if !queryIsA {
+		q, t = stringB, stringA
+	}
+	bases, offsets := polyb200.Flatten([]string{q})
+	score, ec, ep, alignA, alignB, err := polyb200.SWAlignBatch(bases, offsets, t, queryIsA, &lutA, &lutB, table, nA, nB,
+		int64(scoring.GapPenalty), 2*len(q)+64)
+	if err != nil {
+		panic(err)
+	}
+	if ec[0] == 1 {
+		_, e := scoring.SubstitutionMatrix.FirstAlphabet.Encode(string(stringA[ep[0]]))
+		return 0, "", "", e
+	} else if ec[0] == 2 {
+		_, e := scoring.SubstitutionMatrix.SecondAlphabet.Encode(string(stringB[ep[0]]))
+		return 0, "", "", e
+	}
+	return int(score[0]), alignA[0], alignB[0], nil
+}
+
+// NeedlemanWunschScore is the score of align.NeedlemanWunsch(stringA, stringB, scoring).
+func NeedlemanWunschScore(stringA, stringB string, scoring Scoring) (int, error) {
+	lutA, lutB, table, nA, nB := flatten(scoring.SubstitutionMatrix)
+	bases, offsets := polyb200.Flatten([]string{stringA})
+	score, ec, ep, err := polyb200.NWScoreBatch(bases, offsets, stringB, true, &lutA, &lutB, table, nA, nB, int64(scoring.GapPenalty))
+	if err != nil {
+		panic(err)
+	}
+	if ec[0] == 1 {
+		_, e := scoring.SubstitutionMatrix.FirstAlphabet.Encode(string(stringA[ep[0]]))
+		return 0, e
+	} else if ec[0] == 2 {
+		_, e := scoring.SubstitutionMatrix.SecondAlphabet.Encode(string(stringB[ep[0]]))
+		return 0, e
+	}
+	return int(score[0]), nil
 }
 
 var _ = alphabet.DNA

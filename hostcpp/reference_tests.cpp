@@ -68,6 +68,22 @@ static void TestSmithWaterman() {  // align_test.go:139-292 (scores)
     auto nuc4 = align::NewSubstitutionMatrix(an, an, {{0, 0, 0, 0, 0}, {0, 5, -4, -4, -4}, {0, -4, 5, -4, -4}, {0, -4, -4, 5, -4}, {0, -4, -4, -4, 5}});
     EXPECT(align::SmithWaterman("GATTACA", "GCATGCT", align::NewScoring(&nuc4, -1)) == 15);
     EXPECT(align::SmithWaterman("GATTACA", "GCATGCU", align::NewScoring(nullptr, -1)) == 2);
+    // aligned strings (align_test.go:167-196, example_test.go:82,110)
+    auto al = align::SmithWatermanAlign("TGTTACGG", "GGTTGACTA", scoring);
+    EXPECT(al.score == 13 && al.alignA == "GTT-AC" && al.alignB == "GTTGAC");
+    al = align::SmithWatermanAlign("ACACACTA", "AGCACACA", scoring);
+    EXPECT(al.score == 17 && al.alignA == "A-CACACTA" && al.alignB == "AGCACAC-A");
+    al = align::SmithWatermanAlign("GATTACA", "GCATGCT", align::NewScoring(&nuc4, -1));
+    EXPECT(al.score == 15 && al.alignA == "GATTAC" && al.alignB == "GCATGC");
+    al = align::SmithWatermanAlign("", "GAT", scoring);
+    EXPECT(al.score == 0 && al.alignA.empty() && al.alignB.empty());
+    // TestNeedlemanWunsch scores (align_test.go:11-137)
+    auto nws = align::NewScoring(&s5, -1);
+    EXPECT(align::NeedlemanWunschScore("GATTACA", "GCATGCU", nws) == 0);
+    EXPECT(align::NeedlemanWunschScore("GATTACA", "GATTACA", nws) == 7);
+    EXPECT(align::NeedlemanWunschScore("GATTACA", "GAT", nws) == -1);
+    EXPECT(align::NeedlemanWunschScore("", "GAT", nws) == -3);
+    EXPECT(align::NeedlemanWunschScore("G", "GATTACA", nws) == -5);
     bool err = false;
     try { align::SmithWaterman("ACGT", "ACGX", scoring); } catch (const align::AlphabetError &e) { err = std::string(e.what()) == "Symbol X not in alphabet"; }
     EXPECT(err);
