@@ -206,6 +206,34 @@ int pg_tm_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t 
                     double na, double mg, double *d_tm, double *d_dh, double *d_ds,
                     int32_t *d_status, void *stream);
 
+/* ---- pcr.DesignPrimersWithOverhangs core -- primers/pcr/pcr.go:44-60 ---------
+ * For each sequence: fwd_len = length of the forward primer (shortest prefix of >= 15 nt of the
+ * upper-cased sequence with MeltingTemp >= target_tm, pcr.go:46-49), rev_len = length of the
+ * reverse primer (reverse complement of the shortest such suffix, pcr.go:50-53).  Every candidate
+ * is evaluated exactly as primers.MeltingTemp would.  status: PG_ITEM_PANIC where the reference
+ * slices out of range (sequence shorter than 15 nt or exhausted before the target is reached),
+ * PG_ITEM_UNSUPPORTED for bytes >= 0x80.  The primer strings themselves (overhang + primer,
+ * pcr.go:55-59) are assembled by the caller from the lengths. */
+int pg_design_primers_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n,
+                            double target_tm, uint32_t *fwd_len, uint32_t *rev_len, int32_t *status);
+
+/* ---- FASTQ ingest -- io/fastq Parser.ParseNext / ParseN, io/fastq/fastq.go:88-99,117-214 -------
+ * (the step before the hot path.)  Parses a whole FASTQ text buffer on the GPU
+ * into the dense bases + offsets layout the sketch entry points take.  Strict 4-line records;
+ * parsing stops at the first record the reference rejects and the records before it are returned
+ * together with the error, as ParseN does: *err_code 0 none, 1 a line of a record is not newline
+ * terminated (EOF inside a record), 2 empty sequence, 3 empty quality, 4 no '@', 5 the reference
+ * panics (empty identifier line, or an optional datum without '='), 6 line longer than the 64 KiB
+ * reader of fastq.Parse; *err_line = 1-based number of the line the reference stops at.
+ * Returns PG_ERR_ARG when a capacity is too small (*n_records / *total_bases hold the needs).
+ * The _dev variant takes device buffers (text, bases, offsets) and host scalars. */
+int pg_fastq_ingest(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
+                    uint64_t *offsets, uint64_t records_cap, uint64_t *n_records,
+                    uint64_t *total_bases, int32_t *err_code, uint64_t *err_line);
+int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                        uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream);
+
 /* ---- synthetic workloads (bench/test tooling, not a reference API) ---
  * kind 0: independent reads  base(i,j) = code(seed, i*L + j)
  * kind 1: family reads       (family = reads per template, 1/64 substitutions)

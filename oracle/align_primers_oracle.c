@@ -228,3 +228,48 @@ int po_sw_align(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb, cons
     free(m);
     return PO_OK;
 }
+
+
+/* io/fastq/fastq.go:88-99 (ParseN) over :117-214 (ParseNext) for a whole in-memory buffer, with the
+ * 64 KiB reader of Parse/Read (fastq.go:54-58).  Records before the first rejected one are
+ * returned; err_code: 0 none, 1 line not newline terminated (io.EOF inside a record), 2 empty
+ * sequence (:179-181), 3 empty quality (:197-199), 4 no '@' (:203-205), 5 the reference panics
+ * (empty identifier line :160, or an optional datum without '=' :166-169), 6 line longer than the
+ * reader buffer (bufio.ErrBufferFull).  err_line = parser.line when the reference returns. */
+int po_fastq_parse(const uint8_t *text, uint64_t n, uint64_t *seq_start, uint64_t *seq_len, uint64_t cap,
+                   uint64_t *n_records, int32_t *err_code, uint64_t *err_line) {
+    uint64_t pos = 0, line = 0, count = 0;
+    *err_code = 0; *err_line = 0;
+    while (pos < n) {                                   /* Peek(1) succeeds, fastq.go:118 */
+        uint64_t lb[4], le[4];
+        int e = 0, no_at = 0;
+        for (int l = 0; l < 4 && !e; l++) {
+            uint64_t q = pos;
+            while (q < n && text[q] != '\n') q++;
+            line++;                                     /* parser.line++ precedes the error check */
+            if (q >= n) { e = 1; break; }               /* ReadSlice: io.EOF -> handleErr */
+            if (q + 1 - pos > 2 * 32 * 1024) { e = 6; break; }
+            lb[l] = pos; le[l] = q; pos = q + 1;
+            if (l == 0) {
+                if (le[0] == lb[0]) { e = 5; break; }   /* string(line)[0] on "" */
+                no_at = text[lb[0]] != '@';
+                uint64_t token = 0; int has_eq = 0;
+                for (uint64_t p = lb[0]; p <= le[0]; p++) {
+                    uint8_t c = p < le[0] ? text[p] : (uint8_t)' ';
+                    if (c == ' ') { if (token >= 1 && !has_eq) { e = 5; break; } token++; has_eq = 0; }
+                    else if (c == '=') has_eq = 1;
+                }
+            } else if (l == 1) {
+                if (le[1] == lb[1]) e = 2;
+            } else if (l == 3) {
+                if (le[3] == lb[3]) e = 3;
+            }
+        }
+        if (!e && no_at) e = 4;
+        if (e) { *err_code = e; *err_line = line; break; }
+        if (count < cap) { seq_start[count] = lb[1]; seq_len[count] = le[1] - lb[1]; }
+        count++;
+    }
+    *n_records = count;
+    return PO_OK;
+}

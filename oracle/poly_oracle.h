@@ -74,6 +74,10 @@ int po_nw_score(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb,
                 const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int n_b,
                 int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos);
 
+/* io/fastq/fastq.go:88-99,117-214 over a whole buffer (see the definition for the error codes). */
+int po_fastq_parse(const uint8_t *text, uint64_t n, uint64_t *seq_start, uint64_t *seq_len, uint64_t cap,
+                   uint64_t *n_records, int32_t *err_code, uint64_t *err_line);
+
 /* transform/transform.go:15-23,78-109. out has room for len bytes. */
 void po_reverse_complement(const uint8_t *seq, int64_t len, uint8_t *out);
 

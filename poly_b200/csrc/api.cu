@@ -698,6 +698,71 @@ int pg_tm_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n, doubl
     return worst;
 }
 
+int pg_design_primers_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n,
+                            double target_tm, uint32_t *fwd_len, uint32_t *rev_len, int32_t *status) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (n == 0) return PG_OK;
+    if (!offsets || !fwd_len || !rev_len) { set_error("null buffer"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g_streams[0];
+    const uint64_t b0 = offsets[0], nbytes = offsets[n] - b0;
+    Tmp d_b(st), d_off(st), d_f(st), d_r(st), d_st(st);
+    if ((rc = d_b.alloc(nbytes)) || (rc = d_off.alloc((n + 1) * 8)) || (rc = d_f.alloc(n * 4)) ||
+        (rc = d_r.alloc(n * 4)) || (rc = d_st.alloc(n * 4)))
+        return rc;
+    if (nbytes) PG_CUDA(cudaMemcpyAsync(d_b.p, bases + b0, nbytes, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_design_primers(d_b.as<uint8_t>() - b0, d_off.as<uint64_t>(), n, target_tm, d_f.as<uint32_t>(),
+                               d_r.as<uint32_t>(), d_st.as<int32_t>(), st);
+    if (rc != PG_OK) return rc;
+    std::vector<int32_t> hst(n);
+    PG_CUDA(cudaMemcpyAsync(fwd_len, d_f.p, n * 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(rev_len, d_r.p, n * 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(hst.data(), d_st.p, n * 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    int worst = PG_OK;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (status) status[i] = hst[i];
+        if (hst[i] == PG_ITEM_PANIC) worst = PG_ERR_PANIC;
+        else if (hst[i] == PG_ITEM_UNSUPPORTED && worst == PG_OK) worst = PG_ERR_UNSUPPORTED;
+    }
+    if (worst == PG_ERR_PANIC) set_error("at least one sequence is exhausted before the target Tm: pcr.DesignPrimers panics (slice bounds out of range)");
+    if (worst == PG_ERR_UNSUPPORTED) set_error("at least one sequence holds a byte >= 0x80 (unsupported)");
+    return worst;
+}
+
+int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                        uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (!n_records || !total_bases || !err_code || !err_line || !d_offsets) { set_error("null buffer"); return PG_ERR_ARG; }
+    return launch_fastq_ingest(d_text, nbytes, d_bases, bases_cap, d_offsets, records_cap, n_records, total_bases, err_code,
+                               err_line, (cudaStream_t)stream);
+}
+
+int pg_fastq_ingest(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
+                    uint64_t *offsets, uint64_t records_cap, uint64_t *n_records,
+                    uint64_t *total_bases, int32_t *err_code, uint64_t *err_line) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (!n_records || !total_bases || !err_code || !err_line || !offsets) { set_error("null buffer"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g_streams[0];
+    Tmp d_text(st), d_bases(st), d_off(st);
+    if ((rc = d_text.alloc(nbytes + 16)) || (rc = d_bases.alloc(bases_cap + 16)) || (rc = d_off.alloc((records_cap + 1) * 8)))
+        return rc;
+    if (nbytes) PG_CUDA(cudaMemcpyAsync(d_text.p, text, nbytes, cudaMemcpyHostToDevice, st));
+    rc = launch_fastq_ingest(d_text.as<uint8_t>(), nbytes, d_bases.as<uint8_t>(), bases_cap, d_off.as<uint64_t>(), records_cap,
+                             n_records, total_bases, err_code, err_line, st);
+    if (rc != PG_OK) return rc;
+    if (*total_bases) PG_CUDA(cudaMemcpyAsync(bases, d_bases.p, *total_bases, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(offsets, d_off.p, (*n_records + 1) * 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------------------
 int pg_synth_reads_dev(uint8_t *d_bases, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
                        uint64_t seed, int32_t kind, uint32_t family, void *stream) {

@@ -73,6 +73,12 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
 int launch_tm(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double cp, double na,
               double mg, double *d_tm, double *d_dh, double *d_ds, int32_t *d_status,
               cudaStream_t st);
+int launch_design_primers(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double target,
+                          uint32_t *d_fwd, uint32_t *d_rev, int32_t *d_status, cudaStream_t st);
+// fastq_ingest.cu
+int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                        uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st);
 // synth.cu
 int launch_synth_reads(uint8_t *d_bases, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
                        uint64_t seed, int kind, uint32_t family, cudaStream_t st);

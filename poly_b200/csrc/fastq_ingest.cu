@@ -1,0 +1,265 @@
+// fastq_ingest.cu -- the step BEFORE the hot path: FASTQ text -> the dense
+// bases + offsets layout the sketch entry points take, on the GPU.
+//
+// Mirrors Parser.ParseNext / ParseN of /root/reference/io/fastq/fastq.go:117-214,88-99 for a whole
+// buffer: strict 4-line records (identifier, sequence, "+", quality), every line newline
+// terminated; parsing stops at the first record the reference would reject and the records before
+// it are returned together with the error (as ParseN does).  Only what the sketch path needs is
+// materialised (the sequences); identifiers / optionals / qualities are validated, not copied.
+//
+//   1. count '\n' per 4 KB block, exclusive scan of the block counts, write newline positions
+//   2. one thread per record: locate its 4 lines, apply the reference's checks in its order
+//   3. exclusive scan of the sequence lengths of the valid prefix -> offsets
+//   4. one warp per record copies its sequence bytes into the dense buffer
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pg {
+
+namespace {
+
+constexpr int FQ_BLOCK_BYTES = 4096;
+constexpr int FQ_THREADS = 256;  // 16 bytes per thread
+constexpr uint64_t FQ_MAX_LINE = 2 * 32 * 1024;  // fastq.go:56 maxLineSize of Parse / Read
+
+__global__ void __launch_bounds__(FQ_THREADS)
+count_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, uint32_t *__restrict__ block_count) {
+    const uint64_t base = (uint64_t)blockIdx.x * FQ_BLOCK_BYTES + threadIdx.x * 16;
+    uint32_t c = 0;
+    for (int j = 0; j < 16; ++j) c += (base + j < n && __ldg(text + base + j) == '\n');
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    __shared__ uint32_t s[FQ_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < FQ_THREADS / 32; ++w) t += s[w];
+        block_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of `in` (n entries) into `out` (n + 1 entries, out[n] = total); one CTA
+template <typename TIn>
+__global__ void __launch_bounds__(1024) scan_kernel(const TIn *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+    __shared__ uint64_t s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t per = (n + 1023) / 1024, lo = min((uint64_t)tid * per, n), hi = min(lo + per, n);
+    uint64_t sum = 0;
+    for (uint64_t i = lo; i < hi; ++i) sum += in[i];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint64_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const uint64_t t = s_part[i]; s_part[i] = run; run += t; }
+        out[n] = run;
+    }
+    __syncthreads();
+    uint64_t run = s_part[tid];
+    for (uint64_t i = lo; i < hi; ++i) { out[i] = run; run += in[i]; }
+}
+
+__global__ void __launch_bounds__(FQ_THREADS)
+write_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__restrict__ block_start,
+                      uint64_t *__restrict__ nl) {
+    const uint64_t base = (uint64_t)blockIdx.x * FQ_BLOCK_BYTES + threadIdx.x * 16;
+    uint32_t mask = 0;
+    for (int j = 0; j < 16; ++j) mask |= (uint32_t)(base + j < n && __ldg(text + base + j) == '\n') << j;
+    const uint32_t c = __popc(mask);
+    uint32_t incl = c;
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)(threadIdx.x & 31) >= d) incl += y;
+    }
+    __shared__ uint32_t s[FQ_THREADS / 32];
+    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += s[w];
+    uint64_t pos = block_start[blockIdx.x] + wbase + incl - c;
+    for (int j = 0; j < 16; ++j)
+        if (mask & (1u << j)) nl[pos++] = base + j;
+}
+
+// error codes (per record and overall)
+enum : int32_t {
+    FQ_OK = 0,
+    FQ_ERR_EOF = 1,        // a line of the record is not newline terminated ("unexepcted EOF encountered")
+    FQ_ERR_EMPTY_SEQ = 2,  // fastq.go:179-181
+    FQ_ERR_EMPTY_QUAL = 3, // fastq.go:197-199
+    FQ_ERR_NO_AT = 4,      // fastq.go:203-205
+    FQ_ERR_PANIC = 5,      // empty identifier line (string(line)[0]) or an optional without '=' (fastq.go:160-170)
+    FQ_ERR_LINE_TOO_LONG = 6  // bufio.ErrBufferFull with the 64 KiB reader of Parse / Read
+};
+
+// One thread per candidate record r: lines 4r .. 4r+3 (a line ends at nl[i]); the last candidate
+// may be incomplete (text after the last newline, or fewer than 4 lines left).
+__global__ void __launch_bounds__(256)
+record_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__restrict__ nl, uint64_t n_lines,
+              uint64_t n_cand, uint32_t *__restrict__ seq_len, uint64_t *__restrict__ seq_start,
+              int32_t *__restrict__ rec_err, uint32_t *__restrict__ rec_err_line, unsigned long long *__restrict__ first_bad) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_cand) return;
+    auto line_begin = [&](uint64_t li) -> uint64_t { return li == 0 ? 0 : nl[li - 1] + 1; };
+    int32_t err = FQ_OK;
+    uint32_t err_line = 0;
+    uint64_t s_beg = 0, s_len = 0;
+    bool no_at = false;
+    for (int l = 0; l < 4 && err == FQ_OK; ++l) {
+        const uint64_t li = 4 * r + l;
+        if (li >= n_lines) {  // no newline: ReadSlice returns io.EOF (with or without trailing bytes)
+            err = FQ_ERR_EOF;  // includes the empty tail: Peek succeeded earlier only if bytes remain
+            err_line = l + 1;
+            break;
+        }
+        const uint64_t b = line_begin(li), e = nl[li];  // [b, e) without the newline
+        if (e + 1 - b > FQ_MAX_LINE) { err = FQ_ERR_LINE_TOO_LONG; err_line = l + 1; break; }
+        if (l == 0) {
+            if (e == b) { err = FQ_ERR_PANIC; err_line = 1; break; }  // string(line)[0] on ""
+            no_at = __ldg(text + b) != '@';
+            // strings.Split(line, " ")[1:]: every datum (also an empty one) must hold '=' (optionalSplits[1])
+            uint32_t token = 0;
+            bool has_eq = false;
+            for (uint64_t p = b; p <= e; ++p) {
+                const uint8_t c = p < e ? __ldg(text + p) : (uint8_t)' ';  // sentinel ends the last token
+                if (c == ' ') {
+                    if (token >= 1 && !has_eq) { err = FQ_ERR_PANIC; err_line = 1; break; }
+                    ++token;
+                    has_eq = false;
+                } else if (c == '=') {
+                    has_eq = true;
+                }
+            }
+        } else if (l == 1) {
+            if (e == b) { err = FQ_ERR_EMPTY_SEQ; err_line = 2; break; }
+            s_beg = b;
+            s_len = e - b;
+        } else if (l == 3) {
+            if (e == b) { err = FQ_ERR_EMPTY_QUAL; err_line = 4; break; }
+        }
+    }
+    if (err == FQ_OK && no_at) { err = FQ_ERR_NO_AT; err_line = 4; }
+    seq_len[r] = err == FQ_OK ? (uint32_t)s_len : 0u;
+    seq_start[r] = s_beg;
+    rec_err[r] = err;
+    rec_err_line[r] = err_line;
+    if (err != FQ_OK) atomicMin(first_bad, (unsigned long long)r);
+}
+
+__global__ void __launch_bounds__(256)
+copy_sequences_kernel(const uint8_t *__restrict__ text, const uint64_t *__restrict__ seq_start,
+                      const uint64_t *__restrict__ offsets, uint64_t n_rec, uint8_t *__restrict__ bases) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += warps) {
+        const uint8_t *src = text + seq_start[r];
+        uint8_t *dst = bases + offsets[r];
+        const uint64_t len = offsets[r + 1] - offsets[r];
+        for (uint64_t i = lane; i < len; i += 32) dst[i] = __ldg(src + i);
+    }
+}
+
+}  // namespace
+
+// Device-resident ingest.  d_bases needs room for `bases_cap` bytes, d_offsets for records_cap + 1
+// entries.  Host outputs: *n_records, *total_bases, *err_code / *err_line (1-based line number in
+// the file of the line the reference stops at).  PG_ERR_ARG if a capacity is too small
+// (*n_records / *total_bases then hold the required sizes).
+int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                        uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st) {
+    *n_records = 0; *total_bases = 0; *err_code = FQ_OK; *err_line = 0;
+    if (nbytes == 0) {
+        if (records_cap + 1 >= 1 && d_offsets) PG_CUDA(cudaMemsetAsync(d_offsets, 0, 8, st));
+        return PG_OK;
+    }
+    const uint64_t nblocks = (nbytes + FQ_BLOCK_BYTES - 1) / FQ_BLOCK_BYTES;
+    uint32_t *d_bcount = nullptr;
+    uint64_t *d_bstart = nullptr;
+    PG_CUDA(cudaMallocAsync(&d_bcount, nblocks * 4, st));
+    PG_CUDA(cudaMallocAsync(&d_bstart, (nblocks + 1) * 8, st));
+    count_newlines_kernel<<<(unsigned)nblocks, FQ_THREADS, 0, st>>>(d_text, nbytes, d_bcount);
+    note_launch("count_newlines_kernel");
+    scan_kernel<uint32_t><<<1, 1024, 0, st>>>(d_bcount, nblocks, d_bstart);
+    note_launch("scan_kernel");
+    uint64_t n_lines = 0;
+    PG_CUDA(cudaMemcpyAsync(&n_lines, d_bstart + nblocks, 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    uint64_t *d_nl = nullptr;
+    PG_CUDA(cudaMallocAsync(&d_nl, std::max<uint64_t>(n_lines, 1) * 8, st));
+    write_newlines_kernel<<<(unsigned)nblocks, FQ_THREADS, 0, st>>>(d_text, nbytes, d_bstart, d_nl);
+    note_launch("write_newlines_kernel");
+    // candidate records: every full group of 4 lines, plus one more if anything is left over
+    uint64_t last_nl_plus1 = 0;
+    if (n_lines) {
+        uint64_t last = 0;
+        PG_CUDA(cudaMemcpyAsync(&last, d_nl + n_lines - 1, 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        last_nl_plus1 = last + 1;
+    }
+    const bool trailing = last_nl_plus1 < nbytes;  // bytes after the last newline
+    const uint64_t n_cand = n_lines / 4 + ((n_lines % 4 != 0 || trailing) ? 1 : 0);
+    int rc = PG_OK;
+    uint32_t *d_len = nullptr, *d_eline = nullptr;
+    uint64_t *d_sstart = nullptr, *d_off_tmp = nullptr;
+    int32_t *d_err = nullptr;
+    unsigned long long *d_first = nullptr;
+    if (n_cand) {
+        PG_CUDA(cudaMallocAsync(&d_len, n_cand * 4, st));
+        PG_CUDA(cudaMallocAsync(&d_eline, n_cand * 4, st));
+        PG_CUDA(cudaMallocAsync(&d_sstart, n_cand * 8, st));
+        PG_CUDA(cudaMallocAsync(&d_err, n_cand * 4, st));
+        PG_CUDA(cudaMallocAsync(&d_first, 8, st));
+        PG_CUDA(cudaMemsetAsync(d_first, 0xff, 8, st));
+        record_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(d_text, nbytes, d_nl, n_lines, n_cand, d_len, d_sstart,
+                                                                       d_err, d_eline, d_first);
+        note_launch("record_kernel");
+        unsigned long long first_bad = ~0ull;
+        PG_CUDA(cudaMemcpyAsync(&first_bad, d_first, 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        uint64_t n_ok = n_cand;
+        if (first_bad != ~0ull) {
+            n_ok = first_bad;
+            int32_t e = 0;
+            uint32_t el = 0;
+            PG_CUDA(cudaMemcpyAsync(&e, d_err + first_bad, 4, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaMemcpyAsync(&el, d_eline + first_bad, 4, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            *err_code = e;
+            *err_line = 4 * first_bad + el;
+        }
+        *n_records = n_ok;
+        if (n_ok > records_cap) {
+            set_error("records_cap %llu < %llu records", (unsigned long long)records_cap, (unsigned long long)n_ok);
+            rc = PG_ERR_ARG;
+        } else {
+            PG_CUDA(cudaMallocAsync(&d_off_tmp, (n_ok + 1) * 8, st));
+            scan_kernel<uint32_t><<<1, 1024, 0, st>>>(d_len, n_ok, d_off_tmp);
+            note_launch("scan_kernel");
+            PG_CUDA(cudaMemcpyAsync(total_bases, d_off_tmp + n_ok, 8, cudaMemcpyDeviceToHost, st));
+            PG_CUDA(cudaStreamSynchronize(st));
+            if (*total_bases > bases_cap) {
+                set_error("bases_cap %llu < %llu bases", (unsigned long long)bases_cap, (unsigned long long)*total_bases);
+                rc = PG_ERR_ARG;
+            } else {
+                PG_CUDA(cudaMemcpyAsync(d_offsets, d_off_tmp, (n_ok + 1) * 8, cudaMemcpyDeviceToDevice, st));
+                if (n_ok) {
+                    const unsigned blocks = (unsigned)std::min<uint64_t>((n_ok + 7) / 8, (uint64_t)sm_count() * 16);
+                    copy_sequences_kernel<<<blocks, 256, 0, st>>>(d_text, d_sstart, d_off_tmp, n_ok, d_bases);
+                    note_launch("copy_sequences_kernel");
+                }
+            }
+        }
+    } else {
+        PG_CUDA(cudaMemsetAsync(d_offsets, 0, 8, st));
+    }
+    cudaError_t e = cudaGetLastError();
+    PG_CUDA(cudaStreamSynchronize(st));
+    for (void *p : {(void *)d_bcount, (void *)d_bstart, (void *)d_nl, (void *)d_len, (void *)d_eline, (void *)d_sstart,
+                    (void *)d_err, (void *)d_first, (void *)d_off_tmp})
+        if (p) cudaFreeAsync(p, st);
+    if (e != cudaSuccess) return cuda_fail(e, "fastq ingest", __FILE__, __LINE__);
+    return rc;
+}
+
+}  // namespace pg

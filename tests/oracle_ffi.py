@@ -48,6 +48,8 @@ def lib():
         L.po_sw_align.restype = C.c_int
         L.po_sw_align.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int64, i64p, C.c_char_p, C.c_char_p, C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
+        L.po_fastq_parse.restype = C.c_int
+        L.po_fastq_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int32), u64p]
         L.po_nw_score.restype = C.c_int
         L.po_nw_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
@@ -147,6 +149,16 @@ def sw_align(a, b, lut_a, lut_b, table, gap):
                            C.byref(sc), oa, ob, cap, C.byref(n), C.byref(ec), C.byref(ep))
     assert rc == PO_OK, rc
     return sc.value, oa.raw[: n.value], ob.raw[: n.value], ec.value, ep.value
+
+
+def fastq_parse(text: bytes):
+    """Returns (sequences list, err_code, err_line) as fastq.Parse would (valid prefix + error)."""
+    cap = text.count(b"\n") // 4 + 2
+    st, ln = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+    n, ec, el = C.c_uint64(0), C.c_int32(0), C.c_uint64(0)
+    rc = lib().po_fastq_parse(text, len(text), st.ctypes.data, ln.ctypes.data, cap, C.byref(n), C.byref(ec), C.byref(el))
+    assert rc == PO_OK
+    return [text[int(st[i]): int(st[i] + ln[i])] for i in range(n.value)], ec.value, el.value
 
 
 def nw_score(a, b, lut_a, lut_b, table, gap):

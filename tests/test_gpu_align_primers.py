@@ -250,3 +250,33 @@ def test_sw_align_batch_vs_oracle(gpu, oracle, maxq, tlen, gap):
             w = oracle.sw_align(a, b, TEST_LUT, TEST_LUT, TEST_MAT, gap)
             assert res[i][3] is None
             assert (res[i][0], res[i][1].encode(), res[i][2].encode()) == (w[0], w[1], w[2]), (i, query_is_a, qs[i])
+
+
+def test_reference_pcr_examples_batched(gpu):
+    """primers/pcr/example_test.go:10-55: DesignPrimers / DesignPrimersWithOverhangs strings from the
+    batched GPU search (pg_design_primers_batch)."""
+    from poly_b200 import pcr
+
+    assert pcr.DesignPrimers(GENE, 55.0) == ("AATAATTACACCGAGATAACACATCATGG", "TTAAGAAAGCGCATTTTCCAGC")
+    assert pcr.DesignPrimersWithOverhangs(GENE, "TTATAGGTCTCATACT", "ATGAAGAGACCATATA", 55.0) == (
+        "TTATAGGTCTCATACTAATAATTACACCGAGATAACACATCATGG", "TATATGGTCTCTTCATTTAAGAAAGCGCATTTTCCAGC")
+    with pytest.raises(IndexError):
+        pcr.DesignPrimers("ACGTACGTAC", 55.0)          # shorter than 15 nt: sequence[0:15] panics
+    with pytest.raises(IndexError):
+        pcr.DesignPrimers("AT" * 12, 95.0)             # exhausted before the target is reached
+
+
+def test_design_primers_batch_vs_oracle(gpu, oracle):
+    from poly_b200 import pcr
+
+    rng = np.random.default_rng(12)
+    genes = [bytes(rng.choice(list(b"ACGTacgtN"), size=int(rng.integers(40, 400)), p=[.22, .22, .22, .22, .02, .02, .02, .02, .04]).astype(np.uint8)) for _ in range(300)]
+    for target in (48.0, 55.0, 62.5):
+        fwd, rev, st = pcr.design_primer_lengths(genes, target)
+        for i, g in enumerate(genes):
+            try:
+                wf, wr = design_primers(oracle.melting_temp, g.decode("latin-1"), target)
+            except (IndexError, ValueError):
+                assert st[i] == 1, i
+                continue
+            assert st[i] == 0 and (fwd[i], rev[i]) == (len(wf), len(wr)), (i, target)

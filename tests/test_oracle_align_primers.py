@@ -105,15 +105,19 @@ def design_primers(melting_temp, sequence, target_tm, fwd_oh="", rev_oh=""):
     """primers/pcr/pcr.go:44-60 restated over a MeltingTemp callable."""
     seq = sequence.upper()
     rc = lambda s: o.reverse_complement(s).decode()
-    fwd = seq[0:15]
+    def sl(lo, hi):  # Go slice expression: out-of-range bounds panic
+        if lo < 0 or hi > len(seq) or lo > hi:
+            raise IndexError("slice bounds out of range")
+        return seq[lo:hi]
+    fwd = sl(0, 15)
     add = 0
     while melting_temp(fwd) < target_tm:
-        fwd = seq[0:15 + add]
+        fwd = sl(0, 15 + add)
         add += 1
-    rev = rc(seq[len(seq) - 15:])
+    rev = rc(sl(len(seq) - 15, len(seq)))
     add = 0
     while melting_temp(rev) < target_tm:
-        rev = rc(seq[len(seq) - (15 + add):])
+        rev = rc(sl(len(seq) - (15 + add), len(seq)))
         add += 1
     return fwd_oh + fwd, rc(rev_oh) + rev
 
