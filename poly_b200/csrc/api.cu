@@ -21,7 +21,6 @@ static std::mutex g_mu;         // serialises the host-pointer entry points
 static int g_device = -1;       // bound device (-1: not initialised)
 static int g_sms = 0;
 static cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
-static cudaEvent_t g_events[3] = {nullptr, nullptr, nullptr};
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -66,12 +65,10 @@ static int init_locked(int device) {
     if (g_device != device) {
         for (int i = 0; i < 3; ++i) {
             if (g_streams[i]) { cudaStreamDestroy(g_streams[i]); g_streams[i] = nullptr; }
-            if (g_events[i]) { cudaEventDestroy(g_events[i]); g_events[i] = nullptr; }
         }
     }
     for (int i = 0; i < 3; ++i) {
         if (!g_streams[i]) PG_CUDA(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
-        if (!g_events[i]) PG_CUDA(cudaEventCreateWithFlags(&g_events[i], cudaEventDisableTiming));
     }
     g_device = device;
     g_sms = prop.multiProcessorCount;
@@ -158,7 +155,6 @@ int pg_shutdown(void) {
         for (int i = 0; i < 3; ++i) {
             g_in[i].release(); g_out[i].release(); g_aux[i].release(); g_st[i].release();
             if (g_streams[i]) { cudaStreamDestroy(g_streams[i]); g_streams[i] = nullptr; }
-            if (g_events[i]) { cudaEventDestroy(g_events[i]); g_events[i] = nullptr; }
         }
     }
     g_device = -1;

@@ -79,3 +79,37 @@ print(json.dumps({"kernel": "K4 sw_score (cfg5)", "queries": m, "qlen": PL, "tle
 tm = torch.empty(m, dtype=torch.float64, device=dev)
 ms = timed(lambda: _lib.check(L.pg_tm_batch_dev(pr.data_ptr(), off.data_ptr(), m, 500e-9, 50e-3, 0.0, tm.data_ptr(), None, None, None, st)), iters=10)
 print(json.dumps({"kernel": "K5 tm (cfg5)", "primers": m, "ms": ms, "mprimers_per_s": m / ms / 1e3, "first3": tm[:3].cpu().tolist()}))
+
+# ---- widened rows: FASTQ ingest (8f.2) and batched DesignPrimers (8f.3) ------------------------
+import ctypes as C
+from poly_b200 import pcr  # noqa: E402
+
+nrec = 2_000_000
+reads = synth.independent_reads(nrec, 150).reshape(nrec, 150)
+rec = np.empty((nrec, 16 + 151 + 2 + 151), dtype=np.uint8)
+rec[:, :16] = np.frombuffer(b"@r runid=0 ch=1\n", dtype=np.uint8)
+rec[:, 16:166] = reads
+rec[:, 166] = 10
+rec[:, 167:169] = np.frombuffer(b"+\n", dtype=np.uint8)
+rec[:, 169:319] = 73
+rec[:, 319] = 10
+text = torch.from_numpy(rec.reshape(-1)).to(dev)
+d_bases = torch.empty(nrec * 150 + 64, dtype=torch.uint8, device=dev)
+d_off = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
+nr, tot, ec, el = C.c_uint64(0), C.c_uint64(0), C.c_int32(0), C.c_uint64(0)
+
+
+def ingest():
+    _lib.check(L.pg_fastq_ingest_dev(text.data_ptr(), text.numel(), d_bases.data_ptr(), d_bases.numel(), d_off.data_ptr(), nrec,
+                                     C.byref(nr), C.byref(tot), C.byref(ec), C.byref(el), st))
+
+
+ms = timed(ingest, iters=3)
+ok = nr.value == nrec and ec.value == 0 and bool(torch.equal(d_bases[: nrec * 150].cpu(), torch.from_numpy(reads.reshape(-1))))
+print(json.dumps({"kernel": "FASTQ ingest (8f.2)", "records": nrec, "text_GB": text.numel() / 1e9, "ms": ms,
+                  "text_GBps": text.numel() / ms / 1e6, "matches_generator": ok}))
+genes = [bytes(r) for r in synth.independent_reads(100_000, 300).reshape(100_000, 300)]
+import time as _t
+t0 = _t.perf_counter(); fl, rl, stt = pcr.design_primer_lengths(genes, 55.0); dt = _t.perf_counter() - t0
+print(json.dumps({"kernel": "DesignPrimers batch (8f.3, host API incl. copies)", "genes": len(genes), "ms": dt * 1e3,
+                  "mean_fwd_len": float(fl.mean()), "mean_rev_len": float(rl.mean()), "panics": int((stt != 0).sum())}))
