@@ -507,20 +507,26 @@ int pg_mash_distance_block(const uint32_t *sketches, uint64_t n, int32_t s, uint
     Tmp d_sk(st);
     if ((rc = d_sk.alloc(n * (uint64_t)s * 4))) return rc;
     PG_CUDA(cudaMemcpyAsync(d_sk.p, sketches, n * (uint64_t)s * 4, cudaMemcpyHostToDevice, st));
-    const uint64_t rows_per = std::max<uint64_t>(8, ((64ull << 20) / n) & ~7ull);  // <= 64 Mi pairs per pass
-    for (uint64_t rb = row_begin; rb < row_end; rb += rows_per) {
+    // one plan (sortedness + join index) for the whole call; row blocks of <= 64 Mi pairs per pass
+    DistancePlan plan;
+    rc = distance_plan_create(d_sk.as<uint32_t>(), n, s, st, &plan);
+    const uint64_t rows_per = std::max<uint64_t>(8, ((64ull << 20) / n) & ~7ull);
+    for (uint64_t rb = row_begin; rb < row_end && rc == PG_OK; rb += rows_per) {
         const uint64_t re = std::min(row_end, rb + rows_per);
         Tmp d_same(st), d_dist(st);
-        if (same && (rc = d_same.alloc((re - rb) * n * 4))) return rc;
-        if (distance && (rc = d_dist.alloc((re - rb) * n * 8))) return rc;
-        rc = launch_distance_block(d_sk.as<uint32_t>(), n, s, rb, re, same ? d_same.as<uint32_t>() : nullptr,
-                                   distance ? d_dist.as<double>() : nullptr, st);
-        if (rc != PG_OK) return rc;
-        if (same) PG_CUDA(cudaMemcpyAsync(same + (rb - row_begin) * n, d_same.p, (re - rb) * n * 4, cudaMemcpyDeviceToHost, st));
-        if (distance) PG_CUDA(cudaMemcpyAsync(distance + (rb - row_begin) * n, d_dist.p, (re - rb) * n * 8, cudaMemcpyDeviceToHost, st));
-        PG_CUDA(cudaStreamSynchronize(st));
+        if (same && (rc = d_same.alloc((re - rb) * n * 4))) break;
+        if (distance && (rc = d_dist.alloc((re - rb) * n * 8))) break;
+        rc = distance_plan_rows(plan, rb, re, same ? d_same.as<uint32_t>() : nullptr, distance ? d_dist.as<double>() : nullptr, st);
+        if (rc != PG_OK) break;
+        cudaError_t e = cudaSuccess;
+        if (same) e = cudaMemcpyAsync(same + (rb - row_begin) * n, d_same.p, (re - rb) * n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && distance)
+            e = cudaMemcpyAsync(distance + (rb - row_begin) * n, d_dist.p, (re - rb) * n * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = cuda_fail(e, "distance block copy", __FILE__, __LINE__);
     }
-    return PG_OK;
+    distance_plan_destroy(plan, st);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------

@@ -54,9 +54,28 @@ int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_
                             cudaStream_t st);
 int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin,
                           uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st);
-// distance_join.cu (ascending sketches only; *done == false -> caller falls back to the pairwise kernel)
-int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin, uint64_t row_end,
-                         uint32_t *d_same, double *d_dist, cudaStream_t st, bool *done);
+// distance_join.cu (ascending sketches only): bucketed (value, id) index, built once per sketch
+// set and reused for every row block
+struct JoinIndex {
+    uint64_t *entries = nullptr, *start = nullptr;
+    uint64_t nb = 0, n = 0;
+    int s = 0;
+    bool ok = false;
+};
+int join_build(const uint32_t *d_sk, uint64_t n, int s, cudaStream_t st, JoinIndex *ix);
+int join_emit(const JoinIndex &ix, uint64_t row_begin, uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st);
+void join_free(JoinIndex &ix, cudaStream_t st);
+// distance.cu: a plan = sortedness flags (+ join index when every sketch is ascending)
+struct DistancePlan {
+    const uint32_t *d_sk = nullptr;
+    uint64_t n = 0;
+    int s = 0;
+    uint8_t *d_flag = nullptr;
+    JoinIndex join;
+};
+int distance_plan_create(const uint32_t *d_sk, uint64_t n, int s, cudaStream_t st, DistancePlan *plan);
+int distance_plan_rows(const DistancePlan &plan, uint64_t row_begin, uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st);
+void distance_plan_destroy(DistancePlan &plan, cudaStream_t st);
 // sw_score.cu
 int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen,
                     const uint8_t *d_t, uint64_t tlen, int query_is_a, const int16_t *lut_a,

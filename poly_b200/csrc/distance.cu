@@ -204,45 +204,55 @@ int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_
     return PG_OK;
 }
 
-int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin,
-                          uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st) {
-    if (row_end <= row_begin || n == 0) return PG_OK;
+int distance_plan_create(const uint32_t *d_sk, uint64_t n, int s, cudaStream_t st, DistancePlan *plan) {
+    plan->d_sk = d_sk; plan->n = n; plan->s = s; plan->d_flag = nullptr; plan->join = JoinIndex();
+    if (n == 0) return PG_OK;
     if (s <= 0) {
         set_error("distance over sketches of size %d: the reference panics (Sketches[-1])", s);
         return PG_ERR_PANIC;
+    }
+    PG_CUDA(cudaMallocAsync(&plan->d_flag, n + 8, st));
+    uint32_t *d_unsorted = reinterpret_cast<uint32_t *>(plan->d_flag + ((n + 3) & ~3ull));
+    PG_CUDA(cudaMemsetAsync(d_unsorted, 0, 4, st));
+    sorted_flag_kernel<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 4096), 256, 0, st>>>(d_sk, n, s, plan->d_flag, d_unsorted);
+    PG_LAUNCH_CHECK("sorted_flag_kernel");
+    // every sketch ascending (the select regime, L-k >= s): inverted-index join, output-sensitive
+    uint32_t n_unsorted = 1;
+    PG_CUDA(cudaMemcpyAsync(&n_unsorted, d_unsorted, 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    if (n_unsorted == 0 && !getenv("PG_K3_PAIRWISE")) return join_build(d_sk, n, s, st, &plan->join);
+    return PG_OK;
+}
+
+void distance_plan_destroy(DistancePlan &plan, cudaStream_t st) {
+    join_free(plan.join, st);
+    if (plan.d_flag) cudaFreeAsync(plan.d_flag, st);
+    plan.d_flag = nullptr;
+}
+
+int distance_plan_rows(const DistancePlan &plan, uint64_t row_begin, uint64_t row_end, uint32_t *d_same, double *d_dist,
+                       cudaStream_t st) {
+    const uint64_t n = plan.n;
+    const int s = plan.s;
+    if (row_end <= row_begin || n == 0) return PG_OK;
+    const uint64_t rows = row_end - row_begin;
+    if (plan.join.ok) {
+        uint32_t *same = d_same;
+        if (!same) PG_CUDA(cudaMallocAsync(&same, rows * n * 4, st));  // distances only: counts are a temporary
+        int rc = join_emit(plan.join, row_begin, row_end, same, d_dist, st);
+        if (!d_same) cudaFreeAsync(same, st);
+        return rc;
     }
     const size_t smem = (size_t)2 * BT * s * 4;
     if (smem > 200 * 1024) {
         set_error("sketch size %d too large for the all-pairs tile kernel", s);
         return PG_ERR_UNSUPPORTED;
     }
-    uint8_t *d_flag = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_flag, n + 8, st));
-    uint32_t *d_unsorted = reinterpret_cast<uint32_t *>(d_flag + ((n + 3) & ~3ull));
-    PG_CUDA(cudaMemsetAsync(d_unsorted, 0, 4, st));
-    sorted_flag_kernel<<<(unsigned)std::min<uint64_t>((n + 7) / 8, 4096), 256, 0, st>>>(d_sk, n, s, d_flag, d_unsorted);
-    PG_LAUNCH_CHECK("sorted_flag_kernel");
-    // every sketch ascending (the select regime, L-k >= s): inverted-index join, output-sensitive
-    if (d_same) {
-        uint32_t n_unsorted = 1;
-        PG_CUDA(cudaMemcpyAsync(&n_unsorted, d_unsorted, 4, cudaMemcpyDeviceToHost, st));
-        PG_CUDA(cudaStreamSynchronize(st));
-        if (n_unsorted == 0 && !getenv("PG_K3_PAIRWISE")) {
-            bool done = false;
-            int rc = launch_distance_join(d_sk, n, s, row_begin, row_end, d_same, d_dist, st, &done);
-            if (rc != PG_OK || done) {
-                cudaFreeAsync(d_flag, st);
-                return rc;
-            }
-        }
-    }
     static size_t configured = 0;
     if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(distance_block_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(cudaFuncSetAttribute(distance_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const uint64_t rows = row_end - row_begin;
     const uint64_t gy_total = (rows + BT - 1) / BT;
     const uint64_t gx = (n + BT - 1) / BT;
     if (gx > 0x7fffffffull) { set_error("too many sketches"); return PG_ERR_ARG; }
@@ -251,13 +261,22 @@ int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_
         const uint64_t rb = row_begin + y0 * BT;
         dim3 grid((unsigned)gx, (unsigned)gy);
         distance_block_kernel<<<grid, 256, smem, st>>>(
-            d_sk, n, (uint32_t)s, rb, row_end, d_flag,
+            plan.d_sk, n, (uint32_t)s, rb, row_end, plan.d_flag,
             d_same ? d_same + (rb - row_begin) * n : nullptr,
             d_dist ? d_dist + (rb - row_begin) * n : nullptr);
         PG_LAUNCH_CHECK("distance_block_kernel");
     }
-    PG_CUDA(cudaFreeAsync(d_flag, st));
     return PG_OK;
+}
+
+int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin,
+                          uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st) {
+    if (row_end <= row_begin || n == 0) return PG_OK;
+    DistancePlan plan;
+    int rc = distance_plan_create(d_sk, n, s, st, &plan);
+    if (rc == PG_OK) rc = distance_plan_rows(plan, row_begin, row_end, d_same, d_dist, st);
+    distance_plan_destroy(plan, st);
+    return rc;
 }
 
 }  // namespace pg

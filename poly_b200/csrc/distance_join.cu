@@ -155,13 +155,12 @@ __global__ void same_to_distance_kernel(const uint32_t *__restrict__ same, uint6
 
 }  // namespace
 
-// Returns PG_OK and sets *done = true if the join ran; *done = false means "not applicable"
-// (skewed data) and the caller must use the pairwise kernel.  All sketches must be ascending.
-int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin, uint64_t row_end,
-                         uint32_t *d_same, double *d_dist, cudaStream_t st, bool *done) {
-    *done = false;
+// Builds the bucketed (value, id) index of n ascending sketches.  ix->ok == false means "not
+// applicable" (skewed data: a bucket would not fit shared memory) and the caller must use the
+// pairwise kernel.
+int join_build(const uint32_t *d_sk, uint64_t n, int s, cudaStream_t st, JoinIndex *ix) {
+    ix->ok = false; ix->entries = nullptr; ix->start = nullptr; ix->nb = 0; ix->n = n; ix->s = s;
     const uint64_t total = n * (uint64_t)s;
-    const uint64_t rows = row_end - row_begin;
     if (total == 0 || n > 0xffffffffull) return PG_OK;
     uint32_t *d_scalars = nullptr;  // [0] vmax, [1] largest bucket
     PG_CUDA(cudaMallocAsync(&d_scalars, 8, st));
@@ -169,14 +168,12 @@ int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_b
     const unsigned sms = (unsigned)sm_count();
     max_value_kernel<<<sms * 4, 256, 0, st>>>(d_sk, n, (uint32_t)s, d_scalars);
     note_launch("max_value_kernel");
-
     uint64_t nb = 1;
     while (nb * 2048 < total) nb <<= 1;
     nb = std::min<uint64_t>(std::max<uint64_t>(nb, 1), 1u << 22);
-    uint32_t *d_hist = nullptr, *d_cursor = nullptr;
-    uint64_t *d_start = nullptr, *d_entries = nullptr;
-    int rc = PG_OK;
-    for (int attempt = 0; attempt < 3 && !*done; ++attempt) {
+    for (int attempt = 0; attempt < 3 && !ix->ok; ++attempt) {
+        uint32_t *d_hist = nullptr, *d_cursor = nullptr;
+        uint64_t *d_start = nullptr;
         PG_CUDA(cudaMallocAsync(&d_hist, nb * 4, st));
         PG_CUDA(cudaMallocAsync(&d_cursor, nb * 4, st));
         PG_CUDA(cudaMallocAsync(&d_start, (nb + 1) * 8, st));
@@ -190,37 +187,51 @@ int launch_distance_join(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_b
         PG_CUDA(cudaMemcpyAsync(&largest, d_scalars + 1, 4, cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
         if (largest <= JOIN_CAP) {
+            uint64_t *d_entries = nullptr;
             PG_CUDA(cudaMallocAsync(&d_entries, total * 8, st));
             scatter_kernel<<<sms * 16, 256, 0, st>>>(d_sk, total, (uint32_t)s, d_scalars, (uint32_t)nb, d_start, d_cursor, d_entries);
             note_launch("scatter_kernel");
-            PG_CUDA(cudaMemsetAsync(d_same, 0, rows * n * 4, st));
-            static bool configured = false;
-            if (!configured) {
-                PG_CUDA(cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JOIN_CAP * 8));
-                configured = true;
-            }
-            bucket_join_kernel<<<(unsigned)std::min<uint64_t>(nb, (uint64_t)sms * 12), JOIN_THREADS, JOIN_CAP * 8, st>>>(
-                d_entries, d_start, (uint32_t)nb, n, row_begin, row_end, d_same);
-            note_launch("bucket_join_kernel");
-            if (d_dist) {
-                same_to_distance_kernel<<<sms * 8, 256, 0, st>>>(d_same, rows * n, (uint32_t)s, d_dist);
-                note_launch("same_to_distance_kernel");
-            }
-            cudaFreeAsync(d_entries, st);
-            *done = true;
+            ix->entries = d_entries; ix->start = d_start; ix->nb = nb; ix->ok = true;
+        } else {
+            cudaFreeAsync(d_start, st);
         }
         cudaFreeAsync(d_hist, st);
         cudaFreeAsync(d_cursor, st);
-        cudaFreeAsync(d_start, st);
-        if (!*done) {
+        if (!ix->ok) {
             if (nb >= (1u << 22)) break;
             nb = std::min<uint64_t>(nb * 8, 1u << 22);
         }
     }
     cudaFreeAsync(d_scalars, st);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) rc = cuda_fail(e, "distance join", __FILE__, __LINE__);
-    return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "distance join build", __FILE__, __LINE__);
+    return PG_OK;
+}
+
+// Rows [row_begin, row_end) of the matching-count matrix from a built index.
+int join_emit(const JoinIndex &ix, uint64_t row_begin, uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st) {
+    const uint64_t rows = row_end - row_begin;
+    const unsigned sms = (unsigned)sm_count();
+    PG_CUDA(cudaMemsetAsync(d_same, 0, rows * ix.n * 4, st));
+    static bool configured = false;
+    if (!configured) {
+        PG_CUDA(cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JOIN_CAP * 8));
+        configured = true;
+    }
+    bucket_join_kernel<<<(unsigned)std::min<uint64_t>(ix.nb, (uint64_t)sms * 12), JOIN_THREADS, JOIN_CAP * 8, st>>>(
+        ix.entries, ix.start, (uint32_t)ix.nb, ix.n, row_begin, row_end, d_same);
+    PG_LAUNCH_CHECK("bucket_join_kernel");
+    if (d_dist) {
+        same_to_distance_kernel<<<sms * 8, 256, 0, st>>>(d_same, rows * ix.n, (uint32_t)ix.s, d_dist);
+        PG_LAUNCH_CHECK("same_to_distance_kernel");
+    }
+    return PG_OK;
+}
+
+void join_free(JoinIndex &ix, cudaStream_t st) {
+    if (ix.entries) cudaFreeAsync(ix.entries, st);
+    if (ix.start) cudaFreeAsync(ix.start, st);
+    ix.entries = nullptr; ix.start = nullptr; ix.ok = false;
 }
 
 }  // namespace pg

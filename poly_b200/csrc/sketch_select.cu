@@ -303,7 +303,10 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
             const uint32_t npos = nb ? ch + 4 * (nb - 1) : 0;
             for (uint32_t p = tid; p < npos; p += SEL_THREADS) m.kv[p] = mm3_kmix(smem_window(stage, head + p));
             __syncthreads();
-            // phase 2: one k-mer per thread
+            // phase 2: one k-mer per thread.  Until the first prune every hash is a candidate and
+            // its slot is known (base + position): no ballot / shared-memory atomic is needed.
+            const bool unfiltered = limit == (1ull << 32);
+            const uint32_t base_cnt = m.misc[0];
             for (uint32_t i0 = 0; i0 < ch; i0 += SEL_THREADS) {
                 const uint32_t i = i0 + tid;
                 bool take = false;
@@ -316,14 +319,20 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
                     take = (uint64_t)h < limit;
                     if (c0 + i == 0) h_first = h;  // thread 0 only
                 }
-                const uint32_t b = __ballot_sync(0xffffffffu, take);
-                const uint32_t lane = tid & 31u;
-                uint32_t base = 0;
-                if (lane == 0 && b) base = atomicAdd(&m.misc[0], __popc(b));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) m.cand[base + __popc(b & ((1u << lane) - 1u))] = h;
+                if (unfiltered) {
+                    if (i < ch) m.cand[base_cnt + i] = h;
+                } else {
+                    const uint32_t b = __ballot_sync(0xffffffffu, take);
+                    const uint32_t lane = tid & 31u;
+                    uint32_t base = 0;
+                    if (lane == 0 && b) base = atomicAdd(&m.misc[0], __popc(b));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) m.cand[base + __popc(b & ((1u << lane) - 1u))] = h;
+                }
                 if (s == 1 && i < ch && c0 + i > 0) atomicMin(&m.misc[5], h);
             }
+            __syncthreads();
+            if (unfiltered && tid == 0) m.misc[0] = base_cnt + ch;
             __syncthreads();
         }
 
