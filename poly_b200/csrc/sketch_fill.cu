@@ -96,25 +96,38 @@ sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, const SketchDst ds
     constexpr bool LUT = TAIL == 1;
     static_assert(NB >= 1, "fast path needs k >= 4");
 
+    // A CTA holds R/32 warps; every warp owns one tile of 32 reads with its own mbarrier, input
+    // and output staging and bulk store, so the warps of a CTA never wait for each other (they
+    // only share the 1 KB tail table: with R == 64 ten warps fit an SM instead of nine).
+    constexpr int NW = R / 32;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem);
-    uint8_t *s_in = smem + 16;
-    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_in + k1_in_bytes(R, L));
+    __shared__ __align__(8) uint64_t s_bar[NW + 1];  // [w]: tile of warp w; [NW]: the table
+    const uint32_t wid = threadIdx.x >> 5;
+    const uint32_t tid = threadIdx.x & 31u;  // lane == read within the warp's tile
+    const uint32_t warp_smem = k1_in_bytes(32, L) + 32u * nk * 4u;
+    uint8_t *s_in = smem + wid * warp_smem;
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(s_in + k1_in_bytes(32, L));
+    uint64_t *bar = &s_bar[wid];
 
-    const uint32_t tid = threadIdx.x;
-    const uint64_t tile = blockIdx.x;
-    const uint32_t in_bytes = R * L;  // multiple of 16 (host guarantees)
+    const uint64_t tile = (uint64_t)blockIdx.x * NW + wid;
+    const uint32_t in_bytes = 32u * L;  // multiple of 16 (host guarantees)
 
-    if (tid == 0) {
-        mbar_init(bar, 1);
+    if (threadIdx.x == 0) {
+        for (int w = 0; w <= NW; ++w) mbar_init(&s_bar[w], 1);
         fence_mbar_init();
-        mbar_expect_tx(bar, in_bytes + (LUT ? 1024u : 0u));
-        bulk_g2s(s_in, bases + tile * in_bytes, in_bytes, bar);
-        if (LUT) bulk_g2s(s_lut, &g_kmix_byte, 1024u, bar);
+        if (LUT) {
+            mbar_expect_tx(&s_bar[NW], 1024u);
+            bulk_g2s(s_lut, &g_kmix_byte, 1024u, &s_bar[NW]);
+        }
     }
-    __syncthreads();  // barrier init visible to the waiters
+    __syncthreads();  // barrier init visible to everyone (the only CTA-wide barrier)
+    if (tid == 0) {
+        mbar_expect_tx(bar, in_bytes);
+        bulk_g2s(s_in, bases + tile * in_bytes, in_bytes, bar);
+    }
     mbar_wait(bar, 0);
+    if (LUT) mbar_wait(&s_bar[NW], 0);
 
     // my read: bytes [tid*L, tid*L+L) of the tile, realigned to words on the fly
     const uint32_t b0 = tid * L;
@@ -160,12 +173,13 @@ sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, const SketchDst ds
 
     // hand the staged tile to the async proxy and bulk-store it (positional, mash.go:81-84)
     fence_async_smem();
-    __syncthreads();
+    __syncwarp();
     if (tid == 0) {
         // one bulk store per destination: the local buffer, or (fused all-gather) the gathered
         // buffer of every rank, peers reached through their NVLink-mapped addresses
-        for (int p = 0; p < dst.n; ++p)
-            bulk_s2g(dst.ptr[p] + tile * (uint64_t)(R * nk), s_out, R * nk * 4u);  // multiple of 16 (R % 4 == 0)
+#pragma unroll
+        for (int p = 0; p < PG_MAX_PEERS; ++p)  // static indices: the struct stays in parameter space
+            if (p < dst.n) bulk_s2g(dst.ptr[p] + tile * (uint64_t)(32u * nk), s_out, 32u * nk * 4u);  // multiple of 16
         bulk_wait_read0();
     }
 }
@@ -214,7 +228,7 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
 template <int K, int R>
 static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
                      const SketchDst &dst, cudaStream_t st) {
-    const size_t smem = 16 + k1_in_bytes(R, L) + (size_t)R * nk * 4;
+    const size_t smem = (size_t)(R / 32) * (k1_in_bytes(32, L) + (size_t)32 * nk * 4);
     static size_t configured = 0;  // per instantiation (one process = one device)
     if (smem > configured) {
         PG_CUDA(cudaFuncSetAttribute(sketch_fill_uniform_kernel<K, R>,
@@ -241,9 +255,8 @@ static int dispatch_k1(int k, const uint8_t *d_bases, uint64_t n_tiles, uint32_t
     }
 }
 
-// reads per tile == threads per CTA.  32 (one warp per CTA, ~10 CTAs per SM at L=150, k=21)
-// measured fastest: 64 loses ~9 % (profiles/r01_k1_tuning.md).
-constexpr int K1_R = 32;
+// warps (= independent 32-read tiles) per CTA
+constexpr int K1_WARPS = 1;
 
 static int launch_fill_generic(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t ulen,
                                uint64_t n_reads, uint64_t first_read, int k, int s, uint32_t flags,
@@ -273,25 +286,29 @@ int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, 
     bool aligned = ((uintptr_t)d_bases % 16 == 0) && ((uintptr_t)d_out % 16 == 0);
     if (extra)
         for (int p = 0; p < extra->n; ++p) aligned = aligned && ((uintptr_t)extra->ptr[p] % 16 == 0);
-    const size_t smem = 16 + k1_in_bytes(K1_R, L) + (size_t)K1_R * nk * 4;
-    if (compact && aligned && nk > 0 && (K1_R * (uint64_t)L) % 16 == 0 && smem <= 200 * 1024 &&
-        n_reads >= K1_R) {
-        const uint64_t tiles = n_reads / K1_R;
+    // tiles of 32 reads; a CTA runs NW of them on NW independent warps (PG_K1_WARPS=1|2, A/B knob)
+    static const int nw_pref = [] { const char *e = getenv("PG_K1_WARPS"); return e ? atoi(e) : K1_WARPS; }();
+    const size_t smem1 = k1_in_bytes(32, L) + (size_t)32 * nk * 4;
+    if (compact && aligned && nk > 0 && (32 * (uint64_t)L) % 16 == 0 && smem1 <= 100 * 1024 && n_reads >= 32) {
+        const uint64_t tiles = n_reads / 32;
         bool handled = false;
         uint64_t t0 = 0;
-        while (t0 < tiles) {  // grid.x limit
-            const uint64_t nt = std::min<uint64_t>(tiles - t0, 0x7fffffffull);
+        while (t0 < tiles) {
+            const int nw = (nw_pref == 2 && tiles - t0 >= 2) ? 2 : 1;
+            // grid.x limit; with 2 warps per CTA an odd last tile takes a 1-warp launch
+            const uint64_t nt = std::min<uint64_t>((tiles - t0) / nw, 0x7fffffffull) * nw;
             SketchDst dst;
             dst.n = extra ? extra->n : 1;
             for (int p = 0; p < dst.n; ++p)
-                dst.ptr[p] = (extra ? extra->ptr[p] : d_out) + t0 * K1_R * (uint64_t)nk;
-            int rc = dispatch_k1<K1_R>(k, d_bases + t0 * K1_R * (uint64_t)L, nt, L, nk, dst, st, &handled);
+                dst.ptr[p] = (extra ? extra->ptr[p] : d_out) + t0 * 32 * (uint64_t)nk;
+            int rc = nw == 2 ? dispatch_k1<64>(k, d_bases + t0 * 32 * (uint64_t)L, nt / 2, L, nk, dst, st, &handled)
+                             : dispatch_k1<32>(k, d_bases + t0 * 32 * (uint64_t)L, nt, L, nk, dst, st, &handled);
             if (rc != PG_OK) return rc;
             if (!handled) break;
             t0 += nt;
         }
         if (handled) {
-            done = tiles * K1_R;
+            done = tiles * 32;
             if (d_status) PG_CUDA(cudaMemsetAsync(d_status, 0, done * sizeof(int32_t), st));
         }
     }
