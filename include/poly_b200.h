@@ -181,6 +181,16 @@ int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_
                       int64_t *err_pos, uint8_t *align_a, uint8_t *align_b, uint64_t out_stride,
                       uint32_t *align_len, int32_t *status);
 
+/* align.NeedlemanWunsch in full (align.go:100-166): same interface; the traceback starts at
+ * (len(a), len(b)) and runs while both indices are positive (align.go:141), so a leading rest of
+ * one string is not emitted, exactly as in the reference. */
+int pg_nw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table,
+                      int32_t n_a, int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code,
+                      int64_t *err_pos, uint8_t *align_a, uint8_t *align_b, uint64_t out_stride,
+                      uint32_t *align_len, int32_t *status);
+
 /* ---- align.NeedlemanWunsch score -- search/align/align.go:100-134 (fill) and :166 --------
  * (a "next" row of SURVEY.md 8f).  Same arguments and error semantics as the Smith-Waterman
  * entry points; score = matrix[len(a)][len(b)] of the global alignment (gap ramps on the first

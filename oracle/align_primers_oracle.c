@@ -273,3 +273,44 @@ int po_fastq_parse(const uint8_t *text, uint64_t n, uint64_t *seq_start, uint64_
     *n_records = count;
     return PO_OK;
 }
+
+/* search/align/align.go:100-166 in full: fill, traceback from (la, lb) while BOTH indices are
+ * positive (align.go:141: the loop stops as soon as one string is exhausted, the leading rest of
+ * the other string is not emitted), diagonal > up > else-left (align.go:146-159), strings built by
+ * appending and reversed at the end (align.go:162-164). */
+int po_nw_align(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb, const int16_t *lut_a,
+                const int16_t *lut_b, const int64_t *table, int n_b, int64_t gap, int64_t *score,
+                uint8_t *out_a, uint8_t *out_b, int64_t cap, int64_t *out_len, int32_t *err_code,
+                int64_t *err_pos) {
+    const int64_t W = lb + 1;
+    int64_t *m = (int64_t *)calloc((size_t)((la + 1) * W), sizeof(int64_t));
+    if (!m) return -100;
+    *err_code = 0; *err_pos = -1; *out_len = 0;
+    for (int64_t i = 1; i <= la; i++) m[i * W] = m[(i - 1) * W] + gap;   /* align.go:115-117 */
+    for (int64_t j = 1; j <= lb; j++) m[j] = m[j - 1] + gap;             /* align.go:120-122 */
+    for (int64_t i = 1; i <= la; i++)
+        for (int64_t j = 1; j <= lb; j++) {
+            int64_t s = 0;
+            int e = cell_score(a[i - 1], b[j - 1], lut_a, lut_b, table, n_b, &s);
+            if (e) { *err_code = e; *err_pos = e == 1 ? i - 1 : j - 1; *score = 0; free(m); return PO_OK; }
+            m[i * W + j] = max64(m[(i - 1) * W + j - 1] + s, max64(m[(i - 1) * W + j] + gap, m[i * W + j - 1] + gap));
+        }
+    int64_t n = 0, i = la, j = lb;
+    while (i > 0 && j > 0) {                                             /* align.go:141 */
+        int64_t s = 0;
+        cell_score(a[i - 1], b[j - 1], lut_a, lut_b, table, n_b, &s);
+        if (n >= cap) { free(m); return -101; }
+        if (m[i * W + j] == m[(i - 1) * W + j - 1] + s) { out_a[n] = a[i - 1]; out_b[n] = b[j - 1]; i--; j--; }
+        else if (m[i * W + j] == m[(i - 1) * W + j] + gap) { out_a[n] = a[i - 1]; out_b[n] = '-'; i--; }
+        else { out_a[n] = '-'; out_b[n] = b[j - 1]; j--; }
+        n++;
+    }
+    for (int64_t t = 0; t < n / 2; t++) {
+        uint8_t x = out_a[t]; out_a[t] = out_a[n - 1 - t]; out_a[n - 1 - t] = x;
+        x = out_b[t]; out_b[t] = out_b[n - 1 - t]; out_b[n - 1 - t] = x;
+    }
+    *out_len = n;
+    *score = m[la * W + lb];
+    free(m);
+    return PO_OK;
+}

@@ -69,6 +69,12 @@ int po_sw_align(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb, cons
                 uint8_t *out_a, uint8_t *out_b, int64_t cap, int64_t *out_len, int32_t *err_code,
                 int64_t *err_pos);
 
+/* search/align/align.go:100-166 in full (score + the two aligned strings). */
+int po_nw_align(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb, const int16_t *lut_a,
+                const int16_t *lut_b, const int64_t *table, int n_b, int64_t gap, int64_t *score,
+                uint8_t *out_a, uint8_t *out_b, int64_t cap, int64_t *out_len, int32_t *err_code,
+                int64_t *err_pos);
+
 /* search/align/align.go:100-166, score only. */
 int po_nw_score(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb,
                 const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int n_b,

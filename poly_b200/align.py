@@ -150,9 +150,10 @@ def NeedlemanWunsch(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) ->
     return scores[0]
 
 
-def SmithWatermanAligns(queries: Sequence[BytesLike], template: BytesLike, scoring: Scoring, query_is_a: bool = True):
-    """Batched full align.SmithWaterman: [(score, alignA, alignB, err)] per query (stringA = query
-    when query_is_a, else stringA = template)."""
+def SmithWatermanAligns(queries: Sequence[BytesLike], template: BytesLike, scoring: Scoring, query_is_a: bool = True,
+                        global_alignment: bool = False):
+    """Batched full align.SmithWaterman (or NeedlemanWunsch with global_alignment=True):
+    [(score, alignA, alignB, err)] per query (stringA = query when query_is_a, else the template)."""
     m = scoring.SubstitutionMatrix
     lut_a, lut_b = m.FirstAlphabet.byte_lut(), m.SecondAlphabet.byte_lut()
     table = np.ascontiguousarray(m.scores, dtype=np.int64)
@@ -160,12 +161,13 @@ def SmithWatermanAligns(queries: Sequence[BytesLike], template: BytesLike, scori
     bases, offsets = flatten(queries)
     n = len(queries)
     maxq = max((len(_as_bytes(q)) for q in queries), default=0)
-    stride = max(2 * maxq + 64, 64)
+    stride = max(2 * maxq + 64, 64) if not global_alignment else maxq + len(t) + 8
+    fn = _lib.lib().pg_nw_align_batch if global_alignment else _lib.lib().pg_sw_align_batch
     while True:
         score, ec, ep = np.zeros(n, np.int64), np.zeros(n, np.int32), np.zeros(n, np.int64)
         oa, ob = np.zeros((n, stride), np.uint8), np.zeros((n, stride), np.uint8)
         ln, st = np.zeros(n, np.uint32), np.zeros(n, np.int32)
-        rc = _lib.lib().pg_sw_align_batch(bases.ctypes.data, offsets.ctypes.data, n, t.ctypes.data, len(t), int(query_is_a),
+        rc = fn(bases.ctypes.data, offsets.ctypes.data, n, t.ctypes.data, len(t), int(query_is_a),
                                           lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[0], table.shape[1],
                                           scoring.GapPenalty, score.ctypes.data, ec.ctypes.data, ep.ctypes.data, oa.ctypes.data,
                                           ob.ctypes.data, stride, ln.ctypes.data, st.ctypes.data)
@@ -193,6 +195,19 @@ def SmithWatermanAlign(stringA: BytesLike, stringB: BytesLike, scoring: Scoring)
         score, sa, sb, err = SmithWatermanAligns([a], b, scoring, query_is_a=True)[0]
     else:
         score, sa, sb, err = SmithWatermanAligns([b], a, scoring, query_is_a=False)[0]
+    if err is not None:
+        raise err
+    return score, sa, sb
+
+
+def NeedlemanWunschAlign(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> Tuple[int, str, str]:
+    """align.NeedlemanWunsch(stringA, stringB, scoring) -> (score, alignA, alignB) (align.go:100-166),
+    including the reference's loop condition (the traceback stops when one string is exhausted)."""
+    a, b = _as_bytes(stringA), _as_bytes(stringB)
+    if len(a) <= 64:
+        score, sa, sb, err = SmithWatermanAligns([a], b, scoring, query_is_a=True, global_alignment=True)[0]
+    else:
+        score, sa, sb, err = SmithWatermanAligns([b], a, scoring, query_is_a=False, global_alignment=True)[0]
     if err is not None:
         raise err
     return score, sa, sb

@@ -607,7 +607,7 @@ int pg_nw_score_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_
                             score, err_code, err_pos);
 }
 
-int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+static int align_strings_host(int global, const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
                       const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
                       const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
                       int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos,
@@ -638,7 +638,7 @@ int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_
     PG_CUDA(cudaMemsetAsync(d_st.p, 0, n_queries * 4, st));
     rc = launch_sw_align(d_q.as<uint8_t>() - q0, d_off.as<uint64_t>(), n_queries, maxq, d_t.as<uint8_t>(), templ_len, query_is_a,
                          lut_a, lut_b, table, n_a, n_b, gap, d_sc.as<int64_t>(), d_ec.as<int32_t>(), d_ep.as<int64_t>(),
-                         d_a.as<uint8_t>(), d_b.as<uint8_t>(), out_stride, d_len.as<uint32_t>(), d_st.as<int32_t>(), st);
+                         d_a.as<uint8_t>(), d_b.as<uint8_t>(), out_stride, d_len.as<uint32_t>(), d_st.as<int32_t>(), st, global);
     if (rc != PG_OK) return rc;
     PG_CUDA(cudaMemcpyAsync(score, d_sc.p, n_queries * 8, cudaMemcpyDeviceToHost, st));
     if (err_code) PG_CUDA(cudaMemcpyAsync(err_code, d_ec.p, n_queries * 4, cudaMemcpyDeviceToHost, st));
@@ -649,6 +649,25 @@ int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_
     if (status) PG_CUDA(cudaMemcpyAsync(status, d_st.p, n_queries * 4, cudaMemcpyDeviceToHost, st));
     PG_CUDA(cudaStreamSynchronize(st));
     return PG_OK;
+}
+
+int pg_sw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
+                      int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos,
+                      uint8_t *align_a, uint8_t *align_b, uint64_t out_stride, uint32_t *align_len,
+                      int32_t *status) {
+    return align_strings_host(0, queries, q_offsets, n_queries, templ, templ_len, query_is_a, lut_a, lut_b, table, n_a, n_b, gap,
+                              score, err_code, err_pos, align_a, align_b, out_stride, align_len, status);
+}
+int pg_nw_align_batch(const uint8_t *queries, const uint64_t *q_offsets, uint64_t n_queries,
+                      const uint8_t *templ, uint64_t templ_len, int32_t query_is_a,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int32_t n_a,
+                      int32_t n_b, int64_t gap, int64_t *score, int32_t *err_code, int64_t *err_pos,
+                      uint8_t *align_a, uint8_t *align_b, uint64_t out_stride, uint32_t *align_len,
+                      int32_t *status) {
+    return align_strings_host(1, queries, q_offsets, n_queries, templ, templ_len, query_is_a, lut_a, lut_b, table, n_a, n_b, gap,
+                              score, err_code, err_pos, align_a, align_b, out_stride, align_len, status);
 }
 
 // ---------------------------------------------------------------------------------

@@ -35,11 +35,12 @@ struct AlignParams {
     const uint8_t *t;
     uint64_t tlen;
     int query_is_a, n_q, n_t, gap;
+    int global;           // 1: Needleman-Wunsch traceback (align.go:136-166) instead of Smith-Waterman
     uint32_t W;           // ring columns
     uint64_t out_stride;  // bytes per aligned string
 };
 
-template <int ROWS>
+template <int ROWS, bool GLOBAL>
 __global__ void __launch_bounds__(AL_THREADS)
 sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t *__restrict__ lut_t,
                 const int *__restrict__ tab, const int64_t *__restrict__ score, const int32_t *__restrict__ err,
@@ -65,7 +66,9 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
         qbeg = p.qoff[qi];
         qlen = (uint32_t)(p.qoff[qi + 1] - qbeg);
         B = err[qi] ? 0 : (int)score[qi];
-        active = B > 0;  // B == 0: maxScore never updated, the traceback loop does not run
+        // SW: B == 0 means maxScore was never updated and the traceback loop does not run.
+        // NW: the loop runs while both indices are positive (align.go:141).
+        active = GLOBAL ? (!err[qi] && qlen > 0 && p.tlen > 0) : B > 0;
         if (!active) {
             out_len[qi] = 0;
             status[qi] = PG_ITEM_OK;
@@ -87,7 +90,8 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
 #pragma unroll
     for (int i = 0; i < ROWS; ++i) col[i] = 0;
     uint32_t bq = 0xffffffffu, bt = 0xffffffffu;  // 1-based query / template index of the end cell
-    for (uint64_t t0 = 0; t0 < p.tlen; t0 += AL_TCHUNK) {
+    if (GLOBAL) { bq = qlen; bt = (uint32_t)p.tlen; }  // NW starts at (len(a), len(b))
+    for (uint64_t t0 = 0; !GLOBAL && t0 < p.tlen; t0 += AL_TCHUNK) {
         const uint32_t tc = (uint32_t)min((uint64_t)AL_TCHUNK, p.tlen - t0);
         __syncthreads();
         for (uint32_t j = tid; j < tc; j += AL_THREADS) {
@@ -126,7 +130,8 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
     const uint32_t W = p.W;
     const uint32_t first_kept = active ? (bt > W ? bt - W + 1 : 1) : 0;  // 1-based template index
 #pragma unroll
-    for (int i = 0; i < ROWS; ++i) col[i] = 0;
+    for (int i = 0; i < ROWS; ++i) col[i] = GLOBAL ? (i + 1) * gap : 0;
+    int edge = 0;  // NW: H[0][j-1]
     for (uint64_t t0 = 0; t0 < p.tlen; t0 += AL_TCHUNK) {
         const uint32_t tc = (uint32_t)min((uint64_t)AL_TCHUNK, p.tlen - t0);
         __syncthreads();
@@ -142,14 +147,21 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
                 const uint32_t ct = (uint32_t)(t0 + j) + 1;
                 const bool keep = ct >= first_kept;
                 int *slot = ring + ((uint64_t)(ct % W) * ROWS) * p.n + b;
-                int diag = 0, up = 0;
+                int diag = GLOBAL ? edge : 0, up = GLOBAL ? edge + gap : 0;
+                if (GLOBAL) edge += gap;
 #pragma unroll
                 for (int i = 0; i < ROWS; ++i) {
                     if (i < (int)qlen) {
                         const int old = col[i];
-                        int v = __viaddmax_s32(diag, s_tab[qrow[i] + tj], 0);
-                        v = __viaddmax_s32(old, gap, v);
-                        v = __viaddmax_s32(up, gap, v);
+                        int v;
+                        if (GLOBAL) {
+                            v = __viaddmax_s32(diag, s_tab[qrow[i] + tj], old + gap);  // align.go:132-135
+                            v = __viaddmax_s32(up, gap, v);
+                        } else {
+                            v = __viaddmax_s32(diag, s_tab[qrow[i] + tj], 0);
+                            v = __viaddmax_s32(old, gap, v);
+                            v = __viaddmax_s32(up, gap, v);
+                        }
                         if (keep) slot[(uint64_t)i * p.n] = v;
                         diag = old;
                         up = v;
@@ -163,7 +175,7 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
 
     // ---- walk: align.go:205-229 ----------------------------------------------------------
     auto H = [&](uint32_t cq, uint32_t ct, bool &outside) -> int {
-        if (cq == 0 || ct == 0) return 0;
+        if (cq == 0 || ct == 0) return GLOBAL ? (int)(cq + ct) * gap : 0;  // NW gap ramps on the first row / column
         if (ct < first_kept) { outside = true; return 0; }
         return ring[((uint64_t)(ct % W) * ROWS + (cq - 1)) * p.n + b];
     };
@@ -171,7 +183,7 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
     uint32_t cq = bq, ct = bt, len = 0;
     bool outside = false, overflow = false;
     int h = H(cq, ct, outside);
-    while (h > 0 && !outside) {
+    while ((GLOBAL ? (cq > 0 && ct > 0) : h > 0) && !outside) {
         const uint8_t qc = __ldg(p.q + qbeg + cq - 1), tc_ = __ldg(p.t + ct - 1);
         const int lq = lut_q[qc], lt = lut_t[tc_];
         const int sc = (lq < 0 || lt < 0) ? 0 : s_tab[lq * p.n_t + lt];
@@ -189,7 +201,7 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
             ca = p.query_is_a ? qc : tc_;
             cb = '-';
             if (p.query_is_a) --cq; else --ct;
-        } else if (h == h_left + gap) {     // align.go:224-228
+        } else if (GLOBAL || h == h_left + gap) {  // align.go:224-228 (SW) / the plain else of align.go:155-159 (NW)
             ca = '-';
             cb = p.query_is_a ? tc_ : qc;
             if (p.query_is_a) --ct; else --cq;
@@ -214,17 +226,17 @@ sw_align_kernel(AlignParams p, const int16_t *__restrict__ lut_q, const int16_t 
     status[qi] = overflow ? PG_ITEM_UNSUPPORTED : PG_ITEM_OK;
 }
 
-template <int ROWS>
+template <int ROWS, bool GLOBAL>
 int run_align(AlignParams p, const int16_t *d_lut_q, const int16_t *d_lut_t, const int *d_tab, const int64_t *d_score,
               const int32_t *d_err, uint8_t *d_a, uint8_t *d_b, uint32_t *d_len, int32_t *d_status, cudaStream_t st) {
     if (p.n == 0) return PG_OK;
     int *d_ring = nullptr;
     PG_CUDA(cudaMallocAsync(&d_ring, (size_t)p.W * ROWS * p.n * sizeof(int), st));
     const size_t smem = AL_TCHUNK + 512 + (size_t)p.n_q * p.n_t * sizeof(int);
-    PG_CUDA(cudaFuncSetAttribute(sw_align_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sw_align_kernel<ROWS><<<(unsigned)((p.n + AL_THREADS - 1) / AL_THREADS), AL_THREADS, smem, st>>>(
+    PG_CUDA(cudaFuncSetAttribute(sw_align_kernel<ROWS, GLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sw_align_kernel<ROWS, GLOBAL><<<(unsigned)((p.n + AL_THREADS - 1) / AL_THREADS), AL_THREADS, smem, st>>>(
         p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_ring, d_a, d_b, d_len, d_status);
-    note_launch("sw_align_kernel");
+    note_launch(GLOBAL ? "nw_align_kernel" : "sw_align_kernel");
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(d_ring, st);
     if (e != cudaSuccess) return cuda_fail(e, "sw_align_kernel", __FILE__, __LINE__);
@@ -240,7 +252,7 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
                     const int16_t *lut_b, const int64_t *table, int n_a, int n_b, int64_t gap,
                     int64_t *d_score, int32_t *d_err, int64_t *d_errpos, uint8_t *d_align_a,
                     uint8_t *d_align_b, uint64_t out_stride, uint32_t *d_len, int32_t *d_status,
-                    cudaStream_t st) {
+                    cudaStream_t st, int global) {
     if (nq == 0) return PG_OK;
     if (max_qlen > 64) {
         set_error("aligned strings are implemented for queries of <= 64 symbols (got %llu)", (unsigned long long)max_qlen);
@@ -249,12 +261,12 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
     int64_t amax = 0;
     for (int i = 0; i < n_a * n_b; ++i) amax = std::max<int64_t>(amax, table[i] < 0 ? -table[i] : table[i]);
     const int64_t agap = gap < 0 ? -gap : gap;
-    if ((long double)amax * 64 + (long double)std::max(amax, agap) >= 2.0e9L) {
+    if ((global ? (long double)std::max(amax, agap) * (long double)(tlen + 66) : (long double)amax * 64 + (long double)std::max(amax, agap)) >= 2.0e9L) {
         set_error("aligned strings need scores that fit 32 bits");
         return PG_ERR_UNSUPPORTED;
     }
     int rc = launch_sw_score(d_q, d_qoff, nq, max_qlen, d_t, tlen, query_is_a, lut_a, lut_b, table, n_a, n_b, gap,
-                             d_score, d_err, d_errpos, st, 0);
+                             d_score, d_err, d_errpos, st, global);
     if (rc != PG_OK) return rc;
 
     AlignParams p;
@@ -262,6 +274,7 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
     p.n_q = query_is_a ? n_a : n_b;
     p.n_t = query_is_a ? n_b : n_a;
     p.gap = (int)gap;
+    p.global = global;
     p.out_stride = out_stride;
     const int16_t *lut_q = query_is_a ? lut_a : lut_b, *lut_t = query_is_a ? lut_b : lut_a;
     std::vector<uint8_t> blob(1024 + (size_t)p.n_q * p.n_t * sizeof(int));
@@ -279,16 +292,19 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
     const int *d_tab = reinterpret_cast<const int *>(d_blob + 1024);
 
     const int rows = max_qlen <= 32 ? 32 : 64;
-    const uint32_t W0 = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(tlen, 1), 2 * rows + 32);
+    // NW walks the whole matrix: keep every column
+    const uint32_t W0 = global ? (uint32_t)std::max<uint64_t>(tlen, 1) : (uint32_t)std::min<uint64_t>(std::max<uint64_t>(tlen, 1), 2 * rows + 32);
     // batches bounded by ~1 GiB of ring
-    const uint64_t per = std::max<uint64_t>(AL_THREADS, ((1ull << 30) / ((uint64_t)W0 * rows * 4)) / AL_THREADS * AL_THREADS);
+    const uint64_t per = std::max<uint64_t>(1, ((1ull << 30) / ((uint64_t)W0 * rows * 4)));
     for (uint64_t q0 = 0; q0 < nq && rc == PG_OK; q0 += per) {
         p.q_first = q0; p.n = std::min<uint64_t>(per, nq - q0); p.W = W0;
-        rc = rows == 32 ? run_align<32>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st)
-                        : run_align<64>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st);
+        rc = global ? (rows == 32 ? run_align<32, true>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st)
+                                  : run_align<64, true>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st))
+                    : (rows == 32 ? run_align<32, false>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st)
+                                  : run_align<64, false>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st));
     }
     // retries with a full-length window (rare: long gap runs)
-    if (rc == PG_OK && W0 < tlen) {
+    if (rc == PG_OK && !global && W0 < tlen) {
         std::vector<int32_t> hst(nq);
         PG_CUDA(cudaMemcpyAsync(hst.data(), d_status, nq * 4, cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -302,8 +318,8 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
             const uint64_t per2 = std::max<uint64_t>(1, (1ull << 30) / (tlen * rows * 4));
             for (uint64_t r0 = 0; r0 < redo.size() && rc == PG_OK; r0 += per2) {
                 p.qlist = d_list + r0; p.q_first = 0; p.n = std::min<uint64_t>(per2, redo.size() - r0); p.W = (uint32_t)tlen;
-                rc = rows == 32 ? run_align<32>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st)
-                                : run_align<64>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st);
+                rc = rows == 32 ? run_align<32, false>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st)
+                                : run_align<64, false>(p, d_lut_q, d_lut_t, d_tab, d_score, d_err, d_align_a, d_align_b, d_len, d_status, st);
             }
             PG_CUDA(cudaStreamSynchronize(st));
             cudaFreeAsync(d_list, st);

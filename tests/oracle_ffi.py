@@ -50,6 +50,8 @@ def lib():
                                   C.c_int64, i64p, C.c_char_p, C.c_char_p, C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
         L.po_fastq_parse.restype = C.c_int
         L.po_fastq_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int32), u64p]
+        L.po_nw_align.restype = C.c_int
+        L.po_nw_align.argtypes = L.po_sw_align.argtypes
         L.po_nw_score.restype = C.c_int
         L.po_nw_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
@@ -136,7 +138,12 @@ def sw_score(a, b, lut_a, lut_b, table, gap):
     return sc.value, mr.value, mc.value, ec.value, ep.value
 
 
-def sw_align(a, b, lut_a, lut_b, table, gap):
+def nw_align(a, b, lut_a, lut_b, table, gap):
+    """Returns (score, alignA, alignB, err_code, err_pos) of the full align.NeedlemanWunsch."""
+    return sw_align(a, b, lut_a, lut_b, table, gap, _fn="po_nw_align")
+
+
+def sw_align(a, b, lut_a, lut_b, table, gap, _fn="po_sw_align"):
     """Returns (score, alignA, alignB, err_code, err_pos) of the full align.SmithWaterman."""
     a, b = _b(a), _b(b)
     lut_a = np.ascontiguousarray(lut_a, dtype=np.int16)
@@ -145,7 +152,7 @@ def sw_align(a, b, lut_a, lut_b, table, gap):
     cap = len(a) + len(b) + 1
     oa, ob = C.create_string_buffer(cap), C.create_string_buffer(cap)
     sc, n, ep, ec = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int32(0)
-    rc = lib().po_sw_align(a, len(a), b, len(b), lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[1], gap,
+    rc = getattr(lib(), _fn)(a, len(a), b, len(b), lut_a.ctypes.data, lut_b.ctypes.data, table.ctypes.data, table.shape[1], gap,
                            C.byref(sc), oa, ob, cap, C.byref(n), C.byref(ec), C.byref(ep))
     assert rc == PO_OK, rc
     return sc.value, oa.raw[: n.value], ob.raw[: n.value], ec.value, ep.value

@@ -280,3 +280,34 @@ def test_design_primers_batch_vs_oracle(gpu, oracle):
                 assert st[i] == 1, i
                 continue
             assert st[i] == 0 and (fwd[i], rev[i]) == (len(wf), len(wr)), (i, target)
+
+
+def test_reference_nw_alignment_strings(gpu, oracle):
+    """ExampleNeedlemanWunsch (search/align/example_test.go:10-47): score 0, G-ATTACA / GCA-TGCU;
+    plus the reference's loop condition (traceback stops when one string is exhausted)."""
+    a5 = align.NewAlphabet(["A", "C", "G", "T", "U"])
+    sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, 2 * np.eye(5, dtype=np.int64) - 1), -1)
+    assert align.NeedlemanWunschAlign("GATTACA", "GCATGCU", sc) == (0, "G-ATTACA", "GCA-TGCU")
+    assert align.NeedlemanWunschAlign("GATTACA", "GATTACA", sc) == (7, "GATTACA", "GATTACA")
+    assert align.NeedlemanWunschAlign("", "GAT", sc) == (-3, "", "")
+    l5 = lut(["A", "C", "G", "T", "U"])
+    m5 = 2 * np.eye(5, dtype=np.int64) - 1
+    for a, b in [("GATTACA", "GAT"), ("G", "GATTACA"), ("G", "A"), ("GAT", "GATTACA"), ("GCATGCU", "GATTACA")]:
+        w = oracle.nw_align(a, b, l5, l5, m5, -1)
+        assert align.NeedlemanWunschAlign(a, b, sc) == (w[0], w[1].decode(), w[2].decode()), (a, b)
+
+
+@pytest.mark.parametrize("maxq,tlen,gap", [(25, 600, -2), (40, 300, -1), (64, 150, -3), (10, 50, 0)])
+def test_nw_align_batch_vs_oracle(gpu, oracle, maxq, tlen, gap):
+    rng = np.random.default_rng(maxq + tlen)
+    nq = 80
+    qs = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, maxq + 1))).astype(np.uint8)) for _ in range(nq - 1)]
+    qs.append(bytes(rng.choice(list(b"ACGT"), size=maxq).astype(np.uint8)))
+    t = bytes(rng.choice(list(b"ACGT"), size=tlen).astype(np.uint8))
+    sc = align.NewScoring(SC.SubstitutionMatrix, gap)
+    for query_is_a in (True, False):
+        res = align.SmithWatermanAligns(qs, t, sc, query_is_a=query_is_a, global_alignment=True)
+        for i in range(nq):
+            a, b = (qs[i], t) if query_is_a else (t, qs[i])
+            w = oracle.nw_align(a, b, TEST_LUT, TEST_LUT, TEST_MAT, gap)
+            assert res[i][3] is None and (res[i][0], res[i][1].encode(), res[i][2].encode()) == (w[0], w[1], w[2]), (i, query_is_a)
