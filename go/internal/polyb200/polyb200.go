@@ -128,9 +128,20 @@ func NWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA b
 	return score[:n], errCode[:n], errPos[:n], check(rc)
 }
 
+// NWAlignBatch wraps pg_nw_align_batch (same contract as SWAlignBatch).
+func NWAlignBatch(queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
+	nA, nB int, gap int64, stride int) ([]int64, []int32, []int64, []string, []string, error) {
+	return alignBatch(true, queries, qOffsets, template, queryIsA, lutA, lutB, table, nA, nB, gap, stride)
+}
+
 // SWAlignBatch wraps pg_sw_align_batch: scores plus the two aligned strings per query.  Rows that
 // do not fit `stride` bytes are retried with the reported length.
 func SWAlignBatch(queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
+	nA, nB int, gap int64, stride int) ([]int64, []int32, []int64, []string, []string, error) {
+	return alignBatch(false, queries, qOffsets, template, queryIsA, lutA, lutB, table, nA, nB, gap, stride)
+}
+
+func alignBatch(global bool, queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
 	nA, nB int, gap int64, stride int) (score []int64, errCode []int32, errPos []int64, alignA, alignB []string, err error) {
 	n := len(qOffsets) - 1
 	t := []byte(template)
@@ -145,12 +156,22 @@ func SWAlignBatch(queries []byte, qOffsets []uint64, template string, queryIsA b
 		score, errCode, errPos = make([]int64, n+1), make([]int32, n+1), make([]int64, n+1)
 		oa, ob := make([]byte, n*stride+1), make([]byte, n*stride+1)
 		ln, st := make([]uint32, n+1), make([]int32, n+1)
-		rc := C.pg_sw_align_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
-			(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
-			(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
-			(*C.int64_t)(unsafe.Pointer(&score[0])), (*C.int32_t)(unsafe.Pointer(&errCode[0])), (*C.int64_t)(unsafe.Pointer(&errPos[0])),
-			(*C.uint8_t)(unsafe.Pointer(&oa[0])), (*C.uint8_t)(unsafe.Pointer(&ob[0])), C.uint64_t(stride),
-			(*C.uint32_t)(unsafe.Pointer(&ln[0])), (*C.int32_t)(unsafe.Pointer(&st[0])))
+		var rc C.int
+		if global {
+			rc = C.pg_nw_align_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
+				(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
+				(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
+				(*C.int64_t)(unsafe.Pointer(&score[0])), (*C.int32_t)(unsafe.Pointer(&errCode[0])), (*C.int64_t)(unsafe.Pointer(&errPos[0])),
+				(*C.uint8_t)(unsafe.Pointer(&oa[0])), (*C.uint8_t)(unsafe.Pointer(&ob[0])), C.uint64_t(stride),
+				(*C.uint32_t)(unsafe.Pointer(&ln[0])), (*C.int32_t)(unsafe.Pointer(&st[0])))
+		} else {
+			rc = C.pg_sw_align_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
+				(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
+				(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
+				(*C.int64_t)(unsafe.Pointer(&score[0])), (*C.int32_t)(unsafe.Pointer(&errCode[0])), (*C.int64_t)(unsafe.Pointer(&errPos[0])),
+				(*C.uint8_t)(unsafe.Pointer(&oa[0])), (*C.uint8_t)(unsafe.Pointer(&ob[0])), C.uint64_t(stride),
+				(*C.uint32_t)(unsafe.Pointer(&ln[0])), (*C.int32_t)(unsafe.Pointer(&st[0])))
+		}
 		if e := check(rc); e != nil {
 			return nil, nil, nil, nil, nil, e
 		}

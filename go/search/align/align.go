@@ -1,7 +1,7 @@
 // Package align: drop-in for github.com/bebop/poly/search/align.SmithWaterman
 // (search/align/align.go:171-232: score, aligned strings, error) and for the score of
 // NeedlemanWunsch (align.go:100-134,166), backed by libpolyb200.so.  NOT COMPILED HERE.
-// The NeedlemanWunsch traceback strings stay with the pure-Go implementation.
+// Both need the shorter string to have <= 64 symbols; longer pairs keep the pure-Go path.
 package align
 
 import (
@@ -91,6 +91,30 @@ func SmithWaterman(stringA string, stringB string, scoring Scoring) (int, string
 	bases, offsets := polyb200.Flatten([]string{q})
 	score, ec, ep, alignA, alignB, err := polyb200.SWAlignBatch(bases, offsets, t, queryIsA, &lutA, &lutB, table, nA, nB,
 		int64(scoring.GapPenalty), 2*len(q)+64)
+	if err != nil {
+		panic(err)
+	}
+	if ec[0] == 1 {
+		_, e := scoring.SubstitutionMatrix.FirstAlphabet.Encode(string(stringA[ep[0]]))
+		return 0, "", "", e
+	} else if ec[0] == 2 {
+		_, e := scoring.SubstitutionMatrix.SecondAlphabet.Encode(string(stringB[ep[0]]))
+		return 0, "", "", e
+	}
+	return int(score[0]), alignA[0], alignB[0], nil
+}
+
+// NeedlemanWunsch keeps the reference signature (align.go:100): score, aligned strings, error.
+func NeedlemanWunsch(stringA string, stringB string, scoring Scoring) (int, string, string, error) {
+	lutA, lutB, table, nA, nB := flatten(scoring.SubstitutionMatrix)
+	queryIsA := len(stringA) <= 64
+	q, t := stringA, stringB
+	if !queryIsA {
+		q, t = stringB, stringA
+	}
+	bases, offsets := polyb200.Flatten([]string{q})
+	score, ec, ep, alignA, alignB, err := polyb200.NWAlignBatch(bases, offsets, t, queryIsA, &lutA, &lutB, table, nA, nB,
+		int64(scoring.GapPenalty), len(q)+len(t)+8)
 	if err != nil {
 		panic(err)
 	}
