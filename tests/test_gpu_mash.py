@@ -353,3 +353,31 @@ def test_cfg3_full_size_properties(gpu, oracle):
     a = oracle.OracleMash(k, s); a.Sketches[:] = got[0]
     b = oracle.OracleMash(k, s); b.Sketches[:] = got[1]
     assert same[0, 1] == a.SimilarityCount(b)[0]
+
+
+def test_randomized_differential_sketch(gpu, oracle):
+    """120 random (k, s, L, n) combinations over all dispatch paths (TMA tiles, generic fill,
+    select with bucket sort-select / radix fallback, odd sketch sizes, reads shorter than k)."""
+    rng = np.random.default_rng(2026)
+    ks = [0, 1, 3, 4, 7, 11, 13, 15, 16, 17, 19, 20, 21, 23, 24, 25, 27, 29, 31, 32, 33, 40]
+    for trial in range(120):
+        k = int(rng.choice(ks))
+        L = int(rng.choice([0, 1, k, k + 1, 36, 64, 100, 150, 151, 152, 301, 1000, 2500]))
+        s = int(rng.choice([2, 3, 5, 9, 10, 64, 127, 128, 129, 1000, 1001, 2000]))
+        n = int(rng.choice([1, 31, 32, 33, 64, 97]))
+        alpha = [b"ACGT", b"AC", bytes(range(256)), b"A"][trial % 4]
+        reads = rng.choice(list(alpha), size=n * L).astype(np.uint8) if L else np.zeros(0, np.uint8)
+        got = mash.sketch_uniform(reads, n, L, k, s)
+        rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=1)
+        assert rc == 0
+        cnt = min(max(L - k, 0), s)
+        assert np.array_equal(got, want[:, :cnt]), (k, s, L, n, trial)
+    # ragged batches through the offsets entry point
+    for trial in range(20):
+        k = int(rng.choice([4, 13, 21, 31])); s = int(rng.choice([7, 64, 1000]))
+        lens = rng.integers(0, 400, int(rng.integers(1, 80)))
+        seqs = [bytes(rng.choice(list(b"ACGTN"), size=int(l)).astype(np.uint8)) for l in lens]
+        bases, offsets = mash.flatten(seqs)
+        out, count, status = mash.sketch_arrays(bases, offsets, k, s, pad_zero=True)
+        rc, want = oracle.sketch_batch(bases, offsets, k, s, variant=1)
+        assert rc == 0 and not status.any() and np.array_equal(out, want), (k, s, trial)
