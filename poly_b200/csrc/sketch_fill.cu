@@ -183,6 +183,105 @@ sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, const SketchDst ds
         bulk_wait_read0();
     }
 }
+
+// ---- K1r: the same walk for RAGGED reads (every read in the fill regime) --------------------
+// A warp owns 32 consecutive reads; their bytes [offsets[r0], offsets[r0+32]) are contiguous and
+// arrive by one TMA bulk copy (16-byte aligned body; the < 16 tail bytes by plain loads).  Each
+// thread walks its own read with its own length, so lanes only diverge at the end of the shorter
+// reads.  Output rows have a common stride (>= the longest row); the words beyond a row's count
+// are written as zeros (the zero tail of a fresh Mash, as far as the stride reaches), so the whole
+// [32][stride] tile leaves as one bulk store.
+template <int K>
+__global__ void __launch_bounds__(32)
+sketch_fill_ragged_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                          uint32_t *__restrict__ out, uint32_t stride, uint32_t in_cap,
+                          uint32_t *__restrict__ count, int32_t *__restrict__ status, uint32_t lut_stride) {
+    constexpr int NB = K / 4;
+    constexpr int TAIL = K % 4;
+    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
+    constexpr bool LUT = TAIL == 1;
+    static_assert(NB >= 1, "fast path needs k >= 4");
+
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    uint8_t *s_in = smem;                                        // [in_cap] (16-byte multiple, >= range + 47)
+    uint32_t *s_out = reinterpret_cast<uint32_t *>(smem + in_cap);  // [32][stride]
+
+    const uint32_t tid = threadIdx.x;
+    const uint64_t r0 = (uint64_t)blockIdx.x * 32;
+    const uint64_t t_beg = offsets[r0], t_end = offsets[r0 + 32];
+    const uint32_t head = (uint32_t)((uintptr_t)(bases + t_beg) & 15u);
+    const uint32_t range = (uint32_t)(t_end - t_beg);
+    const uint32_t body = (head + range) & ~15u;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+        mbar_expect_tx(&s_bar[0], body);
+        if (body) bulk_g2s(s_in, bases + t_beg - head, body, &s_bar[0]);
+        if (LUT) {
+            mbar_expect_tx(&s_bar[1], 1024u);
+            bulk_g2s(s_lut, &g_kmix_byte, 1024u, &s_bar[1]);
+        }
+    }
+    for (uint32_t i = body + tid; i < head + range + 32; i += 32)  // unaligned tail + over-read pad
+        s_in[i] = i < head + range ? __ldg(bases + t_beg - head + i) : (uint8_t)0;
+    __syncwarp();
+    mbar_wait(&s_bar[0], 0);
+    if (LUT) mbar_wait(&s_bar[1], 0);
+
+    const uint64_t my_beg = offsets[r0 + tid];
+    const uint32_t L = (uint32_t)(offsets[r0 + tid + 1] - my_beg);
+    const uint32_t nk = L > (uint32_t)K ? L - (uint32_t)K : 0u;  // mash.go:73
+    const uint32_t b0 = head + (uint32_t)(my_beg - t_beg);
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(s_in) + (b0 >> 2);
+    const uint8_t *sb = s_in + b0 + 4 * NB;
+    const uint32_t sh = (b0 & 3u) * 8u;
+    uint32_t *my_out = s_out + tid * stride;
+    const uint32_t lut_base = smem_u32(s_lut);
+
+    if (nk > 0) {
+        uint32_t raw_a = sw[0], raw_b = sw[1];
+        uint32_t w_cur = __funnelshift_r(raw_a, raw_b, sh);
+        raw_a = raw_b; raw_b = sw[2];
+        uint32_t w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+        raw_a = raw_b; raw_b = sw[3];
+        const uint32_t *swp = sw + 4;
+        uint32_t ring[4][NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            ring[0][q] = mm3_kmix(w_cur);
+            ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
+            ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
+            ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
+            w_cur = w_nxt;
+            w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+            raw_a = raw_b;
+            raw_b = *swp++;
+        }
+        uint32_t i = 0;
+        const uint32_t n_main = (nk / (4 * NB)) * (4 * NB);
+        while (i < n_main) {
+#pragma unroll
+            for (int u = 0; u < NB; ++u) PG_K1_STEP(u, false)
+        }
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            if (i < nk) PG_K1_STEP(u, true)
+        }
+    }
+    for (uint32_t i = nk; i < stride; ++i) my_out[i] = 0u;  // zero tail up to the row stride
+    if (count) count[r0 + tid] = nk;
+    if (status) status[r0 + tid] = PG_ITEM_OK;
+
+    fence_async_smem();
+    __syncwarp();
+    if (tid == 0) {
+        bulk_s2g(out + r0 * stride, s_out, 32u * stride * 4u);
+        bulk_wait_read0();
+    }
+}
 #undef PG_K1_STEP
 
 // ---- generic fill path -----------------------------------------------------------
@@ -323,18 +422,55 @@ int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, 
     return PG_OK;
 }
 
+template <int K>
+static int launch_k1r(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_tiles, uint32_t stride,
+                      uint32_t in_cap, uint32_t *d_out, uint32_t *d_count, int32_t *d_status, cudaStream_t st) {
+    const size_t smem = (size_t)in_cap + (size_t)32 * stride * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(sketch_fill_ragged_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    sketch_fill_ragged_kernel<K><<<(unsigned)n_tiles, 32, smem, st>>>(d_bases, d_offsets, d_out, stride, in_cap, d_count, d_status, 4u);
+    PG_LAUNCH_CHECK("sketch_fill_ragged_kernel");
+    return PG_OK;
+}
+
 int launch_sketch_ragged(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_reads,
                          uint64_t max_read_len, int k, int s, uint32_t flags, uint32_t *d_out,
                          uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
                          cudaStream_t st) {
     if (n_reads == 0) return PG_OK;
-    int rc = launch_fill_generic(d_bases, d_offsets, 0, n_reads, 0, k, s, flags, d_out, row_stride,
-                                 d_count, d_status, st);
-    if (rc != PG_OK) return rc;
     const uint64_t nmax = max_read_len > (uint64_t)k ? max_read_len - (uint64_t)k : 0;
-    if (nmax >= (uint64_t)s && nmax > 0)  // some read may be in the select regime
-        return launch_sketch_select(d_bases, d_offsets, 0, n_reads, k, s, flags, d_out, row_stride,
-                                    d_count, d_status, st);
+    uint64_t done = 0;
+    // K1r: every read in the fill regime, rows not wider than the staging allows
+    const uint64_t in_cap = (32 * max_read_len + 48 + 15) & ~15ull;
+    const uint64_t need_stride = (flags & PG_SKETCH_PAD_ZERO) ? (uint64_t)s : nmax;
+    if (nmax > 0 && nmax < (uint64_t)s && row_stride >= need_stride && row_stride * 128 <= 96 * 1024 && in_cap <= 64 * 1024 &&
+        (uintptr_t)d_out % 16 == 0 && n_reads >= 32 && (row_stride == need_stride || !(flags & PG_SKETCH_PAD_ZERO) || row_stride >= (uint64_t)s)) {
+        const uint64_t tiles = n_reads / 32;
+        bool handled = true;
+        int rc = PG_OK;
+        switch (k) {
+#define PG_K1R_CASE(KK) \
+    case KK: rc = launch_k1r<KK>(d_bases, d_offsets, tiles, (uint32_t)row_stride, (uint32_t)in_cap, d_out, d_count, d_status, st); break;
+            PG_K1R_CASE(11) PG_K1R_CASE(13) PG_K1R_CASE(15) PG_K1R_CASE(16) PG_K1R_CASE(17) PG_K1R_CASE(19)
+            PG_K1R_CASE(21) PG_K1R_CASE(23) PG_K1R_CASE(24) PG_K1R_CASE(25) PG_K1R_CASE(27) PG_K1R_CASE(29)
+            PG_K1R_CASE(31) PG_K1R_CASE(32)
+#undef PG_K1R_CASE
+            default: handled = false;
+        }
+        if (rc != PG_OK) return rc;
+        if (handled) done = tiles * 32;
+    }
+    if (done < n_reads) {
+        int rc = launch_fill_generic(d_bases, d_offsets, 0, n_reads - done, done, k, s, flags, d_out, row_stride,
+                                     d_count, d_status, st);
+        if (rc != PG_OK) return rc;
+        if (nmax >= (uint64_t)s && nmax > 0)  // some read may be in the select regime
+            return launch_sketch_select(d_bases, d_offsets, 0, n_reads, k, s, flags, d_out, row_stride,
+                                        d_count, d_status, st);
+    }
     return PG_OK;
 }
 

@@ -381,3 +381,23 @@ def test_randomized_differential_sketch(gpu, oracle):
         out, count, status = mash.sketch_arrays(bases, offsets, k, s, pad_zero=True)
         rc, want = oracle.sketch_batch(bases, offsets, k, s, variant=1)
         assert rc == 0 and not status.any() and np.array_equal(out, want), (k, s, trial)
+
+
+@pytest.mark.parametrize("k", [11, 16, 21, 24, 31])
+def test_ragged_fast_path(gpu, oracle, k):
+    """K1r (sketch_fill_ragged_kernel): ragged reads all in the fill regime -- TMA-staged tiles of 32
+    reads with per-thread lengths; includes reads shorter than k, empty reads, a tail < 32 reads and
+    arbitrary bytes."""
+    rng = np.random.default_rng(k)
+    s = 1000
+    lens = np.concatenate([rng.integers(0, 220, 32 * 30 + 11), [0, 1, k - 1, k, k + 1, 219]])
+    rng.shuffle(lens)
+    seqs = [bytes(rng.integers(0, 256, int(l), dtype=np.uint8)) if i % 7 == 0 else bytes(rng.choice(list(b"ACGT"), size=int(l)).astype(np.uint8))
+            for i, l in enumerate(lens)]
+    bases, offsets = mash.flatten(seqs)
+    for pad in (False, True):
+        out, count, status = mash.sketch_arrays(bases, offsets, k, s if not pad else 256, pad_zero=pad)
+        rc, want = oracle.sketch_batch(bases, offsets, k, s if not pad else 256, variant=1)
+        assert rc == 0 and not status.any()
+        assert np.array_equal(count, np.minimum(np.maximum(lens - k, 0), s if not pad else 256))
+        assert np.array_equal(out, want[:, : out.shape[1]]), (k, pad)

@@ -80,6 +80,21 @@ tm = torch.empty(m, dtype=torch.float64, device=dev)
 ms = timed(lambda: _lib.check(L.pg_tm_batch_dev(pr.data_ptr(), off.data_ptr(), m, 500e-9, 50e-3, 0.0, tm.data_ptr(), None, None, None, st)), iters=10)
 print(json.dumps({"kernel": "K5 tm (cfg5)", "primers": m, "ms": ms, "mprimers_per_s": m / ms / 1e3, "first3": tm[:3].cpu().tolist()}))
 
+# ---- ragged short reads (K1r): 2M reads, lengths uniform in [100, 150], k=21, s=1000 ------------
+rng = np.random.default_rng(0)
+nrag = 2_000_000
+lens = rng.integers(100, 151, nrag)
+offs = np.zeros(nrag + 1, dtype=np.int64); offs[1:] = np.cumsum(lens)
+rag = torch.from_numpy(synth.independent_reads(int(offs[-1] // 150 + 1), 150)[: offs[-1]]).to(dev)
+d_offs = torch.from_numpy(offs).to(dev)
+d_rout = torch.empty((nrag, 129), dtype=torch.int32, device=dev)
+d_cnt = torch.empty(nrag, dtype=torch.int32, device=dev)
+ms = timed(lambda: _lib.check(L.pg_mash_sketch_batch_dev(rag.data_ptr(), d_offs.data_ptr(), nrag, 150, 21, 1000, 0, d_rout.data_ptr(), 129,
+                                                         d_cnt.data_ptr(), None, st)), iters=5)
+print(json.dumps({"kernel": "K1r ragged fill (2M reads, len 100..150)", "ms": ms, "gbases_per_s": float(offs[-1]) / ms / 1e6,
+                  "kernel_name": L.pg_last_kernel().decode(), "count_ok": bool((d_cnt.cpu().numpy() == lens - 21).all())}))
+del rag, d_rout
+
 # ---- widened rows: FASTQ ingest (8f.2) and batched DesignPrimers (8f.3) ------------------------
 import ctypes as C
 from poly_b200 import pcr  # noqa: E402
