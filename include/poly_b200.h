@@ -72,8 +72,9 @@ int pg_stream_sync(void *stream);
  *   n_i <  s : out row i = the n_i hashes in positional order   (mash.go:81-84)
  *   n_i >= s : out row i = ascending bottom-s multiset          (mash.go:87-102)
  * count[i] = min(n_i, s) informative words; row i starts at out + i*row_stride.
- * The zero tail that a fresh Mash holds beyond count[i] is NOT written unless
- * PG_SKETCH_PAD_ZERO is set (then row_stride must be >= s and s words are written).
+ * row_stride must be >= the largest count of the batch (>= s with PG_SKETCH_PAD_ZERO); words
+ * [count[i], row_stride) of a row are written as zeros -- the zero tail a fresh Mash holds,
+ * as far as the row reaches.  With PG_SKETCH_PAD_ZERO every row is a full Go array of s words.
  * status[i] (may be NULL) reports per-read PG_ITEM_PANIC for s in {0,1} inputs on
  * which mash.go:96-98 indexes Sketches[-1]; k < 0 or s < 0 is PG_ERR_ARG.
  */

@@ -314,8 +314,9 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
             const uint8_t *p = seq + i;
             dst[i] = mm3_bytes([p](uint32_t j) { return __ldg(p + j); }, k);
         }
-        if (flags & PG_SKETCH_PAD_ZERO)
-            for (uint64_t i = n + lane; i < s; i += 32) dst[i] = 0u;
+        // the zero tail of a fresh Mash, as far as the caller's row reaches (at least s words with
+        // PG_SKETCH_PAD_ZERO): rows are fully defined whichever kernel produced them
+        for (uint64_t i = n + lane; i < row_stride; i += 32) dst[i] = 0u;
         if (lane == 0) {
             if (count) count[row] = (uint32_t)n;
             if (status) status[row] = PG_ITEM_OK;
