@@ -227,7 +227,7 @@ struct Alignment {
     int64_t score;
     std::string alignA, alignB;
 };
-inline Alignment SmithWatermanAlign(const std::string &a, const std::string &b, const Scoring &sc) {
+inline Alignment align_strings(bool global, const std::string &a, const std::string &b, const Scoring &sc) {
     const bool query_is_a = a.size() <= 64;
     const std::string &q = query_is_a ? a : b, &t = query_is_a ? b : a;
     Flat f({q});
@@ -236,15 +236,16 @@ inline Alignment SmithWatermanAlign(const std::string &a, const std::string &b, 
     std::vector<int64_t> table((size_t)na * nb);
     for (int i = 0; i < na; ++i)
         for (int j = 0; j < nb; ++j) table[(size_t)i * nb + j] = sc.Matrix.scores[i][j];
-    uint64_t stride = 2 * q.size() + 64;
+    uint64_t stride = global ? q.size() + t.size() + 8 : 2 * q.size() + 64;
     for (;;) {
         std::vector<uint8_t> oa(stride), ob(stride);
         int64_t score = 0, epos = 0;
         int32_t ecode = 0, status = 0;
         uint32_t len = 0;
-        check(pg_sw_align_batch(f.bases.data(), f.offsets.data(), 1, reinterpret_cast<const uint8_t *>(t.data()), t.size(),
-                                query_is_a ? 1 : 0, lut_a.data(), lut_b.data(), table.data(), na, nb, sc.GapPenalty, &score,
-                                &ecode, &epos, oa.data(), ob.data(), stride, &len, &status));
+        check((global ? pg_nw_align_batch : pg_sw_align_batch)(
+            f.bases.data(), f.offsets.data(), 1, reinterpret_cast<const uint8_t *>(t.data()), t.size(), query_is_a ? 1 : 0,
+            lut_a.data(), lut_b.data(), table.data(), na, nb, sc.GapPenalty, &score, &ecode, &epos, oa.data(), ob.data(), stride,
+            &len, &status));
         if (ecode) {
             const uint8_t bad = ecode == 1 ? (uint8_t)a[epos] : (uint8_t)b[epos];
             throw AlphabetError("Symbol " + go_string_of_byte(bad) + " not in alphabet");
@@ -252,6 +253,14 @@ inline Alignment SmithWatermanAlign(const std::string &a, const std::string &b, 
         if (status == PG_ITEM_UNSUPPORTED) { stride = len + 8; continue; }
         return Alignment{score, std::string(oa.begin(), oa.begin() + len), std::string(ob.begin(), ob.begin() + len)};
     }
+}
+
+inline Alignment SmithWatermanAlign(const std::string &a, const std::string &b, const Scoring &sc) {
+    return align_strings(false, a, b, sc);
+}
+// Full align.NeedlemanWunsch (align.go:100-166), including its loop condition (align.go:141).
+inline Alignment NeedlemanWunschAlign(const std::string &a, const std::string &b, const Scoring &sc) {
+    return align_strings(true, a, b, sc);
 }
 
 // Score of align.NeedlemanWunsch (align.go:100-134,166)

@@ -84,6 +84,8 @@ static void TestSmithWaterman() {  // align_test.go:139-292 (scores)
     EXPECT(align::NeedlemanWunschScore("GATTACA", "GAT", nws) == -1);
     EXPECT(align::NeedlemanWunschScore("", "GAT", nws) == -3);
     EXPECT(align::NeedlemanWunschScore("G", "GATTACA", nws) == -5);
+    al = align::NeedlemanWunschAlign("GATTACA", "GCATGCU", nws);  // example_test.go:10-47
+    EXPECT(al.score == 0 && al.alignA == "G-ATTACA" && al.alignB == "GCA-TGCU");
     bool err = false;
     try { align::SmithWaterman("ACGT", "ACGX", scoring); } catch (const align::AlphabetError &e) { err = std::string(e.what()) == "Symbol X not in alphabet"; }
     EXPECT(err);
