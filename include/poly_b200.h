@@ -245,6 +245,36 @@ int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
                         uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream);
 
+/* ---- FASTA ingest -- fasta.Parse = NewParser(r, maxLineSize).ParseAll(),
+ * io/fasta/fasta.go:72-77,96-118,149-243 -----------------------------------------
+ * Parses a whole FASTA text buffer on the GPU into dense sequences + offsets and (optionally:
+ * pass names, name_offsets both non-NULL) dense names + name_offsets, n_records + 1 offsets each.
+ * max_line_size as NewParser's (fasta.Parse uses 65536; values < 16 behave as 16 like
+ * bufio.NewReaderSize).  Semantics are ParseNext's, quirks included: lines of length <= 1 and
+ * ';' lines are skipped, a '>' line directly after a name line is sequence text, a record
+ * without a trailing newline at the end of the text is dropped without an error, and parsing
+ * stops at the first error with the records before it returned: *err_code 0 none,
+ * 1 "did not find fasta start '>'", 2 "empty fasta sequence", 3 "line too large for buffer"
+ * (>= max_line_size content bytes), 4 bufio.ErrBufferFull (over-long ';' line inside a record);
+ * *err_line = the line number the reference's message prints.
+ * flags & PG_FASTA_BUFIO_ALIAS: also reproduce the reference's use of the bufio line slice after
+ * Peek(1) (fasta.go:192): a line whose newline is the last byte of a full reader buffer is seen
+ * with its bytes replaced by the text one buffer further on, exactly as fasta.Parse over a
+ * strings.Reader / bytes.Reader / *os.File yields.  Without the flag lines are taken as written.
+ * Returns PG_ERR_ARG when a capacity is too small (*n_records, *total_bases, *total_name_bytes
+ * then hold the needs; nbytes bounds both byte counts, the newline count + 1 the records). */
+#define PG_FASTA_BUFIO_ALIAS 1u
+int pg_fasta_ingest(const uint8_t *text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags,
+                    uint8_t *bases, uint64_t bases_cap, uint64_t *offsets, uint8_t *names,
+                    uint64_t names_cap, uint64_t *name_offsets, uint64_t records_cap,
+                    uint64_t *n_records, uint64_t *total_bases, uint64_t *total_name_bytes,
+                    int32_t *err_code, uint64_t *err_line);
+int pg_fasta_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags,
+                        uint8_t *d_bases, uint64_t bases_cap, uint64_t *d_offsets, uint8_t *d_names,
+                        uint64_t names_cap, uint64_t *d_name_offsets, uint64_t records_cap,
+                        uint64_t *n_records, uint64_t *total_bases, uint64_t *total_name_bytes,
+                        int32_t *err_code, uint64_t *err_line, void *stream);
+
 /* ---- synthetic workloads (bench/test tooling, not a reference API) ---
  * kind 0: independent reads  base(i,j) = code(seed, i*L + j)
  * kind 1: family reads       (family = reads per template, 1/64 substitutions)

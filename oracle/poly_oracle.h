@@ -84,6 +84,14 @@ int po_nw_score(const uint8_t *a, int64_t la, const uint8_t *b, int64_t lb,
 int po_fastq_parse(const uint8_t *text, uint64_t n, uint64_t *seq_start, uint64_t *seq_len, uint64_t cap,
                    uint64_t *n_records, int32_t *err_code, uint64_t *err_line);
 
+/* io/fasta/fasta.go:72-77,96-118,149-243 (fasta.Parse) over a whole buffer, with the bufio.Reader
+ * underneath modelled literally; alias=1 keeps the reference's use of `line` after Peek(1)
+ * (fasta.go:192), alias=0 copies the line first.  See fasta_oracle.c for the error codes. */
+int po_fasta_parse(const uint8_t *text, uint64_t n, uint32_t max_line_size, int alias, uint8_t *seq,
+                   uint64_t seq_cap, uint64_t *seq_off, uint8_t *name, uint64_t name_cap,
+                   uint64_t *name_off, uint64_t rec_cap, uint64_t *n_records, int32_t *err_code,
+                   uint64_t *err_line);
+
 /* transform/transform.go:15-23,78-109. out has room for len bytes. */
 void po_reverse_complement(const uint8_t *seq, int64_t len, uint8_t *out);
 

@@ -784,6 +784,48 @@ int pg_fastq_ingest(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64
     return PG_OK;
 }
 
+int pg_fasta_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags,
+                        uint8_t *d_bases, uint64_t bases_cap, uint64_t *d_offsets, uint8_t *d_names,
+                        uint64_t names_cap, uint64_t *d_name_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, uint64_t *total_name_bytes, int32_t *err_code, uint64_t *err_line,
+                        void *stream) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (!n_records || !total_bases || !total_name_bytes || !err_code || !err_line || !d_offsets) { set_error("null buffer"); return PG_ERR_ARG; }
+    return launch_fasta_ingest(d_text, nbytes, max_line_size, flags, d_bases, bases_cap, d_offsets, d_names, names_cap, d_name_offsets,
+                               records_cap, n_records, total_bases, total_name_bytes, err_code, err_line, (cudaStream_t)stream);
+}
+
+int pg_fasta_ingest(const uint8_t *text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags, uint8_t *bases,
+                    uint64_t bases_cap, uint64_t *offsets, uint8_t *names, uint64_t names_cap, uint64_t *name_offsets,
+                    uint64_t records_cap, uint64_t *n_records, uint64_t *total_bases, uint64_t *total_name_bytes,
+                    int32_t *err_code, uint64_t *err_line) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (!n_records || !total_bases || !total_name_bytes || !err_code || !err_line || !offsets) { set_error("null buffer"); return PG_ERR_ARG; }
+    const bool want_names = names != nullptr || name_offsets != nullptr;
+    if (want_names && (!names || !name_offsets)) { set_error("names and name_offsets must be given together"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g_streams[0];
+    Tmp d_text(st), d_bases(st), d_off(st), d_names(st), d_noff(st);
+    if ((rc = d_text.alloc(nbytes + 16)) || (rc = d_bases.alloc(bases_cap + 16)) || (rc = d_off.alloc((records_cap + 1) * 8)))
+        return rc;
+    if (want_names && ((rc = d_names.alloc(names_cap + 16)) || (rc = d_noff.alloc((records_cap + 1) * 8)))) return rc;
+    if (nbytes) PG_CUDA(cudaMemcpyAsync(d_text.p, text, nbytes, cudaMemcpyHostToDevice, st));
+    rc = launch_fasta_ingest(d_text.as<uint8_t>(), nbytes, max_line_size, flags, d_bases.as<uint8_t>(), bases_cap, d_off.as<uint64_t>(),
+                             want_names ? d_names.as<uint8_t>() : nullptr, names_cap, want_names ? d_noff.as<uint64_t>() : nullptr,
+                             records_cap, n_records, total_bases, total_name_bytes, err_code, err_line, st);
+    if (rc != PG_OK) return rc;
+    if (*total_bases) PG_CUDA(cudaMemcpyAsync(bases, d_bases.p, *total_bases, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(offsets, d_off.p, (*n_records + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (want_names) {
+        if (*total_name_bytes) PG_CUDA(cudaMemcpyAsync(names, d_names.p, *total_name_bytes, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(name_offsets, d_noff.p, (*n_records + 1) * 8, cudaMemcpyDeviceToHost, st));
+    }
+    PG_CUDA(cudaStreamSynchronize(st));
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------------------
 int pg_synth_reads_dev(uint8_t *d_bases, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
                        uint64_t seed, int32_t kind, uint32_t family, void *stream) {

@@ -98,6 +98,12 @@ int launch_design_primers(const uint8_t *d_bases, const uint64_t *d_off, uint64_
 int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
                         uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st);
+// fasta_ingest.cu
+int launch_fasta_ingest(const uint8_t *d_text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags,
+                        uint8_t *d_bases, uint64_t bases_cap, uint64_t *d_offsets, uint8_t *d_names,
+                        uint64_t names_cap, uint64_t *d_name_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, uint64_t *total_name_bytes, int32_t *err_code, uint64_t *err_line,
+                        cudaStream_t st);
 // synth.cu
 int launch_synth_reads(uint8_t *d_bases, uint64_t first_read, uint64_t n_reads, uint32_t read_len,
                        uint64_t seed, int kind, uint32_t family, cudaStream_t st);

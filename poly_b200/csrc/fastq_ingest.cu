@@ -11,75 +11,13 @@
 //   2. one thread per record: locate its 4 lines, apply the reference's checks in its order
 //   3. exclusive scan of the sequence lengths of the valid prefix -> offsets
 //   4. one warp per record copies its sequence bytes into the dense buffer
-#include <algorithm>
-
-#include "common.cuh"
+#include "text_scan.cuh"
 
 namespace pg {
 
 namespace {
 
-constexpr int FQ_BLOCK_BYTES = 4096;
-constexpr int FQ_THREADS = 256;  // 16 bytes per thread
 constexpr uint64_t FQ_MAX_LINE = 2 * 32 * 1024;  // fastq.go:56 maxLineSize of Parse / Read
-
-__global__ void __launch_bounds__(FQ_THREADS)
-count_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, uint32_t *__restrict__ block_count) {
-    const uint64_t base = (uint64_t)blockIdx.x * FQ_BLOCK_BYTES + threadIdx.x * 16;
-    uint32_t c = 0;
-    for (int j = 0; j < 16; ++j) c += (base + j < n && __ldg(text + base + j) == '\n');
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    __shared__ uint32_t s[FQ_THREADS / 32];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < FQ_THREADS / 32; ++w) t += s[w];
-        block_count[blockIdx.x] = t;
-    }
-}
-
-// exclusive scan of `in` (n entries) into `out` (n + 1 entries, out[n] = total); one CTA
-template <typename TIn>
-__global__ void __launch_bounds__(1024) scan_kernel(const TIn *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
-    __shared__ uint64_t s_part[1024];
-    const uint32_t tid = threadIdx.x;
-    const uint64_t per = (n + 1023) / 1024, lo = min((uint64_t)tid * per, n), hi = min(lo + per, n);
-    uint64_t sum = 0;
-    for (uint64_t i = lo; i < hi; ++i) sum += in[i];
-    s_part[tid] = sum;
-    __syncthreads();
-    if (tid == 0) {
-        uint64_t run = 0;
-        for (int i = 0; i < 1024; ++i) { const uint64_t t = s_part[i]; s_part[i] = run; run += t; }
-        out[n] = run;
-    }
-    __syncthreads();
-    uint64_t run = s_part[tid];
-    for (uint64_t i = lo; i < hi; ++i) { out[i] = run; run += in[i]; }
-}
-
-__global__ void __launch_bounds__(FQ_THREADS)
-write_newlines_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__restrict__ block_start,
-                      uint64_t *__restrict__ nl) {
-    const uint64_t base = (uint64_t)blockIdx.x * FQ_BLOCK_BYTES + threadIdx.x * 16;
-    uint32_t mask = 0;
-    for (int j = 0; j < 16; ++j) mask |= (uint32_t)(base + j < n && __ldg(text + base + j) == '\n') << j;
-    const uint32_t c = __popc(mask);
-    uint32_t incl = c;
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)(threadIdx.x & 31) >= d) incl += y;
-    }
-    __shared__ uint32_t s[FQ_THREADS / 32];
-    if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += s[w];
-    uint64_t pos = block_start[blockIdx.x] + wbase + incl - c;
-    for (int j = 0; j < 16; ++j)
-        if (mask & (1u << j)) nl[pos++] = base + j;
-}
 
 // error codes (per record and overall)
 enum : int32_t {
@@ -173,29 +111,11 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
         if (records_cap + 1 >= 1 && d_offsets) PG_CUDA(cudaMemsetAsync(d_offsets, 0, 8, st));
         return PG_OK;
     }
-    const uint64_t nblocks = (nbytes + FQ_BLOCK_BYTES - 1) / FQ_BLOCK_BYTES;
-    uint32_t *d_bcount = nullptr;
-    uint64_t *d_bstart = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_bcount, nblocks * 4, st));
-    PG_CUDA(cudaMallocAsync(&d_bstart, (nblocks + 1) * 8, st));
-    count_newlines_kernel<<<(unsigned)nblocks, FQ_THREADS, 0, st>>>(d_text, nbytes, d_bcount);
-    note_launch("count_newlines_kernel");
-    scan_kernel<uint32_t><<<1, 1024, 0, st>>>(d_bcount, nblocks, d_bstart);
-    note_launch("scan_kernel");
-    uint64_t n_lines = 0;
-    PG_CUDA(cudaMemcpyAsync(&n_lines, d_bstart + nblocks, 8, cudaMemcpyDeviceToHost, st));
-    PG_CUDA(cudaStreamSynchronize(st));
     uint64_t *d_nl = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_nl, std::max<uint64_t>(n_lines, 1) * 8, st));
-    write_newlines_kernel<<<(unsigned)nblocks, FQ_THREADS, 0, st>>>(d_text, nbytes, d_bstart, d_nl);
-    note_launch("write_newlines_kernel");
-    // candidate records: every full group of 4 lines, plus one more if anything is left over
-    uint64_t last_nl_plus1 = 0;
-    if (n_lines) {
-        uint64_t last = 0;
-        PG_CUDA(cudaMemcpyAsync(&last, d_nl + n_lines - 1, 8, cudaMemcpyDeviceToHost, st));
-        PG_CUDA(cudaStreamSynchronize(st));
-        last_nl_plus1 = last + 1;
+    uint64_t n_lines = 0, last_nl_plus1 = 0;
+    {
+        const int rc0 = text::newline_positions(d_text, nbytes, &d_nl, &n_lines, &last_nl_plus1, st);
+        if (rc0 != PG_OK) return rc0;
     }
     const bool trailing = last_nl_plus1 < nbytes;  // bytes after the last newline
     const uint64_t n_cand = n_lines / 4 + ((n_lines % 4 != 0 || trailing) ? 1 : 0);
@@ -234,8 +154,10 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
             rc = PG_ERR_ARG;
         } else {
             PG_CUDA(cudaMallocAsync(&d_off_tmp, (n_ok + 1) * 8, st));
-            scan_kernel<uint32_t><<<1, 1024, 0, st>>>(d_len, n_ok, d_off_tmp);
-            note_launch("scan_kernel");
+            {
+                const int rc1 = text::device_scan<text::SumOp<uint32_t>>(d_len, n_ok, (unsigned long long *)d_off_tmp, st);
+                if (rc1 != PG_OK) return rc1;
+            }
             PG_CUDA(cudaMemcpyAsync(total_bases, d_off_tmp + n_ok, 8, cudaMemcpyDeviceToHost, st));
             PG_CUDA(cudaStreamSynchronize(st));
             if (*total_bases > bases_cap) {
@@ -255,7 +177,7 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
     }
     cudaError_t e = cudaGetLastError();
     PG_CUDA(cudaStreamSynchronize(st));
-    for (void *p : {(void *)d_bcount, (void *)d_bstart, (void *)d_nl, (void *)d_len, (void *)d_eline, (void *)d_sstart,
+    for (void *p : {(void *)d_nl, (void *)d_len, (void *)d_eline, (void *)d_sstart,
                     (void *)d_err, (void *)d_first, (void *)d_off_tmp})
         if (p) cudaFreeAsync(p, st);
     if (e != cudaSuccess) return cuda_fail(e, "fastq ingest", __FILE__, __LINE__);

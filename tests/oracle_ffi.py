@@ -50,6 +50,9 @@ def lib():
                                   C.c_int64, i64p, C.c_char_p, C.c_char_p, C.c_int64, i64p, C.POINTER(C.c_int32), i64p]
         L.po_fastq_parse.restype = C.c_int
         L.po_fastq_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int32), u64p]
+        L.po_fasta_parse.restype = C.c_int
+        L.po_fasta_parse.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p,
+                                     C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, u64p, C.POINTER(C.c_int32), u64p]
         L.po_nw_align.restype = C.c_int
         L.po_nw_align.argtypes = L.po_sw_align.argtypes
         L.po_nw_score.restype = C.c_int
@@ -166,6 +169,20 @@ def fastq_parse(text: bytes):
     rc = lib().po_fastq_parse(text, len(text), st.ctypes.data, ln.ctypes.data, cap, C.byref(n), C.byref(ec), C.byref(el))
     assert rc == PO_OK
     return [text[int(st[i]): int(st[i] + ln[i])] for i in range(n.value)], ec.value, el.value
+
+
+def fasta_parse(text: bytes, max_line_size: int = 65536, alias: bool = True):
+    """Returns ([(name, sequence)], err_code, err_line) as fasta.Parse / NewParser(r, max_line_size).ParseAll would."""
+    cap = text.count(b"\n") + 2
+    seq, name = np.zeros(len(text) + 1, np.uint8), np.zeros(len(text) + 1, np.uint8)
+    so, no = np.zeros(cap + 1, np.uint64), np.zeros(cap + 1, np.uint64)
+    n, ec, el = C.c_uint64(0), C.c_int32(0), C.c_uint64(0)
+    rc = lib().po_fasta_parse(text, len(text), max_line_size, int(alias), seq.ctypes.data, len(seq), so.ctypes.data,
+                              name.ctypes.data, len(name), no.ctypes.data, cap, C.byref(n), C.byref(ec), C.byref(el))
+    assert rc == PO_OK
+    sb, nb = seq.tobytes(), name.tobytes()
+    recs = [(nb[int(no[i]): int(no[i + 1])], sb[int(so[i]): int(so[i + 1])]) for i in range(n.value)]
+    return recs, ec.value, el.value
 
 
 def nw_score(a, b, lut_a, lut_b, table, gap):

@@ -123,6 +123,31 @@ ms = timed(ingest, iters=3)
 ok = nr.value == nrec and ec.value == 0 and bool(torch.equal(d_bases[: nrec * 150].cpu(), torch.from_numpy(reads.reshape(-1))))
 print(json.dumps({"kernel": "FASTQ ingest (8f.2)", "records": nrec, "text_GB": text.numel() / 1e9, "ms": ms,
                   "text_GBps": text.numel() / ms / 1e6, "matches_generator": ok}))
+del text, d_bases, d_off
+# FASTA ingest (8f.2): 200k records x 50 lines of 60 residues, both reader models
+nfa, nl_per, width = 200_000, 50, 60
+body = synth.independent_reads(nfa * nl_per, width).reshape(nfa, nl_per, width)
+fa = np.empty((nfa, 12 + nl_per * (width + 1)), dtype=np.uint8)
+fa[:, :12] = np.frombuffer(b">seq0000000\n", dtype=np.uint8)
+blk = fa[:, 12:].reshape(nfa, nl_per, width + 1)
+blk[:, :, :width] = body
+blk[:, :, width] = 10
+ftext = torch.from_numpy(fa.reshape(-1)).to(dev)
+f_bases = torch.empty(nfa * nl_per * width + 64, dtype=torch.uint8, device=dev)
+f_names = torch.empty(nfa * 16, dtype=torch.uint8, device=dev)
+f_off = torch.empty(nfa + 1, dtype=torch.int64, device=dev)
+f_noff = torch.empty(nfa + 1, dtype=torch.int64, device=dev)
+ntot = C.c_uint64(0)
+for alias in (0, 1):
+    def fasta_ingest():
+        _lib.check(L.pg_fasta_ingest_dev(ftext.data_ptr(), ftext.numel(), 65536, alias, f_bases.data_ptr(), f_bases.numel(), f_off.data_ptr(),
+                                         f_names.data_ptr(), f_names.numel(), f_noff.data_ptr(), nfa, C.byref(nr), C.byref(tot), C.byref(ntot),
+                                         C.byref(ec), C.byref(el), st))
+    ms = timed(fasta_ingest, iters=3)
+    same = bool(torch.equal(f_bases[: nfa * nl_per * width].cpu(), torch.from_numpy(body.reshape(-1))))
+    print(json.dumps({"kernel": "FASTA ingest (8f.2)", "bufio_alias": alias, "records": nr.value, "text_GB": ftext.numel() / 1e9, "ms": ms,
+                      "text_GBps": ftext.numel() / ms / 1e6, "err_code": ec.value, "sequences_equal_generator": same}))
+del ftext, f_bases
 genes = [bytes(r) for r in synth.independent_reads(100_000, 300).reshape(100_000, 300)]
 import time as _t
 t0 = _t.perf_counter(); fl, rl, stt = pcr.design_primer_lengths(genes, 55.0); dt = _t.perf_counter() - t0
