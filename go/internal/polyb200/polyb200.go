@@ -203,3 +203,35 @@ func TmBatch(bases []byte, offsets []uint64, cp, na, mg float64) (tm, dH, dS []f
 		(*C.double)(unsafe.Pointer(&dS[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
 	return tm[:n], dH[:n], dS[:n], status[:n], check(rc)
 }
+
+// FastaIngest parses a whole FASTA text on the GPU (pg_fasta_ingest): dense sequence bytes +
+// offsets and dense name bytes + offsets for the records fasta.Parse would return, and the
+// error it would stop with (errCode 0 = nil; errLine = the line number its message prints).
+func FastaIngest(text []byte, maxLineSize int, bufioAlias bool) (seq []byte, seqOff []uint64, names []byte, nameOff []uint64, errCode int, errLine uint64, err error) {
+	if len(text) == 0 {
+		return nil, []uint64{0}, nil, []uint64{0}, 0, 0, nil
+	}
+	lines := 1
+	for _, c := range text {
+		if c == '\n' {
+			lines++
+		}
+	}
+	seq, names = make([]byte, len(text)), make([]byte, len(text))
+	seqOff, nameOff = make([]uint64, lines+1), make([]uint64, lines+1)
+	var n, tot, ntot C.uint64_t
+	var ec C.int32_t
+	var el C.uint64_t
+	flags := C.uint32_t(0)
+	if bufioAlias {
+		flags = C.PG_FASTA_BUFIO_ALIAS
+	}
+	rc := C.pg_fasta_ingest((*C.uint8_t)(unsafe.Pointer(&text[0])), C.uint64_t(len(text)), C.uint32_t(maxLineSize), flags,
+		(*C.uint8_t)(unsafe.Pointer(&seq[0])), C.uint64_t(len(seq)), (*C.uint64_t)(unsafe.Pointer(&seqOff[0])),
+		(*C.uint8_t)(unsafe.Pointer(&names[0])), C.uint64_t(len(names)), (*C.uint64_t)(unsafe.Pointer(&nameOff[0])),
+		C.uint64_t(lines), &n, &tot, &ntot, &ec, &el)
+	if err = check(rc); err != nil {
+		return nil, nil, nil, nil, 0, 0, err
+	}
+	return seq[:tot], seqOff[:n+1], names[:ntot], nameOff[:n+1], int(ec), uint64(el), nil
+}

@@ -10,6 +10,7 @@
 //        <- alphabet/alphabet.go:25-41, search/align/matrix/matrix.go:13-38,
 //           search/align/align.go:73-95,171-203
 //   poly::primers::SantaLucia / MeltingTemp <- primers/primers.go:70-105,121-128
+//   poly::fasta::Parse / ParseAll            <- io/fasta/fasta.go:72-77,89-118,149-243
 // A Go panic surfaces as poly::GoPanic; align's alphabet.Error as poly::align::AlphabetError.
 // The Go package in go/ (cgo) is the real drop-in; this header is what the tests in this
 // repository can compile and run (tests/test_gpu_hostcpp.py).  No compute happens here.
@@ -316,4 +317,50 @@ inline std::vector<double> MeltingTemps(const std::vector<std::string> &seqs) {
 }
 
 }  // namespace primers
+
+namespace fasta {
+
+// fasta.Fasta, io/fasta/fasta.go:66-69
+struct Fasta {
+    std::string Name, Sequence;
+    bool operator==(const Fasta &o) const { return Name == o.Name && Sequence == o.Sequence; }
+};
+// the `error` half of ([]Fasta, error): code as pg_fasta_ingest reports it, 0 = nil
+struct ParseResult {
+    std::vector<Fasta> fastas;
+    int32_t err_code = 0;
+    uint64_t err_line = 0;
+    std::string error() const {
+        switch (err_code) {
+            case 1: return "did not find fasta start '>', got to line " + std::to_string(err_line);
+            case 2: return "empty fasta sequence, got to line " + std::to_string(err_line);
+            case 3: return "line " + std::to_string(err_line) + " too large for buffer, use larger maxLineSize";
+            case 4: return "bufio: buffer full";
+            default: return "";
+        }
+    }
+};
+
+// NewParser(r, maxLineSize).ParseAll(), fasta.go:89-99; bufioAlias = give exactly what the reference
+// gives over a strings.Reader / *os.File (see include/poly_b200.h, PG_FASTA_BUFIO_ALIAS)
+inline ParseResult ParseAll(const std::string &text, uint32_t maxLineSize, bool bufioAlias = true) {
+    uint64_t lines = 1;
+    for (char c : text) lines += c == '\n';
+    std::vector<uint8_t> bases(text.size() + 1), names(text.size() + 1);
+    std::vector<uint64_t> off(lines + 1), noff(lines + 1);
+    uint64_t n = 0, tot = 0, ntot = 0;
+    ParseResult r;
+    check(pg_fasta_ingest(reinterpret_cast<const uint8_t *>(text.data()), text.size(), maxLineSize,
+                          bufioAlias ? PG_FASTA_BUFIO_ALIAS : 0u, bases.data(), bases.size(), off.data(), names.data(),
+                          names.size(), noff.data(), lines, &n, &tot, &ntot, &r.err_code, &r.err_line));
+    r.fastas.reserve(n);
+    for (uint64_t i = 0; i < n; ++i)
+        r.fastas.push_back({std::string(names.begin() + noff[i], names.begin() + noff[i + 1]),
+                            std::string(bases.begin() + off[i], bases.begin() + off[i + 1])});
+    return r;
+}
+// fasta.Parse, fasta.go:72-77
+inline ParseResult Parse(const std::string &text, bool bufioAlias = true) { return ParseAll(text, 2 * 32 * 1024, bufioAlias); }
+
+}  // namespace fasta
 }  // namespace poly

@@ -104,8 +104,27 @@ static void TestSantaLucia() {  // primers_test.go:29-84
     EXPECT(panicked);
 }
 
+static void TestFastaParser() {  // io/fasta/fasta_test.go:135-170,199-237
+    using fasta::Fasta;
+    for (bool alias : {true, false}) {
+        auto r = fasta::ParseAll(">humen\nGATTACA\nCATGAT", 256, alias);  // EOF-ended Fasta not valid
+        EXPECT(r.err_code == 0 && r.fastas.empty());
+        r = fasta::ParseAll(">humen\nGATTACA\nCATGAT\n", 256, alias);
+        EXPECT(r.err_code == 0 && r.fastas == std::vector<Fasta>({{"humen", "GATTACACATGAT"}}));
+        r = fasta::ParseAll(">doggy or something\nGATTACA\n\nCATGAT\n>homunculus\nAAAA\n", 256, alias);
+        EXPECT(r.err_code == 0 && r.fastas == std::vector<Fasta>({{"doggy or something", "GATTACACATGAT"}, {"homunculus", "AAAA"}}));
+        r = fasta::Parse("testing\natagtagtagtagtagatgatgatgatgagatg\n\n\n\n\n\n\n\n\n\n\n", alias);  // TestReadEmptyFasta
+        EXPECT(r.err_code != 0 && r.fastas.empty() && r.error() == "did not find fasta start '>', got to line 13");
+        r = fasta::ParseAll(">0\n0123456789ABCDEF\n>1\nCAC\n", 2, alias);  // TestParseBufferFail
+        EXPECT(r.err_code == 3);
+        r = fasta::ParseAll(">OK Fasta\nABGABA\n>NotOKFasta\n", 2, alias);  // TestParseEOFAfterName
+        EXPECT(r.err_code == 2 && r.fastas.size() == 1);
+    }
+}
+
 int main() {
     check(pg_init(0));
+    TestFastaParser();
     TestMash();
     TestSmithWaterman();
     TestSantaLucia();
