@@ -228,6 +228,26 @@ int pg_tm_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t 
 int pg_design_primers_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n,
                             double target_tm, uint32_t *fwd_len, uint32_t *rev_len, int32_t *status);
 
+/* ---- pcr.SimulateSimple building blocks -- primers/pcr/pcr.go:73-169 ---------
+ * pg_pcr_minimal_primer_batch: the minimal-primer loop of pcr.go:93-100 for every primer:
+ * min_len = the longest 3' suffix of >= 15 nt whose MeltingTemp is still below target_tm (the
+ * reference's loop keeps the last length that FAILED the test), 0 when the 15-mer already reaches
+ * it, the primer's length when even the whole primer stays below (the reference then ignores the
+ * primer, pcr.go:103).  status: PG_ITEM_PANIC for primers shorter than 15 nt, PG_ITEM_UNSUPPORTED
+ * for bytes >= 0x80.
+ * pg_find_sites_batch: every (possibly overlapping) exact occurrence of every pattern in every
+ * sequence -- what suffixarray.Lookup(pattern, -1) returns at pcr.go:110,113; empty patterns have
+ * none.  flags & PG_SITES_UPPER compares the ASCII-upper-cased sequence bytes (pcr.go:82).  Hits
+ * come back unordered as (sequence index, position inside it, pattern index); *n_hits is the
+ * number found, PG_ERR_ARG (with the first hits_cap stored) if it exceeds hits_cap. */
+#define PG_SITES_UPPER 1u
+int pg_pcr_minimal_primer_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n,
+                                double target_tm, uint32_t *min_len, int32_t *status);
+int pg_find_sites_batch(const uint8_t *seqs, const uint64_t *seq_offsets, uint64_t n_seq,
+                        const uint8_t *patterns, const uint64_t *pat_offsets, uint32_t n_pat,
+                        uint32_t flags, uint32_t *hit_seq, uint64_t *hit_pos, uint32_t *hit_pat,
+                        uint64_t hits_cap, uint64_t *n_hits);
+
 /* ---- FASTQ ingest -- io/fastq Parser.ParseNext / ParseN, io/fastq/fastq.go:88-99,117-214 -------
  * (the step before the hot path.)  Parses a whole FASTQ text buffer on the GPU
  * into the dense bases + offsets layout the sketch entry points take.  Strict 4-line records;

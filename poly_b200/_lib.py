@@ -66,6 +66,8 @@ _SIGS = {
     "pg_tm_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_double, C.c_double, C.c_double, _f64p, _f64p, _f64p, _i32p]),
     "pg_tm_batch_dev": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_double, C.c_double, C.c_double, _f64p, _f64p, _f64p, _i32p, C.c_void_p]),
     "pg_design_primers_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_double, _u32p, _u32p, _i32p]),
+    "pg_pcr_minimal_primer_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_double, _u32p, _i32p]),
+    "pg_find_sites_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, _u8p, _u64p, C.c_uint32, C.c_uint32, _u32p, _u64p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pg_fastq_ingest": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "pg_fastq_ingest_dev": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p]),
     "pg_fasta_ingest": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_uint32, _u8p, C.c_uint64, _u64p, _u8p, C.c_uint64, _u64p, C.c_uint64,

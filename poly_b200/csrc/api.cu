@@ -753,6 +753,80 @@ int pg_design_primers_batch(const uint8_t *bases, const uint64_t *offsets, uint6
     return worst;
 }
 
+int pg_pcr_minimal_primer_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n, double target_tm,
+                                uint32_t *min_len, int32_t *status) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (n == 0) return PG_OK;
+    if (!offsets || !min_len) { set_error("null buffer"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g_streams[0];
+    const uint64_t b0 = offsets[0], nbytes = offsets[n] - b0;
+    Tmp d_b(st), d_off(st), d_m(st), d_st(st);
+    if ((rc = d_b.alloc(nbytes)) || (rc = d_off.alloc((n + 1) * 8)) || (rc = d_m.alloc(n * 4)) || (rc = d_st.alloc(n * 4))) return rc;
+    if (nbytes) PG_CUDA(cudaMemcpyAsync(d_b.p, bases + b0, nbytes, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_off.p, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_minimal_primer(d_b.as<uint8_t>() - b0, d_off.as<uint64_t>(), n, target_tm, d_m.as<uint32_t>(), d_st.as<int32_t>(), st);
+    if (rc != PG_OK) return rc;
+    std::vector<int32_t> hst(n);
+    PG_CUDA(cudaMemcpyAsync(min_len, d_m.p, n * 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(hst.data(), d_st.p, n * 4, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    int worst = PG_OK;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (status) status[i] = hst[i];
+        if (hst[i] == PG_ITEM_PANIC) worst = PG_ERR_PANIC;
+        else if (hst[i] == PG_ITEM_UNSUPPORTED && worst == PG_OK) worst = PG_ERR_UNSUPPORTED;
+    }
+    if (worst == PG_ERR_PANIC) set_error("at least one primer is shorter than 15 nt: pcr.SimulateSimple panics (slice bounds out of range)");
+    if (worst == PG_ERR_UNSUPPORTED) set_error("at least one primer holds a byte >= 0x80 (unsupported)");
+    return worst;
+}
+
+int pg_find_sites_batch(const uint8_t *seqs, const uint64_t *seq_offsets, uint64_t n_seq, const uint8_t *patterns,
+                        const uint64_t *pat_offsets, uint32_t n_pat, uint32_t flags, uint32_t *hit_seq, uint64_t *hit_pos,
+                        uint32_t *hit_pat, uint64_t hits_cap, uint64_t *n_hits) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (!n_hits) { set_error("null buffer"); return PG_ERR_ARG; }
+    *n_hits = 0;
+    if (n_seq == 0 || n_pat == 0) return PG_OK;
+    if (!seq_offsets || !pat_offsets || (hits_cap && (!hit_seq || !hit_pos || !hit_pat))) { set_error("null buffer"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    cudaStream_t st = g_streams[0];
+    const uint64_t s0 = seq_offsets[0], sbytes = seq_offsets[n_seq] - s0, p0 = pat_offsets[0], pbytes = pat_offsets[n_pat] - p0;
+    std::vector<uint64_t> poff(n_pat + 1);
+    for (uint32_t q = 0; q <= n_pat; ++q) poff[q] = pat_offsets[q] - p0;  // the kernel stages patterns from offset 0
+    Tmp d_s(st), d_soff(st), d_p(st), d_poff(st), d_hs(st), d_hp(st), d_hq(st), d_n(st);
+    if ((rc = d_s.alloc(sbytes)) || (rc = d_soff.alloc((n_seq + 1) * 8)) || (rc = d_p.alloc(pbytes)) || (rc = d_poff.alloc((n_pat + 1) * 8)) ||
+        (rc = d_hs.alloc(hits_cap * 4)) || (rc = d_hp.alloc(hits_cap * 8)) || (rc = d_hq.alloc(hits_cap * 4)) || (rc = d_n.alloc(8)))
+        return rc;
+    if (sbytes) PG_CUDA(cudaMemcpyAsync(d_s.p, seqs + s0, sbytes, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_soff.p, seq_offsets, (n_seq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (pbytes) PG_CUDA(cudaMemcpyAsync(d_p.p, patterns + p0, pbytes, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_poff.p, poff.data(), (n_pat + 1) * 8, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemsetAsync(d_n.p, 0, 8, st));
+    rc = launch_find_sites(d_s.as<uint8_t>() - s0, d_soff.as<uint64_t>(), n_seq, sbytes, d_p.as<uint8_t>(), d_poff.as<uint64_t>(), n_pat, pbytes,
+                           flags, d_hs.as<uint32_t>(), d_hp.as<uint64_t>(), d_hq.as<uint32_t>(), hits_cap, d_n.as<unsigned long long>(), st);
+    if (rc != PG_OK) return rc;
+    unsigned long long found = 0;
+    PG_CUDA(cudaMemcpyAsync(&found, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    *n_hits = found;
+    const uint64_t kept = std::min<uint64_t>(found, hits_cap);
+    if (kept) {
+        PG_CUDA(cudaMemcpyAsync(hit_seq, d_hs.p, kept * 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(hit_pos, d_hp.p, kept * 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(hit_pat, d_hq.p, kept * 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+    }
+    if (found > hits_cap) {
+        set_error("hits_cap %llu < %llu occurrences", (unsigned long long)hits_cap, found);
+        return PG_ERR_ARG;
+    }
+    return PG_OK;
+}
+
 int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
                         uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream) {

@@ -94,6 +94,13 @@ int launch_tm(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double 
               cudaStream_t st);
 int launch_design_primers(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double target,
                           uint32_t *d_fwd, uint32_t *d_rev, int32_t *d_status, cudaStream_t st);
+int launch_minimal_primer(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double target,
+                          uint32_t *d_min_len, int32_t *d_status, cudaStream_t st);
+// find_sites.cu
+int launch_find_sites(const uint8_t *d_seqs, const uint64_t *d_seq_off, uint64_t n_seq, uint64_t total_bytes,
+                      const uint8_t *d_pats, const uint64_t *d_pat_off, uint32_t n_pat, uint64_t pat_bytes, uint32_t flags,
+                      uint32_t *d_hit_seq, uint64_t *d_hit_pos, uint32_t *d_hit_pat, uint64_t cap,
+                      unsigned long long *d_n_hits, cudaStream_t st);
 // fastq_ingest.cu
 int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,

@@ -152,7 +152,45 @@ design_primers_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restr
     }
 }
 
+// pcr.SimulateSimple's minimal-primer loop, /root/reference/primers/pcr/pcr.go:93-100:
+//     for index := 15; MeltingTemp(primer[len-index:]) < targetTm; index++ {
+//         minimalLength = index; if primer[len-index:] == primer { break } }
+// i.e. the LONGEST 3' suffix (>= 15 nt) whose Tm is still below the target, 0 when the 15-mer
+// already reaches it, len when even the whole primer stays below.  One thread per primer.
+__global__ void __launch_bounds__(256)
+minimal_primer_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off, uint64_t n, double target,
+                      uint32_t *__restrict__ min_len, int32_t *__restrict__ status) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t beg = off[i], len = off[i + 1] - beg;
+    const uint8_t *s = bases + beg;
+    min_len[i] = 0;
+    bool ascii = true;
+    for (uint64_t j = 0; j < len; ++j) ascii &= __ldg(s + j) < 0x80;
+    if (!ascii) { status[i] = PG_ITEM_UNSUPPORTED; return; }
+    if (len < 15) { status[i] = PG_ITEM_PANIC; return; }  // primer[len(primer)-15:] out of range
+    const double cp = 500e-9, na = 50e-3, mg = 0.0;        // MeltingTemp defaults, primers.go:122-124
+    uint32_t minimal = 0;
+    for (uint64_t index = 15;; ++index) {
+        const uint8_t *suffix = s + (len - index);
+        const double tm = santalucia_core([suffix](uint64_t j) { return upper(__ldg(suffix + j)); }, index, cp, na, mg, nullptr, nullptr);
+        if (!(tm < target)) break;
+        minimal = (uint32_t)index;
+        if (index == len) break;
+    }
+    min_len[i] = minimal;
+    status[i] = PG_ITEM_OK;
+}
+
 }  // namespace
+
+int launch_minimal_primer(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double target,
+                          uint32_t *d_min_len, int32_t *d_status, cudaStream_t st) {
+    if (n == 0) return PG_OK;
+    minimal_primer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_bases, d_off, n, target, d_min_len, d_status);
+    PG_LAUNCH_CHECK("minimal_primer_kernel");
+    return PG_OK;
+}
 
 int launch_tm(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double cp, double na,
               double mg, double *d_tm, double *d_dh, double *d_ds, int32_t *d_status,
