@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "murmur3.cuh"
 #include "tma.cuh"
+#include "kmer_walk.cuh"
 
 namespace pg {
 
@@ -36,53 +37,6 @@ namespace pg {
 __host__ __device__ inline uint32_t k1_in_bytes(uint32_t R, uint32_t L) {
     return (R * L + 16u + 15u) & ~15u;
 }
-
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
-    uint32_t v;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-
-// kmix(b) for a single tail byte b, built at compile time
-struct KmixTable {
-    uint32_t v[256];
-};
-constexpr uint32_t c_rotl(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
-constexpr KmixTable make_kmix_table() {
-    KmixTable t{};
-    for (uint32_t b = 0; b < 256; ++b) t.v[b] = c_rotl(b * MM3_C1, 15) * MM3_C2;
-    return t;
-}
-__device__ __align__(16) const KmixTable g_kmix_byte = make_kmix_table();
-
-// One word step = 4 k-mers (ring slot U).  Uses the locals of the enclosing kernel.
-#define PG_K1_STEP(U, CHECKED)                                                                 \
-    {                                                                                          \
-        uint32_t w[4];                                                                         \
-        w[0] = w_cur;                                                                          \
-        w[1] = __funnelshift_r(w_cur, w_nxt, 8);                                               \
-        w[2] = __funnelshift_r(w_cur, w_nxt, 16);                                              \
-        w[3] = __funnelshift_r(w_cur, w_nxt, 24);                                              \
-        uint32_t h[4];                                                                         \
-        _Pragma("unroll") for (int r = 0; r < 4; ++r) {                                        \
-            uint32_t x = mm3_round0(ring[r][U]);                                               \
-            _Pragma("unroll") for (int j = 1; j < NB; ++j) x = mm3_round(x, ring[r][((U) + j) % NB]); \
-            if (LUT) x ^= lds_u32(sb[i + r] * lut_stride + lut_base);                          \
-            else if (TAIL) x ^= mm3_kmix(w[r] & TAILMASK);                                     \
-            x ^= (uint32_t)K;                                                                  \
-            h[r] = mm3_fmix(x);                                                                \
-            ring[r][U] = mm3_kmix(w[r]);                                                       \
-        }                                                                                      \
-        my_out[i] = h[0];                                                                      \
-        if (!(CHECKED) || i + 1 < nk) my_out[i + 1] = h[1];                                    \
-        if (!(CHECKED) || i + 2 < nk) my_out[i + 2] = h[2];                                    \
-        if (!(CHECKED) || i + 3 < nk) my_out[i + 3] = h[3];                                    \
-        w_cur = w_nxt;                                                                         \
-        w_nxt = __funnelshift_r(raw_a, raw_b, sh);                                             \
-        raw_a = raw_b;                                                                         \
-        raw_b = *swp++;                                                                        \
-        i += 4;                                                                                \
-    }
 
 // lut_stride == 4 arrives as a kernel argument so that the table address byte*4 + base
 // stays an IMAD (FMA pipe) instead of being strength-reduced to LEA (ALU pipe).
@@ -282,7 +236,6 @@ sketch_fill_ragged_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
         bulk_wait_read0();
     }
 }
-#undef PG_K1_STEP
 
 // ---- generic fill path -----------------------------------------------------------
 // One warp per read.  Handles reads with n = max(len-k,0) < s (others are left to the

@@ -19,10 +19,12 @@
 //            bitonic sort in shared memory.
 // Nothing but the read bytes and the s output words touches HBM.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "murmur3.cuh"
 #include "tma.cuh"
+#include "kmer_walk.cuh"
 
 namespace pg {
 
@@ -54,13 +56,14 @@ __device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_
 
 // exact selection: on return cand[0..s) holds the s smallest values (as a multiset) of
 // cand[0..cnt); returns the s-th smallest value.  All threads must call.
+template <int NT>
 __device__ uint32_t prune_to_s(const SelSmem &m, uint32_t cnt, uint32_t s) {
     const uint32_t tid = threadIdx.x;
     uint32_t prefix = 0, mask = 0, want = s;  // want: 1-based rank inside the current bucket
     for (int shift = 24; shift >= 0; shift -= 8) {
-        if (tid < 256) m.hist[tid] = 0;
+        for (uint32_t i = tid; i < 256; i += NT) m.hist[i] = 0;
         __syncthreads();
-        for (uint32_t i = tid; i < cnt; i += SEL_THREADS) {
+        for (uint32_t i = tid; i < cnt; i += NT) {
             const uint32_t e = m.cand[i];
             if ((e & mask) == prefix) atomicAdd(&m.hist[(e >> shift) & 255u], 1u);
         }
@@ -100,7 +103,7 @@ __device__ uint32_t prune_to_s(const SelSmem &m, uint32_t cnt, uint32_t s) {
     const uint32_t n_lt = s - need_eq;
     if (tid == 0) { m.misc[3] = 0; m.misc[4] = 0; }
     __syncthreads();
-    for (uint32_t i0 = 0; i0 < cnt; i0 += SEL_THREADS) {
+    for (uint32_t i0 = 0; i0 < cnt; i0 += NT) {
         const uint32_t i = i0 + tid;
         const uint32_t e = i < cnt ? m.cand[i] : 0xffffffffu;
         const bool lt = i < cnt && e < v;
@@ -121,16 +124,17 @@ __device__ uint32_t prune_to_s(const SelSmem &m, uint32_t cnt, uint32_t s) {
         }
     }
     __syncthreads();
-    for (uint32_t i = tid; i < s; i += SEL_THREADS) m.cand[i] = m.keep[i];
+    for (uint32_t i = tid; i < s; i += NT) m.cand[i] = m.keep[i];
     __syncthreads();
     return v;
 }
 
+template <int NT>
 __device__ void bitonic_sort(uint32_t *x, uint32_t P) {
     const uint32_t tid = threadIdx.x;
     for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
         for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
-            for (uint32_t t = tid; t < (P >> 1); t += SEL_THREADS) {
+            for (uint32_t t = tid; t < (P >> 1); t += NT) {
                 const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const uint32_t ixj = i | j;
                 const bool up = (i & k2) == 0;
@@ -145,17 +149,18 @@ __device__ void bitonic_sort(uint32_t *x, uint32_t P) {
 // Final stage, fast path.  cand[0..cnt) holds a superset of the bottom-s multiset (cnt >= s).
 // Writes the ascending bottom-s to dst and returns true, or returns false (nothing written) if
 // the buckets up to the threshold bucket do not fit the scratch area.  All threads must call.
+template <int NT>
 __device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, uint32_t *__restrict__ dst) {
     const uint32_t tid = threadIdx.x;
     uint32_t *bstart = m.hist;  // counts, then exclusive starts; [SEL_NBK] = total
     uint32_t *tmp = m.keep;
-    for (uint32_t i = tid; i <= SEL_NBK; i += SEL_THREADS) bstart[i] = 0;
+    for (uint32_t i = tid; i <= SEL_NBK; i += NT) bstart[i] = 0;
     if (tid == 0) { m.misc[6] = 0xffffffffu; m.misc[7] = 0; }
     __syncthreads();
-    for (uint32_t i = tid; i < cnt; i += SEL_THREADS) atomicAdd(&bstart[m.cand[i] >> SEL_BSHIFT], 1u);
+    for (uint32_t i = tid; i < cnt; i += NT) atomicAdd(&bstart[m.cand[i] >> SEL_BSHIFT], 1u);
     __syncthreads();
     // exclusive scan: 4 buckets per thread, warp scan, then the 16 warp totals
-    constexpr int PER = SEL_NBK / SEL_THREADS;
+    constexpr int PER = SEL_NBK / NT;
     uint32_t c[PER], sum = 0;
 #pragma unroll
     for (int j = 0; j < PER; ++j) { c[j] = bstart[tid * PER + j]; sum += c[j]; }
@@ -165,7 +170,7 @@ __device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, ui
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
         if ((int)(tid & 31u) >= d) incl += y;
     }
-    __shared__ uint32_t s_warp[SEL_THREADS / 32];
+    __shared__ uint32_t s_warp[NT / 32];
     if ((tid & 31u) == 31u) s_warp[tid >> 5] = incl;
     __syncthreads();
     uint32_t base = 0;
@@ -177,7 +182,7 @@ __device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, ui
         if (run < s && run + c[j] >= s) { m.misc[6] = tid * PER + j; m.misc[7] = run + c[j]; }  // threshold bucket
         run += c[j];
     }
-    if (tid == SEL_THREADS - 1) bstart[SEL_NBK] = run;
+    if (tid == NT - 1) bstart[SEL_NBK] = run;
     __syncthreads();
     const uint32_t bt = m.misc[6], need = m.misc[7];
     if (bt == 0xffffffffu || need > m.tmpcap) return false;
@@ -185,15 +190,15 @@ __device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, ui
     // sit right behind the scattered elements in the scratch area
     uint32_t *cursor = tmp + need;  // [bt + 1]
     if (need + bt + 1 > m.tmpcap) return false;
-    for (uint32_t i = tid; i <= bt; i += SEL_THREADS) cursor[i] = 0;
+    for (uint32_t i = tid; i <= bt; i += NT) cursor[i] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < cnt; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < cnt; i += NT) {
         const uint32_t e = m.cand[i], b = e >> SEL_BSHIFT;
         if (b <= bt) tmp[bstart[b] + atomicAdd(&cursor[b], 1u)] = e;
     }
     __syncthreads();
     // rank inside the bucket -> final position (ties keep distinct slots via the index tie-break)
-    for (uint32_t p = tid; p < need; p += SEL_THREADS) {
+    for (uint32_t p = tid; p < need; p += NT) {
         const uint32_t e = tmp[p], b = e >> SEL_BSHIFT;
         const uint32_t lo = bstart[b], hi = bstart[b + 1];
         uint32_t r = 0;
@@ -295,7 +300,7 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
             uint32_t cnt = m.misc[0];
             __syncthreads();
             if (cnt + ch > cap) {
-                limit = prune_to_s(m, cnt, s);
+                limit = prune_to_s<SEL_THREADS>(m, cnt, s);
                 if (tid == 0) m.misc[0] = s;
                 __syncthreads();
             }
@@ -338,11 +343,11 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
 
         uint32_t cnt = m.misc[0];
         __syncthreads();
-        if (!final_bucket_sort(m, cnt, s, dst)) {
-            if (cnt > s) prune_to_s(m, cnt, s);
+        if (!final_bucket_sort<SEL_THREADS>(m, cnt, s, dst)) {
+            if (cnt > s) prune_to_s<SEL_THREADS>(m, cnt, s);
             for (uint32_t i = s + tid; i < P; i += SEL_THREADS) m.cand[i] = 0xffffffffu;
             __syncthreads();
-            bitonic_sort(m.cand, P);
+            bitonic_sort<SEL_THREADS>(m.cand, P);
             for (uint32_t i = tid; i < s; i += SEL_THREADS) dst[i] = m.cand[i];
         }
         // fused all-gather: replicate the finished row into the gathered buffer of every rank
@@ -366,6 +371,240 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
     }
 }
 
+// ---- K2w: the select regime with the register-ring walk of K1 -----------------------------------
+// Same CTA-per-read streaming, candidate buffer, prune and final stage as sketch_select_kernel, but
+// the hashing of a chunk is K1's walk: thread t walks SELW_SEG consecutive k-mer positions of the
+// staged chunk with the block pre-mixes in a register ring (kmer_walk.cuh), so a k-mer costs its
+// body chain + fmix instead of k/4 shared-memory loads plus a loop, and no barrier separates a
+// pre-mix phase from a hash phase.  While no prune has happened every hash is a candidate and is
+// stored positionally (lane stride SELW_SEG = 17 words: conflict-free); afterwards the walk itself
+// tests each hash against the admission limit and appends the few that pass (one shared-memory
+// atomic each) -- for long sequences almost nothing passes, so the steady state is pure hashing.
+// Half the instructions of the generic kernel (ncu: 0.74 G vs 1.46 G warp instructions on 20 k
+// cfg3 reads); 256 threads x 3 CTAs per SM keep the issue slots busy.
+constexpr int SELW_THREADS = 256;
+constexpr int SELW_SEG = 17;
+constexpr int SELW_CHUNK = SELW_THREADS * SELW_SEG;                      // 4352 k-mer positions
+constexpr int SELW_STAGE_WORDS = (15 + SELW_CHUNK + 32 + 48 + 15) / 16 * 4;  // head + chunk + k + over-read pad
+
+#define PG_EMIT_ADMIT(R_, H_)                                              \
+    if ((H_) < limit32) {                                                  \
+        m.cand[atomicAdd(&m.misc[0], 1u)] = (H_);                          \
+        if (s == 1) atomicMin(&m.misc[5], (H_));                           \
+    }
+
+template <int K>
+__global__ void __launch_bounds__(SELW_THREADS)
+sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
+                          uint32_t uniform_len, uint64_t n_reads, uint32_t s, uint32_t P, uint32_t cap,
+                          uint32_t *__restrict__ out, uint64_t row_stride, uint32_t *__restrict__ count,
+                          int32_t *__restrict__ status, const SketchDst extra, uint32_t lut_stride) {
+    constexpr int NB = K / 4;
+    constexpr int TAIL = K % 4;
+    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
+    constexpr bool LUT = TAIL == 1;
+    constexpr uint32_t k = K;
+    static_assert(NB >= 1 && K <= 32, "walk path: 4 <= k <= 32");
+
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    SelSmem m;
+    m.cand = smem_w;
+    m.keep = m.cand + cap;
+    m.kv = nullptr;
+    m.bytes = m.keep + ((s + 3u) & ~3u) + 4u;  // 16-byte granules keep the TMA stage buffers aligned
+    m.hist = m.bytes + 2 * SELW_STAGE_WORDS;
+    m.misc = m.hist + SEL_NBK + 1;
+    m.tmpcap = (uint32_t)(m.hist - m.keep);
+
+    __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
+    __shared__ __align__(8) uint64_t s_bar[3];
+    uint32_t par0 = 0u, par1 = 0u;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
+        fence_mbar_init();
+        if (LUT) {
+            mbar_expect_tx(&s_bar[2], 1024u);
+            bulk_g2s(s_lut, &g_kmix_byte, 1024u, &s_bar[2]);
+        }
+    }
+    __syncthreads();
+    if (LUT) mbar_wait(&s_bar[2], 0);
+    const uint32_t lut_base = smem_u32(s_lut);
+
+    for (uint64_t row = blockIdx.x; row < n_reads; row += gridDim.x) {
+        uint64_t beg, len;
+        if (offsets) {
+            beg = offsets[row];
+            len = offsets[row + 1] - beg;
+        } else {
+            beg = row * (uint64_t)uniform_len;
+            len = uniform_len;
+        }
+        const uint64_t n = len > k ? len - k : 0;
+        if (n < s || n == 0) continue;  // fill regime: other kernel
+        const uint8_t *seq = bases + beg;
+        uint32_t *dst = out + row * row_stride;
+        if (s == 0) {  // mash.go:96 reads Sketches[-1] on the first k-mer
+            if (tid == 0) {
+                if (status) status[row] = PG_ITEM_PANIC;
+                if (count) count[row] = 0;
+            }
+            continue;
+        }
+        if (tid == 0) { m.misc[0] = 0; m.misc[5] = 0xffffffffu; }
+        __syncthreads();
+        uint64_t limit = 1ull << 32;  // admit h < limit
+        uint32_t h_first = 0;
+
+        auto issue_stage = [&](uint64_t c0, uint32_t buf) {
+            const uint32_t ch = (uint32_t)min((uint64_t)SELW_CHUNK, n - c0);
+            const uint32_t nbytes = ch + k;
+            const uint8_t *src = seq + c0;
+            const uint32_t head = (uint32_t)((uintptr_t)src & 15u);
+            const uint32_t body = (head + nbytes) & ~15u;
+            uint8_t *sb8 = reinterpret_cast<uint8_t *>(m.bytes + buf * SELW_STAGE_WORDS);
+            if (tid == 0) {
+                if (body) {
+                    mbar_expect_tx(&s_bar[buf], body);
+                    bulk_g2s(sb8, src - head, body, &s_bar[buf]);
+                } else {
+                    mbar_expect_tx(&s_bar[buf], 0);
+                }
+            }
+            for (uint32_t i = body + tid; i < head + nbytes + 32; i += SELW_THREADS)  // tail + over-read pad
+                sb8[i] = i < head + nbytes ? __ldg(src - head + i) : (uint8_t)0;
+        };
+        issue_stage(0, 0);
+        uint32_t chunk_idx = 0;
+        for (uint64_t c0 = 0; c0 < n; c0 += SELW_CHUNK, ++chunk_idx) {
+            const uint32_t ch = (uint32_t)min((uint64_t)SELW_CHUNK, n - c0);
+            const uint32_t buf = chunk_idx & 1u;
+            if (c0 + SELW_CHUNK < n) issue_stage(c0 + SELW_CHUNK, buf ^ 1u);
+            const uint32_t head = (uint32_t)((uintptr_t)(seq + c0) & 15u);
+            const uint8_t *stage = reinterpret_cast<const uint8_t *>(m.bytes + buf * SELW_STAGE_WORDS);
+            if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1u; }
+            else          { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
+            uint32_t cnt = m.misc[0];
+            __syncthreads();  // also: the plain-store part of this stage is visible
+            if (cnt + ch > cap) {  // worst case every hash of the chunk is admitted
+                limit = prune_to_s<SELW_THREADS>(m, cnt, s);
+                if (tid == 0) m.misc[0] = s;
+                cnt = s;
+                __syncthreads();
+            }
+            const bool unfiltered = limit == (1ull << 32);
+            const uint32_t limit32 = (uint32_t)limit;
+
+            // the walk: my segment = positions [seg, seg + nk) of the chunk
+            const uint32_t seg = tid * SELW_SEG;
+            if (seg < ch) {
+                const uint32_t nk = min((uint32_t)SELW_SEG, ch - seg);
+                const uint32_t b0 = head + seg;
+                const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (b0 >> 2);
+                const uint8_t *sb = stage + b0 + 4 * NB;
+                const uint32_t sh = (b0 & 3u) * 8u;
+                uint32_t *my_out = m.cand + cnt + seg;  // positional target while unfiltered
+                uint32_t raw_a = sw[0], raw_b = sw[1];
+                uint32_t w_cur = __funnelshift_r(raw_a, raw_b, sh);
+                raw_a = raw_b; raw_b = sw[2];
+                uint32_t w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+                raw_a = raw_b; raw_b = sw[3];
+                const uint32_t *swp = sw + 4;
+                uint32_t ring[4][NB];
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    ring[0][q] = mm3_kmix(w_cur);
+                    ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
+                    ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
+                    ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
+                    w_cur = w_nxt;
+                    w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+                    raw_a = raw_b;
+                    raw_b = *swp++;
+                }
+                uint32_t i = 0;
+                if (unfiltered) {
+#pragma unroll 1
+                    while (i < nk) {
+#pragma unroll
+                        for (int u = 0; u < NB; ++u) {
+                            if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_POSITIONAL)
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    while (i < nk) {
+#pragma unroll
+                        for (int u = 0; u < NB; ++u) {
+                            if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_ADMIT)
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (unfiltered) {
+                if (c0 == 0 && tid == 0) h_first = m.cand[cnt];
+                if (s == 1) {  // mash.go:96-98: a later hash strictly below Sketches[0] indexes Sketches[-1]
+                    for (uint32_t q = tid; q < ch; q += SELW_THREADS)
+                        if (c0 + q > 0) atomicMin(&m.misc[5], m.cand[cnt + q]);
+                }
+                if (tid == 0) m.misc[0] = cnt + ch;
+                __syncthreads();
+            }
+        }
+
+        uint32_t cnt = m.misc[0];
+        __syncthreads();
+        if (!final_bucket_sort<SELW_THREADS>(m, cnt, s, dst)) {
+            if (cnt > s) prune_to_s<SELW_THREADS>(m, cnt, s);
+            for (uint32_t i = s + tid; i < P; i += SELW_THREADS) m.cand[i] = 0xffffffffu;
+            __syncthreads();
+            bitonic_sort<SELW_THREADS>(m.cand, P);
+            for (uint32_t i = tid; i < s; i += SELW_THREADS) dst[i] = m.cand[i];
+        }
+        if (extra.n > 0) {  // fused all-gather: replicate the finished row into every rank's buffer
+            __syncthreads();
+#pragma unroll
+            for (int pr = 0; pr < PG_MAX_PEERS; ++pr) {  // static indices: the struct stays in parameter space
+                if (pr >= extra.n) continue;
+                uint32_t *peer = extra.ptr[pr] + row * row_stride;
+                if (peer == dst) continue;
+                for (uint32_t i = tid; i < s; i += SELW_THREADS) peer[i] = dst[i];
+            }
+        }
+        if (tid == 0) {
+            int32_t st = PG_ITEM_OK;
+            if (s == 1 && m.misc[5] < h_first) st = PG_ITEM_PANIC;
+            if (status) status[row] = st;
+            if (count) count[row] = s;
+        }
+        __syncthreads();
+    }
+}
+#undef PG_EMIT_ADMIT
+
+template <int K>
+static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
+                              uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
+                              cudaStream_t st, const SketchDst &ex) {
+    const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + 2 * SELW_CHUNK) + 3u) & ~3u;
+    const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + 2 * SELW_STAGE_WORDS + (SEL_NBK + 1) + 8;
+    const size_t smem = words * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PG_CUDA(cudaFuncSetAttribute(sketch_select_walk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 4);
+    sketch_select_walk_kernel<K><<<(unsigned)blocks, SELW_THREADS, smem, st>>>(d_bases, d_offsets, read_len, n_reads, (uint32_t)s, P, cap,
+                                                                              d_out, row_stride, d_count, d_status, ex, 4u);
+    PG_LAUNCH_CHECK("sketch_select_walk_kernel");
+    return PG_OK;
+}
+
 }  // namespace
 
 int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len,
@@ -387,6 +626,19 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     uint32_t P = 1;
     while (P < (uint32_t)std::max(s, 1)) P <<= 1;
     if (P < 2) P = 2;
+    // K2w (register-ring walk) for the instantiated k; PG_K2_GENERIC=1 forces the generic kernel (A/B knob)
+    static const bool force_generic = [] { const char *e = getenv("PG_K2_GENERIC"); return e && atoi(e) != 0; }();
+    if (!force_generic && (size_t)s * 8 + 56 * 1024 <= 227 * 1024) {  // shared memory of the walk kernel
+        switch (k) {
+#define PG_K2W_CASE(KK) \
+    case KK: return launch_select_walk<KK>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex);
+            PG_K2W_CASE(11) PG_K2W_CASE(13) PG_K2W_CASE(15) PG_K2W_CASE(16) PG_K2W_CASE(17) PG_K2W_CASE(19)
+            PG_K2W_CASE(21) PG_K2W_CASE(23) PG_K2W_CASE(24) PG_K2W_CASE(25) PG_K2W_CASE(27) PG_K2W_CASE(29)
+            PG_K2W_CASE(31) PG_K2W_CASE(32)
+#undef PG_K2W_CASE
+            default: break;
+        }
+    }
     uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + 4 * SEL_CHUNK) + 3u) & ~3u;
     const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + (SEL_CHUNK + SEL_LOOKAHEAD) +
                          2 * SEL_STAGE_WORDS + (SEL_NBK + 1) + 8;

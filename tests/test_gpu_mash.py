@@ -127,6 +127,28 @@ def test_select_regime_duplicates_and_ties(gpu, oracle):
             assert np.array_equal(out[i, : count[i]], o.Sketches[: count[i]]), (k, s, L, i)
 
 
+def test_select_regime_long_reads_with_pruning(gpu, oracle):
+    """Reads far longer than the candidate buffer: chunked streaming, admission limit, repeated exact
+    prunes; ragged lengths at arbitrary byte alignment; low-complexity reads for ties."""
+    rng = np.random.default_rng(31)
+    for k, s in [(21, 1000), (31, 2000), (16, 64), (32, 3), (13, 1), (24, 5000), (20, 300)]:
+        lens = [int(x) for x in rng.integers(30_000, 120_000, 4)] + [4224 + k, 4225 + k, 2 * 4224 + k + 1, s + k, s + k + 1]
+        seqs = [bytes(rng.choice(list(b"ACGT"), size=l).astype(np.uint8)) for l in lens]
+        seqs.append(bytes(rng.choice(list(b"AC"), size=70_001).astype(np.uint8)))
+        seqs.append(b"ACG" * 20_000)
+        bases, offsets = mash.flatten(seqs)
+        out, count, status = mash.sketch_arrays(bases, offsets, k, s)
+        for i, q in enumerate(seqs):
+            o = oracle.OracleMash(k, s)
+            rc = o.Sketch(q, faithful=False)
+            if rc != 0:
+                assert status[i] == 1, (k, s, i)
+                continue
+            cnt = min(len(q) - k, s)
+            assert status[i] == 0 and count[i] == cnt, (k, s, i)
+            assert np.array_equal(out[i, :cnt], o.Sketches[:cnt]), (k, s, i, len(q))
+
+
 def test_cfg3_shape_sample_golden(gpu, oracle):
     """8 family reads of the cfg3 shape (10 kbp, k=31, s=2000, R=4): SURVEY 8d goldens."""
     n, L, k, s = 8, 10000, 31, 2000

@@ -19,6 +19,7 @@ ap.add_argument("--reads", type=int, default=100_000)
 ap.add_argument("--rows", type=int, default=512, help="row block of the all-pairs matrix to time")
 ap.add_argument("--primers", type=int, default=1_000_000)
 ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--only-k2", action="store_true", help="stop after the K2 legs (A/B runs with PG_K2_GENERIC=1)")
 args = ap.parse_args()
 
 L = _lib.lib()
@@ -49,6 +50,19 @@ ms = timed(lambda: _lib.check(L.pg_mash_sketch_uniform_dev(d_reads.data_ptr(), n
 alg = n * (RL + 4 * s)
 print(json.dumps({"kernel": "K2 sketch_select (cfg3)", "reads": n, "read_len": RL, "k": k, "s": s, "ms": ms,
                   "gbases_per_s": n * RL / ms / 1e6, "algorithmic_GBps": alg / ms / 1e6, "kernel_name": L.pg_last_kernel().decode()}))
+# genome-scale select regime: 256 sequences x 4 Mbp, k=21, s=1000 (n/s = 4000: the admission limit does the work)
+gn, gL, gk, gs = 256, 4_000_000, 21, 1000
+d_gen = torch.empty(gn * gL, dtype=torch.uint8, device=dev)
+_lib.check(L.pg_synth_reads_dev(d_gen.data_ptr(), 0, gn, gL, synth.SEED_READS + 7, 0, 1, st))
+d_gsk = torch.empty((gn, gs), dtype=torch.int32, device=dev)
+ms_g = timed(lambda: _lib.check(L.pg_mash_sketch_uniform_dev(d_gen.data_ptr(), gn, gL, gk, gs, 0, d_gsk.data_ptr(), gs, None, st)))
+g = d_gsk.cpu().numpy().view(np.uint32)
+print(json.dumps({"kernel": "K2 sketch_select (256 x 4 Mbp genomes)", "k": gk, "s": gs, "ms": ms_g, "gbases_per_s": gn * gL / ms_g / 1e6,
+                  "ascending": bool((np.diff(g.astype(np.int64), axis=1) >= 0).all()), "fnv": hex(synth.fnv1a64(g)),
+                  "kernel_name": L.pg_last_kernel().decode()}))
+del d_gen
+if args.only_k2:
+    sys.exit(0)
 rows = min(args.rows, n)
 d_same = torch.empty((rows, n), dtype=torch.int32, device=dev)
 ms = timed(lambda: _lib.check(L.pg_mash_distance_block_dev(d_sk.data_ptr(), n, s, 0, rows, d_same.data_ptr(), None, st)), iters=1, warm=1)
