@@ -20,6 +20,7 @@
 // Nothing but the read bytes and the s output words touches HBM.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 #include "murmur3.cuh"
@@ -44,7 +45,7 @@ struct SelSmem {
     uint32_t *kv;     // [SEL_CHUNK + SEL_LOOKAHEAD]
     uint32_t *bytes;  // 2 x [SEL_STAGE_WORDS] staged read bytes (word view), double-buffered
     uint32_t *hist;   // [SEL_NBK + 1] (radix select uses the first 256 words)
-    uint32_t *misc;   // [8]: 0 cnt, 1 prefix, 2 want, 3 kept_lt, 4 kept_eq, 5 hmin_later, 6 bt, 7 need
+    uint32_t *misc;   // [8]: 0 cnt, 1 prefix, 2 want, 3 kept_lt, 4 kept_eq, 5 hmin_later, 6 bt, 7 need (K2w: 8..10 per-chunk counters)
     uint32_t tmpcap;  // words available at keep[] for the final scatter (keep+kv+bytes are contiguous)
 };
 
@@ -376,29 +377,38 @@ sketch_select_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restri
 // the hashing of a chunk is K1's walk: thread t walks SELW_SEG consecutive k-mer positions of the
 // staged chunk with the block pre-mixes in a register ring (kmer_walk.cuh), so a k-mer costs its
 // body chain + fmix instead of k/4 shared-memory loads plus a loop, and no barrier separates a
-// pre-mix phase from a hash phase.  While no prune has happened every hash is a candidate and is
-// stored positionally (lane stride SELW_SEG = 17 words: conflict-free); afterwards the walk itself
-// tests each hash against the admission limit and appends the few that pass (one shared-memory
-// atomic each) -- for long sequences almost nothing passes, so the steady state is pure hashing.
+// pre-mix phase from a hash phase.  Lanes read the staged bytes 20 bytes (5 words) apart, which
+// is bank-conflict free.  While no prune has happened every hash is a candidate: full chunks store
+// them transposed (k-mer j of thread t at [j][t]: conflict-free, order is irrelevant for a
+// multiset), a partial last chunk stores them positionally; afterwards the walk itself tests each hash
+// against the admission limit and appends the few that pass (one shared-memory atomic each) --
+// for long sequences almost nothing passes, so the steady state is pure hashing.
 // Half the instructions of the generic kernel (ncu: 0.74 G vs 1.46 G warp instructions on 20 k
 // cfg3 reads); 256 threads x 3 CTAs per SM keep the issue slots busy.
 constexpr int SELW_THREADS = 256;
-constexpr int SELW_SEG = 17;
-constexpr int SELW_CHUNK = SELW_THREADS * SELW_SEG;                      // 4352 k-mer positions
+constexpr int SELW_SEG = 20;  // bytes between the segments of adjacent lanes = 5 words: conflict-free smem reads
+constexpr int SELW_CHUNK = SELW_THREADS * SELW_SEG;                      // 5120 k-mer positions
+constexpr int SELW_ROOM = 8192;                                          // candidate room beyond s
 constexpr int SELW_STAGE_WORDS = (15 + SELW_CHUNK + 32 + 48 + 15) / 16 * 4;  // head + chunk + k + over-read pad
 
 #define PG_EMIT_ADMIT(R_, H_)                                              \
     if ((H_) < limit32) {                                                  \
-        m.cand[atomicAdd(&m.misc[0], 1u)] = (H_);                          \
+        m.cand[cnt + atomicAdd(chunk_ctr, 1u)] = (H_);                     \
         if (s == 1) atomicMin(&m.misc[5], (H_));                           \
     }
+// unfiltered, full chunk: k-mer i + r of this thread -> row i + r of a [SELW_SEG][SELW_THREADS] tile
+#define PG_EMIT_TRANSPOSED(R_, H_) my_out[(i + (R_)) * SELW_THREADS] = (H_)
+// unfiltered, partial chunk: positional (lane stride SELW_SEG words: 4-way conflicts, last chunk only)
+#define PG_EMIT_APPEND(R_, H_) my_pos[i + (R_)] = (H_)
 
 template <int K>
 __global__ void __launch_bounds__(SELW_THREADS)
 sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
                           uint32_t uniform_len, uint64_t n_reads, uint32_t s, uint32_t P, uint32_t cap,
                           uint32_t *__restrict__ out, uint64_t row_stride, uint32_t *__restrict__ count,
-                          int32_t *__restrict__ status, const SketchDst extra, uint32_t lut_stride) {
+                          int32_t *__restrict__ status, const SketchDst extra, uint32_t lut_stride,
+                          const uint64_t *__restrict__ slice_beg, const uint32_t *__restrict__ slice_n,
+                          unsigned long long *__restrict__ next_row) {
     constexpr int NB = K / 4;
     constexpr int TAIL = K % 4;
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
@@ -434,16 +444,30 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     if (LUT) mbar_wait(&s_bar[2], 0);
     const uint32_t lut_base = smem_u32(s_lut);
 
-    for (uint64_t row = blockIdx.x; row < n_reads; row += gridDim.x) {
-        uint64_t beg, len;
-        if (offsets) {
-            beg = offsets[row];
-            len = offsets[row + 1] - beg;
+    // rows are handed out dynamically (reads / slices differ in length): the grid is exactly the
+    // resident CTA count, every CTA takes the next row when it is done
+    __shared__ unsigned long long s_row;
+    for (;;) {
+        if (tid == 0) s_row = atomicAdd(next_row, 1ull);
+        __syncthreads();
+        const uint64_t row = s_row;
+        __syncthreads();
+        if (row >= n_reads) break;
+        uint64_t beg, n;
+        if (slice_beg) {  // `row` is a slice of a long sequence: k-mer positions [beg, beg + n)
+            beg = slice_beg[row];
+            n = slice_n[row];
         } else {
-            beg = row * (uint64_t)uniform_len;
-            len = uniform_len;
+            uint64_t len;
+            if (offsets) {
+                beg = offsets[row];
+                len = offsets[row + 1] - beg;
+            } else {
+                beg = row * (uint64_t)uniform_len;
+                len = uniform_len;
+            }
+            n = len > k ? len - k : 0;
         }
-        const uint64_t n = len > k ? len - k : 0;
         if (n < s || n == 0) continue;  // fill regime: other kernel
         const uint8_t *seq = bases + beg;
         uint32_t *dst = out + row * row_stride;
@@ -454,17 +478,23 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
             }
             continue;
         }
-        if (tid == 0) { m.misc[0] = 0; m.misc[5] = 0xffffffffu; }
+        if (tid == 0) { m.misc[5] = 0xffffffffu; m.misc[8] = 0; m.misc[9] = 0; m.misc[10] = 0; }
         __syncthreads();
         uint64_t limit = 1ull << 32;  // admit h < limit
         uint32_t h_first = 0;
+        uint32_t cnt = 0;  // candidates held (uniform across the CTA)
 
+        // A chunk that is not the last of its row may over-read up to 15 bytes (they belong to the
+        // same sequence): the whole stage is then one TMA copy.  Otherwise the 16-byte aligned body
+        // comes by TMA and the tail by plain loads (+ a barrier before use).
+        auto tail_by_tma = [&](uint64_t c0, uint32_t ch) { return n - (c0 + ch) >= 16; };
         auto issue_stage = [&](uint64_t c0, uint32_t buf) {
             const uint32_t ch = (uint32_t)min((uint64_t)SELW_CHUNK, n - c0);
             const uint32_t nbytes = ch + k;
             const uint8_t *src = seq + c0;
             const uint32_t head = (uint32_t)((uintptr_t)src & 15u);
-            const uint32_t body = (head + nbytes) & ~15u;
+            const bool all_tma = tail_by_tma(c0, ch);
+            const uint32_t body = all_tma ? (head + nbytes + 15u) & ~15u : (head + nbytes) & ~15u;
             uint8_t *sb8 = reinterpret_cast<uint8_t *>(m.bytes + buf * SELW_STAGE_WORDS);
             if (tid == 0) {
                 if (body) {
@@ -474,28 +504,28 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
                     mbar_expect_tx(&s_bar[buf], 0);
                 }
             }
-            for (uint32_t i = body + tid; i < head + nbytes + 32; i += SELW_THREADS)  // tail + over-read pad
-                sb8[i] = i < head + nbytes ? __ldg(src - head + i) : (uint8_t)0;
+            if (!all_tma)
+                for (uint32_t i = body + tid; i < head + nbytes + 32; i += SELW_THREADS)  // tail + over-read pad
+                    sb8[i] = i < head + nbytes ? __ldg(src - head + i) : (uint8_t)0;
         };
         issue_stage(0, 0);
         uint32_t chunk_idx = 0;
         for (uint64_t c0 = 0; c0 < n; c0 += SELW_CHUNK, ++chunk_idx) {
             const uint32_t ch = (uint32_t)min((uint64_t)SELW_CHUNK, n - c0);
             const uint32_t buf = chunk_idx & 1u;
-            if (c0 + SELW_CHUNK < n) issue_stage(c0 + SELW_CHUNK, buf ^ 1u);
+            if (c0 + SELW_CHUNK < n) issue_stage(c0 + SELW_CHUNK, buf ^ 1u);  // its last readers passed the barrier below
             const uint32_t head = (uint32_t)((uintptr_t)(seq + c0) & 15u);
             const uint8_t *stage = reinterpret_cast<const uint8_t *>(m.bytes + buf * SELW_STAGE_WORDS);
             if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1u; }
             else          { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
-            uint32_t cnt = m.misc[0];
-            __syncthreads();  // also: the plain-store part of this stage is visible
+            if (!tail_by_tma(c0, ch)) __syncthreads();  // plain-store part of this stage
             if (cnt + ch > cap) {  // worst case every hash of the chunk is admitted
                 limit = prune_to_s<SELW_THREADS>(m, cnt, s);
-                if (tid == 0) m.misc[0] = s;
                 cnt = s;
-                __syncthreads();
             }
+            uint32_t *chunk_ctr = &m.misc[8 + chunk_idx % 3u];  // admitted by this chunk (zeroed two chunks ago)
             const bool unfiltered = limit == (1ull << 32);
+            const bool full_chunk = ch == SELW_CHUNK;
             const uint32_t limit32 = (uint32_t)limit;
 
             // the walk: my segment = positions [seg, seg + nk) of the chunk
@@ -506,7 +536,8 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
                 const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (b0 >> 2);
                 const uint8_t *sb = stage + b0 + 4 * NB;
                 const uint32_t sh = (b0 & 3u) * 8u;
-                uint32_t *my_out = m.cand + cnt + seg;  // positional target while unfiltered
+                uint32_t *my_out = m.cand + cnt + tid;  // transposed target (full chunk, unfiltered)
+                uint32_t *my_pos = m.cand + cnt + seg;  // positional target (partial chunk, unfiltered)
                 uint32_t raw_a = sw[0], raw_b = sw[1];
                 uint32_t w_cur = __funnelshift_r(raw_a, raw_b, sh);
                 raw_a = raw_b; raw_b = sw[2];
@@ -526,37 +557,30 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
                     raw_b = *swp++;
                 }
                 uint32_t i = 0;
-                if (unfiltered) {
-#pragma unroll 1
-                    while (i < nk) {
-#pragma unroll
-                        for (int u = 0; u < NB; ++u) {
-                            if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_POSITIONAL)
-                        }
-                    }
-                } else {
-#pragma unroll 1
-                    while (i < nk) {
-#pragma unroll
-                        for (int u = 0; u < NB; ++u) {
-                            if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_ADMIT)
-                        }
-                    }
-                }
+#define PG_WALK_SEGMENT(EMIT)                                              \
+    _Pragma("unroll 1") while (i < nk) {                                   \
+        _Pragma("unroll") for (int u = 0; u < NB; ++u) {                   \
+            if (i < nk) PG_KMER_STEP(u, true, EMIT)                        \
+        }                                                                  \
+    }
+                if (!unfiltered) PG_WALK_SEGMENT(PG_EMIT_ADMIT)
+                else if (full_chunk) PG_WALK_SEGMENT(PG_EMIT_TRANSPOSED)
+                else PG_WALK_SEGMENT(PG_EMIT_APPEND)
+#undef PG_WALK_SEGMENT
             }
-            __syncthreads();
-            if (unfiltered) {
+            __syncthreads();  // the one barrier per chunk: hashes / admissions of the chunk are in place
+            if (unfiltered) {  // position 0 of the chunk is index 0 in both layouts
                 if (c0 == 0 && tid == 0) h_first = m.cand[cnt];
                 if (s == 1) {  // mash.go:96-98: a later hash strictly below Sketches[0] indexes Sketches[-1]
                     for (uint32_t q = tid; q < ch; q += SELW_THREADS)
                         if (c0 + q > 0) atomicMin(&m.misc[5], m.cand[cnt + q]);
                 }
-                if (tid == 0) m.misc[0] = cnt + ch;
-                __syncthreads();
+                cnt += ch;
+            } else {
+                cnt += *chunk_ctr;
             }
+            if (tid == 0) m.misc[8 + (chunk_idx + 2) % 3u] = 0;  // next use: chunk_idx + 2, after the next barrier
         }
-
-        uint32_t cnt = m.misc[0];
         __syncthreads();
         if (!final_bucket_sort<SELW_THREADS>(m, cnt, s, dst)) {
             if (cnt > s) prune_to_s<SELW_THREADS>(m, cnt, s);
@@ -585,24 +609,200 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     }
 }
 #undef PG_EMIT_ADMIT
+#undef PG_EMIT_TRANSPOSED
+#undef PG_EMIT_APPEND
+
+// ---- merge of partial sketches (long sequences cut into slices) ---------------------------------
+// The bottom-s multiset of a sequence is the bottom-s multiset of the union of the bottom-s multisets
+// of its slices.  One CTA per row streams the row's partial sketches (slices are consecutive in
+// `part`, s ascending words each) through the same candidate buffer / admission limit / prune /
+// final stage as the hashing kernels.
+constexpr int SELM_THREADS = 256;
+constexpr int SELM_CHUNK = 4096;
+
+__global__ void __launch_bounds__(SELM_THREADS)
+select_merge_kernel(const uint32_t *__restrict__ part, const uint32_t *__restrict__ row_slice0, uint64_t n_rows,
+                    uint32_t s, uint32_t P, uint32_t cap, uint32_t *__restrict__ out, uint64_t row_stride,
+                    uint32_t *__restrict__ count, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    SelSmem m;
+    m.cand = smem_w;
+    m.keep = m.cand + cap;
+    m.kv = nullptr;
+    m.bytes = nullptr;
+    m.hist = m.keep + s + SEL_NBK + 64;  // scratch of the final stage: s + ties + one cursor per bucket
+    m.misc = m.hist + SEL_NBK + 1;
+    m.tmpcap = (uint32_t)(m.hist - m.keep);
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const uint32_t sl0 = row_slice0[row], sl1 = row_slice0[row + 1];
+        if (sl1 == sl0) continue;  // not a select-regime row
+        uint32_t *dst = out + row * row_stride;
+        const uint32_t *src = part + (uint64_t)sl0 * s;
+        if (sl1 - sl0 == 1) {  // a single slice is already the answer
+            for (uint32_t i = tid; i < s; i += SELM_THREADS) dst[i] = src[i];
+        } else {
+            const uint64_t total = (uint64_t)(sl1 - sl0) * s;
+            if (tid == 0) m.misc[0] = 0;
+            __syncthreads();
+            uint64_t limit = 1ull << 32;
+            for (uint64_t c0 = 0; c0 < total; c0 += SELM_CHUNK) {
+                const uint32_t ch = (uint32_t)min((uint64_t)SELM_CHUNK, total - c0);
+                uint32_t cnt = m.misc[0];
+                __syncthreads();
+                if (cnt + ch > cap) {
+                    limit = prune_to_s<SELM_THREADS>(m, cnt, s);
+                    if (tid == 0) m.misc[0] = s;
+                    cnt = s;
+                    __syncthreads();
+                }
+                if (limit == (1ull << 32)) {
+                    for (uint32_t q = tid; q < ch; q += SELM_THREADS) m.cand[cnt + q] = __ldg(src + c0 + q);
+                    __syncthreads();
+                    if (tid == 0) m.misc[0] = cnt + ch;
+                } else {
+                    const uint32_t limit32 = (uint32_t)limit;
+                    for (uint32_t q = tid; q < ch; q += SELM_THREADS) {
+                        const uint32_t h = __ldg(src + c0 + q);
+                        if (h < limit32) m.cand[atomicAdd(&m.misc[0], 1u)] = h;
+                    }
+                }
+                __syncthreads();
+            }
+            const uint32_t cnt = m.misc[0];
+            __syncthreads();
+            if (!final_bucket_sort<SELM_THREADS>(m, cnt, s, dst)) {
+                if (cnt > s) prune_to_s<SELM_THREADS>(m, cnt, s);
+                for (uint32_t i = s + tid; i < P; i += SELM_THREADS) m.cand[i] = 0xffffffffu;
+                __syncthreads();
+                bitonic_sort<SELM_THREADS>(m.cand, P);
+                for (uint32_t i = tid; i < s; i += SELM_THREADS) dst[i] = m.cand[i];
+            }
+        }
+        if (tid == 0) {
+            if (status) status[row] = PG_ITEM_OK;
+            if (count) count[row] = s;
+        }
+        __syncthreads();
+    }
+}
 
 template <int K>
 static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
                               uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
-                              cudaStream_t st, const SketchDst &ex) {
-    const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + 2 * SELW_CHUNK) + 3u) & ~3u;
-    const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + 2 * SELW_STAGE_WORDS + (SEL_NBK + 1) + 8;
+                              cudaStream_t st, const SketchDst &ex, const uint64_t *d_slice_beg = nullptr,
+                              const uint32_t *d_slice_n = nullptr) {
+    const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + SELW_ROOM) + 3u) & ~3u;
+    const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + 2 * SELW_STAGE_WORDS + (SEL_NBK + 1) + 16;
     const size_t smem = words * 4;
     static size_t configured = 0;
     if (smem > configured) {
         PG_CUDA(cudaFuncSetAttribute(sketch_select_walk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 4);
+    int per_sm = 1;
+    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_select_walk_kernel<K>, SELW_THREADS, smem));
+    const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * std::max(per_sm, 1));
+    unsigned long long *d_next = nullptr;
+    PG_CUDA(cudaMallocAsync(&d_next, 8, st));
+    PG_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
     sketch_select_walk_kernel<K><<<(unsigned)blocks, SELW_THREADS, smem, st>>>(d_bases, d_offsets, read_len, n_reads, (uint32_t)s, P, cap,
-                                                                              d_out, row_stride, d_count, d_status, ex, 4u);
+                                                                              d_out, row_stride, d_count, d_status, ex, 4u, d_slice_beg,
+                                                                              d_slice_n, d_next);
+    cudaFreeAsync(d_next, st);
     PG_LAUNCH_CHECK("sketch_select_walk_kernel");
     return PG_OK;
+}
+
+// Few, long sequences (genomes): one CTA per sequence leaves the GPU idle.  Cut every
+// select-regime row into slices of >= max(4 chunks, 8 s) k-mer positions (about 8 slices per
+// resident CTA slot over the whole batch), sketch the slices independently, merge per row.
+// *sliced = false when slicing would not add parallelism (the caller then runs the direct path).
+template <int K>
+static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
+                             uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
+                             cudaStream_t st, bool *sliced) {
+    *sliced = false;
+    const uint64_t slots = (uint64_t)sm_count() * 3;
+    if (s < 2 || n_reads > 4 * slots) return PG_OK;  // s == 1 needs the positional panic rule; enough rows already
+    std::vector<uint64_t> off(n_reads + 1);
+    if (d_offsets) {
+        PG_CUDA(cudaMemcpyAsync(off.data(), d_offsets, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+    } else {
+        for (uint64_t r = 0; r <= n_reads; ++r) off[r] = r * (uint64_t)read_len;
+    }
+    uint64_t total = 0, rows_sel = 0;
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        const uint64_t len = off[r + 1] - off[r], n = len > (uint64_t)K ? len - K : 0;
+        if (n >= (uint64_t)s && n > 0) { total += n; ++rows_sel; }
+    }
+    if (rows_sel == 0 || rows_sel >= slots) return PG_OK;  // every resident CTA slot already has a row of its own
+    uint64_t sl = std::max<uint64_t>({(uint64_t)4 * SELW_CHUNK, (uint64_t)8 * s, (total + 8 * slots - 1) / (8 * slots)});
+    sl = (sl + SELW_CHUNK - 1) / SELW_CHUNK * SELW_CHUNK;
+    std::vector<uint64_t> beg;
+    std::vector<uint32_t> cnt, row0(n_reads + 1);
+    for (uint64_t r = 0; r < n_reads; ++r) {
+        row0[r] = (uint32_t)beg.size();
+        const uint64_t len = off[r + 1] - off[r], n = len > (uint64_t)K ? len - K : 0;
+        if (!(n >= (uint64_t)s && n > 0)) continue;
+        const uint64_t nsl = std::max<uint64_t>(1, n / sl);  // the last slice takes the remainder (< 2 sl)
+        if (n / nsl + sl > 0xffffffffull) return PG_OK;      // slice length must fit 32 bits
+        for (uint64_t j = 0; j < nsl; ++j) {
+            beg.push_back(off[r] + j * sl);
+            cnt.push_back((uint32_t)(j + 1 < nsl ? sl : n - j * sl));
+        }
+    }
+    row0[n_reads] = (uint32_t)beg.size();
+    const uint64_t n_slices = beg.size();
+    if (n_slices <= rows_sel) return PG_OK;  // nothing gets split
+    uint64_t *d_beg = nullptr;
+    uint32_t *d_cnt = nullptr, *d_row0 = nullptr, *d_part = nullptr;
+    PG_CUDA(cudaMallocAsync(&d_beg, n_slices * 8, st));
+    PG_CUDA(cudaMallocAsync(&d_cnt, n_slices * 4, st));
+    PG_CUDA(cudaMallocAsync(&d_row0, (n_reads + 1) * 4, st));
+    PG_CUDA(cudaMallocAsync(&d_part, n_slices * (uint64_t)s * 4, st));
+    PG_CUDA(cudaMemcpyAsync(d_beg, beg.data(), n_slices * 8, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), n_slices * 4, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(d_row0, row0.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaStreamSynchronize(st));  // the host vectors are pageable
+    SketchDst none;
+    none.n = 0;
+    int rc = launch_select_walk<K>(d_bases, nullptr, 0, n_slices, s, P, d_part, (uint64_t)s, nullptr, nullptr, st, none, d_beg, d_cnt);
+    if (rc == PG_OK) {
+        const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + 2 * SELM_CHUNK) + 3u) & ~3u;
+        const size_t smem = ((size_t)cap + s + SEL_NBK + 64 + SEL_NBK + 1 + 8) * 4;
+        static size_t configured = 0;
+        if (smem > configured) {
+            PG_CUDA(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 2);
+        select_merge_kernel<<<(unsigned)blocks, SELM_THREADS, smem, st>>>(d_part, d_row0, n_reads, (uint32_t)s, P, cap, d_out, row_stride,
+                                                                         d_count, d_status);
+        note_launch("select_merge_kernel");
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "select_merge_kernel", __FILE__, __LINE__);
+    }
+    cudaFreeAsync(d_beg, st);
+    cudaFreeAsync(d_cnt, st);
+    cudaFreeAsync(d_row0, st);
+    cudaFreeAsync(d_part, st);
+    *sliced = rc == PG_OK;
+    return rc;
+}
+
+template <int K>
+static int launch_select_auto(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
+                              uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
+                              cudaStream_t st, const SketchDst &ex) {
+    static const bool no_slices = [] { const char *e = getenv("PG_K2_NO_SLICES"); return e && atoi(e) != 0; }();
+    if (ex.n == 0 && !no_slices) {
+        bool sliced = false;
+        const int rc = try_select_sliced<K>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, &sliced);
+        if (rc != PG_OK || sliced) return rc;
+    }
+    return launch_select_walk<K>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex);
 }
 
 }  // namespace
@@ -631,7 +831,7 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     if (!force_generic && (size_t)s * 8 + 56 * 1024 <= 227 * 1024) {  // shared memory of the walk kernel
         switch (k) {
 #define PG_K2W_CASE(KK) \
-    case KK: return launch_select_walk<KK>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex);
+    case KK: return launch_select_auto<KK>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex);
             PG_K2W_CASE(11) PG_K2W_CASE(13) PG_K2W_CASE(15) PG_K2W_CASE(16) PG_K2W_CASE(17) PG_K2W_CASE(19)
             PG_K2W_CASE(21) PG_K2W_CASE(23) PG_K2W_CASE(24) PG_K2W_CASE(25) PG_K2W_CASE(27) PG_K2W_CASE(29)
             PG_K2W_CASE(31) PG_K2W_CASE(32)
@@ -649,7 +849,9 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 4);
+    int per_sm = 1;
+    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_select_kernel, SEL_THREADS, smem));
+    const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * std::max(per_sm, 1));  // one wave, grid-stride over rows
     sketch_select_kernel<<<(unsigned)blocks, SEL_THREADS, smem, st>>>(
         d_bases, d_offsets, read_len, n_reads, (uint32_t)k, (uint32_t)s, P, cap, flags, d_out,
         row_stride, d_count, d_status, ex);

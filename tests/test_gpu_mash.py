@@ -136,6 +136,9 @@ def test_select_regime_long_reads_with_pruning(gpu, oracle):
         seqs = [bytes(rng.choice(list(b"ACGT"), size=l).astype(np.uint8)) for l in lens]
         seqs.append(bytes(rng.choice(list(b"AC"), size=70_001).astype(np.uint8)))
         seqs.append(b"ACG" * 20_000)
+        if s == 1000:  # a genome-sized sequence: cut into slices, sketched in parallel, merged
+            seqs.append(bytes(rng.choice(list(b"ACGT"), size=2_500_003).astype(np.uint8)))
+            seqs += [bytes(rng.choice(list(b"ACGT"), size=int(l)).astype(np.uint8)) for l in rng.integers(0, 3000, 40)]
         bases, offsets = mash.flatten(seqs)
         out, count, status = mash.sketch_arrays(bases, offsets, k, s)
         for i, q in enumerate(seqs):
@@ -144,7 +147,7 @@ def test_select_regime_long_reads_with_pruning(gpu, oracle):
             if rc != 0:
                 assert status[i] == 1, (k, s, i)
                 continue
-            cnt = min(len(q) - k, s)
+            cnt = min(max(len(q) - k, 0), s)
             assert status[i] == 0 and count[i] == cnt, (k, s, i)
             assert np.array_equal(out[i, :cnt], o.Sketches[:cnt]), (k, s, i, len(q))
 

@@ -60,6 +60,9 @@ g = d_gsk.cpu().numpy().view(np.uint32)
 print(json.dumps({"kernel": "K2 sketch_select (256 x 4 Mbp genomes)", "k": gk, "s": gs, "ms": ms_g, "gbases_per_s": gn * gL / ms_g / 1e6,
                   "ascending": bool((np.diff(g.astype(np.int64), axis=1) >= 0).all()), "fnv": hex(synth.fnv1a64(g)),
                   "kernel_name": L.pg_last_kernel().decode()}))
+ms_1 = timed(lambda: _lib.check(L.pg_mash_sketch_uniform_dev(d_gen.data_ptr(), 1, gL, gk, gs, 0, d_gsk.data_ptr(), gs, None, st)))
+print(json.dumps({"kernel": "K2 sketch_select (ONE 4 Mbp sequence = mash.Sketch(genome))", "ms": ms_1, "gbases_per_s": gL / ms_1 / 1e6,
+                  "same_as_batch_row0": bool((d_gsk[0].cpu().numpy().view(np.uint32) == g[0]).all()), "kernel_name": L.pg_last_kernel().decode()}))
 del d_gen
 if args.only_k2:
     sys.exit(0)
