@@ -22,8 +22,9 @@
 //     line's newline is the last byte of a full buffer, Peek refills the buffer and the line's
 //     bytes are replaced by the text one buffer size further on (clipped to what the refill read).
 //     With a reader that fills every Read (strings.Reader, bytes.Reader, *os.File) the refill
-//     points are a chain F' = 1 + (last newline < F + B): one thread walks it (nbytes / B steps)
-//     and flags the affected lines; their "effective" bytes are used for the name test, the name
+//     points are a chain F' = 1 + (last newline < F + B): the successor of every line start is
+//     computed in parallel, one thread then follows the chain from line 0 (nbytes / B dependent
+//     loads) and flags the affected lines; their "effective" bytes are used for the name test, the name
 //     and the appended sequence exactly as the reference would.
 #include "text_scan.cuh"
 
@@ -74,22 +75,40 @@ __device__ __forceinline__ uint8_t effective_byte(const uint8_t *__restrict__ te
     return __ldg(text + v.b + j);
 }
 
-// bufio refill chain (alias mode): flags the lines whose newline is the last byte of a full buffer
-__global__ void refill_chain_kernel(const uint64_t *__restrict__ nl, uint64_t n_lines, uint64_t nbytes, uint64_t bufsz,
-                                    uint8_t *__restrict__ corrupt) {
-    uint64_t start = 0, idx = 0;  // buffer = text[start, start + bufsz); idx = first line inside it
-    while (start + bufsz < nbytes) {  // a full buffer with text left behind it
+// bufio refill chain (alias mode).  A buffer that starts at line i holds text[b_i, b_i + B); the
+// next buffer starts at line next(i) = number of newlines below b_i + B.  next() of EVERY line is
+// computed in parallel (one binary search each); bit 31 marks "the newline of line next(i) - 1 is
+// the last byte of the buffer" (that line is seen corrupted), next(i) == i ends the chain (no full
+// buffer with text behind it, or a line longer than the buffer: the parse stops there).
+constexpr uint32_t NEXT_LAST_BYTE = 0x80000000u;
+
+__global__ void __launch_bounds__(256)
+refill_next_kernel(const uint64_t *__restrict__ nl, uint64_t n_lines, uint64_t nbytes, uint64_t bufsz,
+                   uint32_t *__restrict__ next) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_lines) return;
+    const uint64_t start = i == 0 ? 0 : nl[i - 1] + 1;
+    uint32_t v = (uint32_t)i;
+    if (start + bufsz < nbytes) {  // a full buffer with text left behind it
         const uint64_t end = start + bufsz;
-        uint64_t lo = idx, hi = min(idx + bufsz, n_lines);  // number of newlines below `end`
+        uint64_t lo = i, hi = min(i + bufsz, n_lines);  // number of newlines below `end`
         while (lo < hi) {
             const uint64_t mid = (lo + hi) >> 1;
             if (nl[mid] < end) lo = mid + 1; else hi = mid;
         }
-        if (lo == idx) break;  // no newline in the buffer: the parse stops on this line
-        const uint64_t last = lo - 1;
-        if (nl[last] == end - 1) corrupt[last] = 1;
-        start = nl[last] + 1;
-        idx = lo;
+        if (lo > i) v = (uint32_t)lo | (nl[lo - 1] == end - 1 ? NEXT_LAST_BYTE : 0u);
+    }
+    next[i] = v;
+}
+
+// one thread follows the chain from line 0: one dependent load per refill
+__global__ void refill_chain_kernel(const uint32_t *__restrict__ next, uint64_t n_lines, uint8_t *__restrict__ corrupt) {
+    uint32_t idx = 0;
+    while (idx < n_lines) {
+        const uint32_t v = next[idx], j = v & ~NEXT_LAST_BYTE;
+        if (j == idx) break;
+        if (v & NEXT_LAST_BYTE) corrupt[j - 1] = 1;
+        idx = j;
     }
 }
 
@@ -249,9 +268,17 @@ int launch_fasta_ingest(const uint8_t *d_text, uint64_t nbytes, uint32_t max_lin
     PG_CUDA(tmp.alloc(&d_app_ex, n_lines + 1));
     const unsigned line_blocks = (unsigned)((n_lines + 255) / 256);
     if ((flags & PG_FASTA_BUFIO_ALIAS) && n_lines && nbytes > bufsz) {
+        if (n_lines >= 0x7fffffffull) {
+            set_error("PG_FASTA_BUFIO_ALIAS supports fewer than 2^31 lines");
+            return PG_ERR_UNSUPPORTED;
+        }
+        uint32_t *d_next = nullptr;
         PG_CUDA(tmp.alloc(&d_corrupt, n_lines));
+        PG_CUDA(tmp.alloc(&d_next, n_lines));
         PG_CUDA(cudaMemsetAsync(d_corrupt, 0, n_lines, st));
-        refill_chain_kernel<<<1, 1, 0, st>>>(d_nl, n_lines, nbytes, bufsz, d_corrupt);
+        refill_next_kernel<<<line_blocks, 256, 0, st>>>(d_nl, n_lines, nbytes, bufsz, d_next);
+        PG_LAUNCH_CHECK("refill_next_kernel");
+        refill_chain_kernel<<<1, 1, 0, st>>>(d_next, n_lines, d_corrupt);
         PG_LAUNCH_CHECK("refill_chain_kernel");
     }
     if (n_lines) {
