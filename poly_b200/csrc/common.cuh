@@ -28,6 +28,30 @@ void note_launch(const char *kernel_name);
 
 int sm_count();
 
+// Stream-ordered temporaries that are released together when the scope ends -- also on the early
+// returns of PG_CUDA -- with cudaFreeAsync on the stream they were allocated on.
+struct StreamScratch {
+    cudaStream_t st;
+    void *ptr[24];
+    int n = 0;
+    explicit StreamScratch(cudaStream_t s) : st(s) {}
+    StreamScratch(const StreamScratch &) = delete;
+    StreamScratch &operator=(const StreamScratch &) = delete;
+    ~StreamScratch() {
+        for (int i = 0; i < n; ++i) cudaFreeAsync(ptr[i], st);
+    }
+    template <typename T>
+    cudaError_t alloc(T **p, uint64_t count) {  // at least one element, so the pointer is always valid
+        if (n >= 24) return cudaErrorMemoryAllocation;
+        cudaError_t e = cudaMallocAsync((void **)p, (count ? count : 1) * sizeof(T), st);
+        if (e == cudaSuccess) ptr[n++] = *p;
+        return e;
+    }
+    void adopt(void *p) {  // take ownership of a buffer allocated elsewhere on the same stream
+        if (p && n < 24) ptr[n++] = p;
+    }
+};
+
 // destinations of a sketch row block: the local buffer, or the gathered buffers of all ranks
 struct SketchDst {
     uint32_t *ptr[PG_MAX_PEERS];

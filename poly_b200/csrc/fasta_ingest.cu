@@ -204,20 +204,6 @@ copy_lines_kernel(const uint8_t *__restrict__ text, uint64_t nbytes, uint64_t bu
     }
 }
 
-struct Scratch {  // stream-ordered temporaries, released together
-    cudaStream_t st;
-    void *ptr[16];
-    int n = 0;
-    explicit Scratch(cudaStream_t s) : st(s) {}
-    ~Scratch() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptr[i], st); }
-    template <typename T>
-    cudaError_t alloc(T **p, uint64_t count) {
-        cudaError_t e = cudaMallocAsync((void **)p, std::max<uint64_t>(count, 1) * sizeof(T), st);
-        if (e == cudaSuccess) ptr[n++] = *p;
-        return e;
-    }
-};
-
 template <typename T>
 int fetch(T *host, const T *dev, cudaStream_t st) {
     PG_CUDA(cudaMemcpyAsync(host, dev, sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -245,11 +231,14 @@ int launch_fasta_ingest(const uint8_t *d_text, uint64_t nbytes, uint32_t max_lin
         if (want_names) PG_CUDA(cudaMemsetAsync(d_name_offsets, 0, 8, st));
         return PG_OK;
     }
-    Scratch tmp(st);
+    StreamScratch tmp(st);
     uint64_t *d_nl = nullptr;
     uint64_t n_lines = 0, last_plus1 = 0;
-    FA_TRY(text::newline_positions(d_text, nbytes, &d_nl, &n_lines, &last_plus1, st));
-    tmp.ptr[tmp.n++] = d_nl;
+    {
+        const int rc0 = text::newline_positions(d_text, nbytes, &d_nl, &n_lines, &last_plus1, st);
+        tmp.adopt(d_nl);
+        if (rc0 != PG_OK) return rc0;
+    }
     const uint64_t frag_len = nbytes - last_plus1;  // bytes after the last newline
     uint8_t frag_first = 0;
     if (frag_len) FA_TRY(fetch(&frag_first, d_text + last_plus1, st));

@@ -111,10 +111,12 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
         if (records_cap + 1 >= 1 && d_offsets) PG_CUDA(cudaMemsetAsync(d_offsets, 0, 8, st));
         return PG_OK;
     }
+    StreamScratch tmp(st);
     uint64_t *d_nl = nullptr;
     uint64_t n_lines = 0, last_nl_plus1 = 0;
     {
         const int rc0 = text::newline_positions(d_text, nbytes, &d_nl, &n_lines, &last_nl_plus1, st);
+        tmp.adopt(d_nl);
         if (rc0 != PG_OK) return rc0;
     }
     const bool trailing = last_nl_plus1 < nbytes;  // bytes after the last newline
@@ -125,11 +127,11 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
     int32_t *d_err = nullptr;
     unsigned long long *d_first = nullptr;
     if (n_cand) {
-        PG_CUDA(cudaMallocAsync(&d_len, n_cand * 4, st));
-        PG_CUDA(cudaMallocAsync(&d_eline, n_cand * 4, st));
-        PG_CUDA(cudaMallocAsync(&d_sstart, n_cand * 8, st));
-        PG_CUDA(cudaMallocAsync(&d_err, n_cand * 4, st));
-        PG_CUDA(cudaMallocAsync(&d_first, 8, st));
+        PG_CUDA(tmp.alloc(&d_len, n_cand));
+        PG_CUDA(tmp.alloc(&d_eline, n_cand));
+        PG_CUDA(tmp.alloc(&d_sstart, n_cand));
+        PG_CUDA(tmp.alloc(&d_err, n_cand));
+        PG_CUDA(tmp.alloc(&d_first, 1));
         PG_CUDA(cudaMemsetAsync(d_first, 0xff, 8, st));
         record_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(d_text, nbytes, d_nl, n_lines, n_cand, d_len, d_sstart,
                                                                        d_err, d_eline, d_first);
@@ -153,7 +155,7 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
             set_error("records_cap %llu < %llu records", (unsigned long long)records_cap, (unsigned long long)n_ok);
             rc = PG_ERR_ARG;
         } else {
-            PG_CUDA(cudaMallocAsync(&d_off_tmp, (n_ok + 1) * 8, st));
+            PG_CUDA(tmp.alloc(&d_off_tmp, n_ok + 1));
             {
                 const int rc1 = text::device_scan<text::SumOp<uint32_t>>(d_len, n_ok, (unsigned long long *)d_off_tmp, st);
                 if (rc1 != PG_OK) return rc1;
@@ -177,9 +179,6 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
     }
     cudaError_t e = cudaGetLastError();
     PG_CUDA(cudaStreamSynchronize(st));
-    for (void *p : {(void *)d_nl, (void *)d_len, (void *)d_eline, (void *)d_sstart,
-                    (void *)d_err, (void *)d_first, (void *)d_off_tmp})
-        if (p) cudaFreeAsync(p, st);
     if (e != cudaSuccess) return cuda_fail(e, "fastq ingest", __FILE__, __LINE__);
     return rc;
 }

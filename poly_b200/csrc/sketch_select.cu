@@ -703,13 +703,13 @@ static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets,
     int per_sm = 1;
     PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_select_walk_kernel<K>, SELW_THREADS, smem));
     const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * std::max(per_sm, 1));
+    StreamScratch tmp(st);
     unsigned long long *d_next = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_next, 8, st));
+    PG_CUDA(tmp.alloc(&d_next, 1));
     PG_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
     sketch_select_walk_kernel<K><<<(unsigned)blocks, SELW_THREADS, smem, st>>>(d_bases, d_offsets, read_len, n_reads, (uint32_t)s, P, cap,
                                                                               d_out, row_stride, d_count, d_status, ex, 4u, d_slice_beg,
                                                                               d_slice_n, d_next);
-    cudaFreeAsync(d_next, st);
     PG_LAUNCH_CHECK("sketch_select_walk_kernel");
     return PG_OK;
 }
@@ -756,12 +756,13 @@ static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, 
     row0[n_reads] = (uint32_t)beg.size();
     const uint64_t n_slices = beg.size();
     if (n_slices <= rows_sel) return PG_OK;  // nothing gets split
+    StreamScratch tmp(st);
     uint64_t *d_beg = nullptr;
     uint32_t *d_cnt = nullptr, *d_row0 = nullptr, *d_part = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_beg, n_slices * 8, st));
-    PG_CUDA(cudaMallocAsync(&d_cnt, n_slices * 4, st));
-    PG_CUDA(cudaMallocAsync(&d_row0, (n_reads + 1) * 4, st));
-    PG_CUDA(cudaMallocAsync(&d_part, n_slices * (uint64_t)s * 4, st));
+    PG_CUDA(tmp.alloc(&d_beg, n_slices));
+    PG_CUDA(tmp.alloc(&d_cnt, n_slices));
+    PG_CUDA(tmp.alloc(&d_row0, n_reads + 1));
+    PG_CUDA(tmp.alloc(&d_part, n_slices * (uint64_t)s));
     PG_CUDA(cudaMemcpyAsync(d_beg, beg.data(), n_slices * 8, cudaMemcpyHostToDevice, st));
     PG_CUDA(cudaMemcpyAsync(d_cnt, cnt.data(), n_slices * 4, cudaMemcpyHostToDevice, st));
     PG_CUDA(cudaMemcpyAsync(d_row0, row0.data(), (n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -784,10 +785,6 @@ static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, 
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = cuda_fail(e, "select_merge_kernel", __FILE__, __LINE__);
     }
-    cudaFreeAsync(d_beg, st);
-    cudaFreeAsync(d_cnt, st);
-    cudaFreeAsync(d_row0, st);
-    cudaFreeAsync(d_part, st);
     *sliced = rc == PG_OK;
     return rc;
 }

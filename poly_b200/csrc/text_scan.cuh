@@ -100,8 +100,9 @@ template <typename Op>
 int device_scan(const typename Op::In *d_in, uint64_t n, typename Op::T *d_out, cudaStream_t st) {
     using T = typename Op::T;
     const uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    StreamScratch tmp(st);
     T *d_partial = nullptr;
-    PG_CUDA(cudaMallocAsync(&d_partial, std::max<uint64_t>(ntiles, 1) * sizeof(T), st));
+    PG_CUDA(tmp.alloc(&d_partial, ntiles));
     if (ntiles) {
         tile_reduce_kernel<Op><<<(unsigned)ntiles, 256, 0, st>>>(d_in, n, d_partial);
         note_launch("tile_reduce_kernel");
@@ -112,7 +113,6 @@ int device_scan(const typename Op::In *d_in, uint64_t n, typename Op::T *d_out, 
         tile_scan_kernel<Op><<<(unsigned)ntiles, 256, 0, st>>>(d_in, n, d_partial, d_out);
         note_launch("tile_scan_kernel");
     }
-    PG_CUDA(cudaFreeAsync(d_partial, st));
     return PG_OK;
 }
 
@@ -173,8 +173,9 @@ static inline int newline_positions(const uint8_t *d_text, uint64_t nbytes, uint
     unsigned long long *d_bstart = nullptr;
     *d_nl = nullptr; *n_lines = 0; *last_plus1 = 0;
     if (!nblocks) return PG_OK;
-    PG_CUDA(cudaMallocAsync(&d_bcount, nblocks * 4, st));
-    PG_CUDA(cudaMallocAsync(&d_bstart, (nblocks + 1) * 8, st));
+    StreamScratch tmp(st);
+    PG_CUDA(tmp.alloc(&d_bcount, nblocks));
+    PG_CUDA(tmp.alloc(&d_bstart, nblocks + 1));
     count_newlines_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d_text, nbytes, d_bcount);
     note_launch("count_newlines_kernel");
     int rc = device_scan<SumOp<uint32_t>>(d_bcount, nblocks, d_bstart, st);
@@ -191,8 +192,6 @@ static inline int newline_positions(const uint8_t *d_text, uint64_t nbytes, uint
         PG_CUDA(cudaStreamSynchronize(st));
         *last_plus1 = last + 1;
     }
-    PG_CUDA(cudaFreeAsync(d_bcount, st));
-    PG_CUDA(cudaFreeAsync(d_bstart, st));
     *n_lines = nlines;
     return PG_OK;
 }
