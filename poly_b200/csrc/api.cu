@@ -70,6 +70,17 @@ static int init_locked(int device) {
     for (int i = 0; i < 3; ++i) {
         if (!g_streams[i]) PG_CUDA(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
     }
+    {   // Stream-ordered temporaries (cudaMallocAsync) are freed at the end of every call and most calls
+        // synchronise: with the default release threshold of 0 the pool would hand its memory back to the
+        // driver each time.  Keep up to 1 GiB cached so that small calls do not pay a driver allocation.
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = 1ull << 30, cur = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     g_device = device;
     g_sms = prop.multiProcessorCount;
     return PG_OK;

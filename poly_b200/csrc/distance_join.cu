@@ -100,7 +100,6 @@ __global__ void __launch_bounds__(JOIN_THREADS)
 bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restrict__ start, uint32_t nbuckets,
                    uint64_t n, uint64_t row_begin, uint64_t row_end, uint32_t *__restrict__ same) {
     extern __shared__ __align__(16) uint64_t key[];  // [JOIN_CAP]
-    __shared__ uint32_t s_cnt;
     for (uint32_t b = blockIdx.x; b < nbuckets; b += gridDim.x) {
         const uint64_t lo = start[b];
         const uint32_t m = (uint32_t)(start[b + 1] - lo);
@@ -144,7 +143,6 @@ bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restr
         }
         __syncthreads();
     }
-    (void)s_cnt;
 }
 
 __global__ void same_to_distance_kernel(const uint32_t *__restrict__ same, uint64_t count, uint32_t s,

@@ -402,7 +402,7 @@ constexpr int SELW_STAGE_WORDS = (15 + SELW_CHUNK + 32 + 48 + 15) / 16 * 4;  // 
 #define PG_EMIT_APPEND(R_, H_) my_pos[i + (R_)] = (H_)
 
 template <int K>
-__global__ void __launch_bounds__(SELW_THREADS)
+__global__ void __launch_bounds__(SELW_THREADS, 3)
 sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets,
                           uint32_t uniform_len, uint64_t n_reads, uint32_t s, uint32_t P, uint32_t cap,
                           uint32_t *__restrict__ out, uint64_t row_stride, uint32_t *__restrict__ count,
@@ -415,6 +415,7 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     constexpr bool LUT = TAIL == 1;
     constexpr uint32_t k = K;
     static_assert(NB >= 1 && K <= 32, "walk path: 4 <= k <= 32");
+    static_assert(SELW_SEG % 4 == 0, "a segment is a whole number of word steps");
 
     extern __shared__ __align__(16) uint32_t smem_w[];
     SelSmem m;
@@ -557,11 +558,14 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
                     raw_b = *swp++;
                 }
                 uint32_t i = 0;
-#define PG_WALK_SEGMENT(EMIT)                                              \
-    _Pragma("unroll 1") while (i < nk) {                                   \
-        _Pragma("unroll") for (int u = 0; u < NB; ++u) {                   \
-            if (i < nk) PG_KMER_STEP(u, true, EMIT)                        \
-        }                                                                  \
+    // a full segment is SELW_SEG / 4 word steps with no bounds tests; the last segment of a chunk is checked
+#define PG_WALK_SEGMENT(EMIT)                                                          \
+    if (nk == SELW_SEG) {                                                              \
+        _Pragma("unroll") for (int q = 0; q < SELW_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, EMIT) \
+    } else {                                                                           \
+        _Pragma("unroll") for (int q = 0; q < SELW_SEG / 4; ++q) {                     \
+            if (i < nk) PG_KMER_STEP(q % NB, true, EMIT)                               \
+        }                                                                              \
     }
                 if (!unfiltered) PG_WALK_SEGMENT(PG_EMIT_ADMIT)
                 else if (full_chunk) PG_WALK_SEGMENT(PG_EMIT_TRANSPOSED)
@@ -715,8 +719,8 @@ static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets,
 }
 
 // Few, long sequences (genomes): one CTA per sequence leaves the GPU idle.  Cut every
-// select-regime row into slices of >= max(4 chunks, 8 s) k-mer positions (about 8 slices per
-// resident CTA slot over the whole batch), sketch the slices independently, merge per row.
+// select-regime row into slices of >= max(4 chunks, 8 s) k-mer positions (about 4 slices per
+// resident CTA slot over the whole batch; rows are handed out dynamically), sketch the slices independently, merge per row.
 // *sliced = false when slicing would not add parallelism (the caller then runs the direct path).
 template <int K>
 static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
@@ -738,7 +742,7 @@ static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, 
         if (n >= (uint64_t)s && n > 0) { total += n; ++rows_sel; }
     }
     if (rows_sel == 0 || rows_sel >= slots) return PG_OK;  // every resident CTA slot already has a row of its own
-    uint64_t sl = std::max<uint64_t>({(uint64_t)4 * SELW_CHUNK, (uint64_t)8 * s, (total + 8 * slots - 1) / (8 * slots)});
+    uint64_t sl = std::max<uint64_t>({(uint64_t)4 * SELW_CHUNK, (uint64_t)8 * s, (total + 4 * slots - 1) / (4 * slots)});
     sl = (sl + SELW_CHUNK - 1) / SELW_CHUNK * SELW_CHUNK;
     std::vector<uint64_t> beg;
     std::vector<uint32_t> cnt, row0(n_reads + 1);
