@@ -235,3 +235,67 @@ func FastaIngest(text []byte, maxLineSize int, bufioAlias bool) (seq []byte, seq
 	}
 	return seq[:tot], seqOff[:n+1], names[:ntot], nameOff[:n+1], int(ec), uint64(el), nil
 }
+
+// DesignPrimersBatch wraps pg_design_primers_batch: per sequence the lengths of the forward and
+// reverse primers of pcr.DesignPrimersWithOverhangs (status 1: the reference slices out of range).
+func DesignPrimersBatch(bases []byte, offsets []uint64, targetTm float64) (fwdLen, revLen []uint32, status []int32, err error) {
+	n := len(offsets) - 1
+	fwdLen, revLen, status = make([]uint32, n+1), make([]uint32, n+1), make([]int32, n+1)
+	base := (*C.uint8_t)(nil)
+	if len(bases) > 0 {
+		base = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
+	}
+	rc := C.pg_design_primers_batch(base, (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n), C.double(targetTm),
+		(*C.uint32_t)(unsafe.Pointer(&fwdLen[0])), (*C.uint32_t)(unsafe.Pointer(&revLen[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
+	return fwdLen[:n], revLen[:n], status[:n], check(rc)
+}
+
+// MinimalPrimerBatch wraps pg_pcr_minimal_primer_batch (the loop of pcr.go:93-100 for every primer).
+func MinimalPrimerBatch(bases []byte, offsets []uint64, targetTm float64) (minLen []uint32, status []int32, err error) {
+	n := len(offsets) - 1
+	minLen, status = make([]uint32, n+1), make([]int32, n+1)
+	base := (*C.uint8_t)(nil)
+	if len(bases) > 0 {
+		base = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
+	}
+	rc := C.pg_pcr_minimal_primer_batch(base, (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n), C.double(targetTm),
+		(*C.uint32_t)(unsafe.Pointer(&minLen[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
+	return minLen[:n], status[:n], check(rc)
+}
+
+// Site is one exact occurrence of a pattern in a sequence.
+type Site struct {
+	Seq     int
+	Pos     int
+	Pattern int
+}
+
+// FindSites wraps pg_find_sites_batch: every (overlapping) occurrence of every pattern in every
+// sequence, what suffixarray.Lookup(pattern, -1) returns per sequence.  Order is unspecified.
+func FindSites(seqs []byte, seqOff []uint64, patterns []byte, patOff []uint64) ([]Site, error) {
+	nSeq, nPat := len(seqOff)-1, len(patOff)-1
+	if nSeq <= 0 || nPat <= 0 || len(seqs) == 0 || len(patterns) == 0 {
+		return nil, nil
+	}
+	capHits := 1024
+	for {
+		hs, hp, hq := make([]uint32, capHits), make([]uint64, capHits), make([]uint32, capHits)
+		var n C.uint64_t
+		rc := C.pg_find_sites_batch((*C.uint8_t)(unsafe.Pointer(&seqs[0])), (*C.uint64_t)(unsafe.Pointer(&seqOff[0])), C.uint64_t(nSeq),
+			(*C.uint8_t)(unsafe.Pointer(&patterns[0])), (*C.uint64_t)(unsafe.Pointer(&patOff[0])), C.uint32_t(nPat), 0,
+			(*C.uint32_t)(unsafe.Pointer(&hs[0])), (*C.uint64_t)(unsafe.Pointer(&hp[0])), (*C.uint32_t)(unsafe.Pointer(&hq[0])),
+			C.uint64_t(capHits), &n)
+		if rc == C.PG_ERR_ARG && int(n) > capHits {
+			capHits = int(n)
+			continue
+		}
+		if err := check(rc); err != nil {
+			return nil, err
+		}
+		sites := make([]Site, int(n))
+		for i := range sites {
+			sites[i] = Site{Seq: int(hs[i]), Pos: int(hp[i]), Pattern: int(hq[i])}
+		}
+		return sites, nil
+	}
+}

@@ -13,7 +13,7 @@ import (
 	"github.com/bebop/poly/internal/polyb200"
 )
 
-// Fasta is a struct representing a single Fasta file element with a Name and its corresponding Sequence.
+// Fasta: one record, the header line without '>' and the concatenated sequence lines (reference: fasta.go:66-69).
 type Fasta struct {
 	Name     string `json:"name"`
 	Sequence string `json:"sequence"`
@@ -27,7 +27,7 @@ var BufioAlias = true
 
 var errBufferFull = errors.New("bufio: buffer full")
 
-// Parse parses a given Fasta file into an array of Fasta structs (reference: fasta.go:72).
+// Parse reads r to the end and returns what the reference's Parse returns for the same bytes (fasta.go:72-77).
 func Parse(r io.Reader) ([]Fasta, error) {
 	const maxLineSize = 2 * 32 * 1024
 	return parseAll(r, maxLineSize)
