@@ -170,7 +170,10 @@ empty_record_kernel(const unsigned long long *__restrict__ seq_off, uint64_t n_c
     if (m < n_check && seq_off[m + 1] == seq_off[m]) atomicMin(first_empty, (unsigned long long)m);
 }
 
-// one warp per line: appended content -> bases, header content -> names (records < n_ok only)
+// Copy: appended content -> bases, header content -> names (records < n_ok only).  A warp takes 32
+// consecutive lines: lane l gathers the metadata of line i0 + l (coalesced loads), then the warp
+// copies the 32 lines one after the other, the per-line source / destination / length broadcast by
+// shuffles -- lines are ~60 bytes, so the metadata (7 words per line) costs as much as the text.
 __global__ void __launch_bounds__(256)
 copy_lines_kernel(const uint8_t *__restrict__ text, uint64_t nbytes, uint64_t bufsz, const uint64_t *__restrict__ nl,
                   uint64_t n_lines, const uint8_t *__restrict__ flags, const uint32_t *__restrict__ is_hdr,
@@ -179,26 +182,39 @@ copy_lines_kernel(const uint8_t *__restrict__ text, uint64_t nbytes, uint64_t bu
                   uint64_t n_ok, uint8_t *__restrict__ bases, uint8_t *__restrict__ names) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_lines; i += warps) {
-        const unsigned long long hc = hdr_ex[i + 1];  // headers up to and including this line
-        if (hc == 0 || hc - 1 >= n_ok) continue;
-        const bool hdr = is_hdr[i];
-        const uint32_t alen = app_len[i];
-        if (!hdr && alen == 0) continue;
-        const LineView v = line_view(nl, i);
-        const bool cor = flags[i] & LF_CORRUPT;
-        if (hdr) {
-            if (!names) continue;
-            uint8_t *dst = names + name_off[hc - 1];
-            const uint64_t len = v.e - v.b - 1;
-            for (uint64_t j = lane; j < len; j += 32) dst[j] = effective_byte(text, nbytes, bufsz, v, cor, j + 1);
-        } else {
-            uint8_t *dst = bases + app_ex[i];
-            if (!cor) {
-                const uint8_t *src = text + v.b;
-                for (uint64_t j = lane; j < alen; j += 32) dst[j] = __ldg(src + j);
-            } else {
-                for (uint64_t j = lane; j < alen; j += 32) dst[j] = effective_byte(text, nbytes, bufsz, v, true, j);
+    const uint64_t n_groups = (n_lines + 31) / 32;
+    for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const uint64_t i = g * 32 + lane;
+        // my line: source offset, destination pointer, length, and whether it needs the slow path
+        uint64_t src = 0, len = 0;
+        uint8_t *dst = nullptr;
+        bool cor = false, hdr = false;
+        if (i < n_lines) {
+            const unsigned long long hc = hdr_ex[i + 1];  // headers up to and including this line
+            if (hc != 0 && hc - 1 < n_ok) {
+                const LineView v = line_view(nl, i);
+                cor = flags[i] & LF_CORRUPT;
+                hdr = is_hdr[i];
+                if (hdr) {
+                    if (names) { dst = names + name_off[hc - 1]; src = v.b + 1; len = v.e - v.b - 1; }
+                } else if (app_len[i]) {
+                    dst = bases + app_ex[i]; src = v.b; len = app_len[i];
+                }
+            }
+        }
+        uint32_t todo = __ballot_sync(0xffffffffu, len != 0);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint64_t s_src = __shfl_sync(0xffffffffu, src, l), s_len = __shfl_sync(0xffffffffu, len, l);
+            uint8_t *s_dst = reinterpret_cast<uint8_t *>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(dst), l));
+            const bool s_cor = __shfl_sync(0xffffffffu, (int)cor, l);
+            if (!s_cor) {
+                for (uint64_t j = lane; j < s_len; j += 32) s_dst[j] = __ldg(text + s_src + j);
+            } else {  // bytes as the reference sees them after the reader refill (rare)
+                const bool s_hdr = __shfl_sync(0xffffffffu, (int)hdr, l);
+                const LineView v = line_view(nl, g * 32 + l);
+                for (uint64_t j = lane; j < s_len; j += 32) s_dst[j] = effective_byte(text, nbytes, bufsz, v, true, j + (s_hdr ? 1 : 0));
             }
         }
     }
@@ -386,7 +402,7 @@ int launch_fasta_ingest(const uint8_t *d_text, uint64_t nbytes, uint32_t max_lin
     PG_CUDA(cudaMemcpyAsync(d_offsets, d_seq_off, (n_ok + 1) * 8, cudaMemcpyDeviceToDevice, st));
     if (want_names) PG_CUDA(cudaMemcpyAsync(d_name_offsets, d_name_off, (n_ok + 1) * 8, cudaMemcpyDeviceToDevice, st));
     if (n_ok && n_lines) {
-        const unsigned blocks = (unsigned)std::min<uint64_t>((n_lines + 7) / 8, (uint64_t)sm_count() * 16);
+        const unsigned blocks = (unsigned)std::min<uint64_t>((n_lines + 255) / 256, (uint64_t)sm_count() * 16);
         copy_lines_kernel<<<blocks, 256, 0, st>>>(d_text, nbytes, bufsz, d_nl, n_lines, d_flags, d_hdr, d_app, d_hdr_ex, d_app_ex,
                                                  d_name_off, n_ok, d_bases, want_names ? d_names : nullptr);
         PG_LAUNCH_CHECK("copy_lines_kernel");
