@@ -22,15 +22,20 @@ from . import _lib
 from ._lib import GoPanic
 from .mash import BytesLike, _as_bytes, flatten
 
-_COMP = bytes.maketrans(b"ABCDGHKMNRSTVWYabcdghkmnrstvwy", b"TVGHCDMKNYSABWRtvghcdmknysabwr")
-
-
-def reverse_complement(seq: bytes) -> bytes:
-    """transform.ReverseComplement (transform/transform.go:15-23): unlisted bytes map to 0."""
+def _complement_table() -> bytes:
+    """complementTable of transform/transform.go:78-109 as a 256-byte translation table: unlisted bytes map to 0."""
     table = bytearray(256)
     for a, b in zip(b"ABCDGHKMNRSTVWYabcdghkmnrstvwy", b"TVGHCDMKNYSABWRtvghcdmknysabwr"):
         table[a] = b
-    return bytes(seq[::-1].translate(bytes(table)))
+    return bytes(table)
+
+
+_COMPLEMENT = _complement_table()
+
+
+def reverse_complement(seq: bytes) -> bytes:
+    """transform.ReverseComplement (transform/transform.go:15-23)."""
+    return bytes(seq[::-1].translate(_COMPLEMENT))
 
 
 def design_primer_lengths(sequences: Sequence[BytesLike], target_tm: float):
