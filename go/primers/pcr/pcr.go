@@ -15,8 +15,9 @@ import (
 	"github.com/bebop/poly/transform"
 )
 
-// shortest primer the searches start from (reference: pcr.go:41)
-const minimalPrimerLength = 15
+// shortest binding part the Tm loop of SimulateSimple starts from (reference: pcr.go:35; the 15 of
+// pcr.go:38, designedMinimalPrimerLength, only concerns DesignPrimers and lives in the kernel)
+const minimalPrimerLength = 7
 
 // DesignPrimersWithOverhangs: reference pcr.go:44-60.  The two Tm searches run on the GPU; the
 // strings are cut from the upper-cased sequence with the lengths that come back.
@@ -80,7 +81,7 @@ func SimulateSimple(sequences []string, targetTm float64, circular bool, primerL
 		minLen, status, err := polyb200.MinimalPrimerBatch(flat, bounds, targetTm)
 		for _, st := range status {
 			if st == 1 {
-				panic("runtime error: slice bounds out of range") // primer shorter than 15 nt
+				panic("runtime error: slice bounds out of range") // primer shorter than 7 nt
 			}
 		}
 		if err != nil {

@@ -232,10 +232,10 @@ int pg_design_primers_batch(const uint8_t *bases, const uint64_t *offsets, uint6
 
 /* ---- pcr.SimulateSimple building blocks -- primers/pcr/pcr.go:73-169 ---------
  * pg_pcr_minimal_primer_batch: the minimal-primer loop of pcr.go:93-100 for every primer:
- * min_len = the longest 3' suffix of >= 15 nt whose MeltingTemp is still below target_tm (the
- * reference's loop keeps the last length that FAILED the test), 0 when the 15-mer already reaches
+ * min_len = the longest 3' suffix of >= 7 nt (minimalPrimerLength, pcr.go:35) whose MeltingTemp is still below target_tm (the
+ * reference's loop keeps the last length that FAILED the test), 0 when the 7-mer already reaches
  * it, the primer's length when even the whole primer stays below (the reference then ignores the
- * primer, pcr.go:103).  status: PG_ITEM_PANIC for primers shorter than 15 nt, PG_ITEM_UNSUPPORTED
+ * primer, pcr.go:103).  status: PG_ITEM_PANIC for primers shorter than 7 nt, PG_ITEM_UNSUPPORTED
  * for bytes >= 0x80.
  * pg_find_sites_batch: every (possibly overlapping) exact occurrence of every pattern in every
  * sequence -- what suffixarray.Lookup(pattern, -1) returns at pcr.go:110,113; empty patterns have

@@ -789,7 +789,7 @@ int pg_pcr_minimal_primer_batch(const uint8_t *bases, const uint64_t *offsets, u
         if (hst[i] == PG_ITEM_PANIC) worst = PG_ERR_PANIC;
         else if (hst[i] == PG_ITEM_UNSUPPORTED && worst == PG_OK) worst = PG_ERR_UNSUPPORTED;
     }
-    if (worst == PG_ERR_PANIC) set_error("at least one primer is shorter than 15 nt: pcr.SimulateSimple panics (slice bounds out of range)");
+    if (worst == PG_ERR_PANIC) set_error("at least one primer is shorter than 7 nt: pcr.SimulateSimple panics (slice bounds out of range)");
     if (worst == PG_ERR_UNSUPPORTED) set_error("at least one primer holds a byte >= 0x80 (unsupported)");
     return worst;
 }

@@ -153,10 +153,11 @@ design_primers_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restr
 }
 
 // pcr.SimulateSimple's minimal-primer loop, /root/reference/primers/pcr/pcr.go:93-100:
-//     for index := 15; MeltingTemp(primer[len-index:]) < targetTm; index++ {
+//     for index := minimalPrimerLength (= 7, pcr.go:35); MeltingTemp(primer[len-index:]) < targetTm; index++ {
 //         minimalLength = index; if primer[len-index:] == primer { break } }
-// i.e. the LONGEST 3' suffix (>= 15 nt) whose Tm is still below the target, 0 when the 15-mer
+// i.e. the LONGEST 3' suffix (>= 7 nt) whose Tm is still below the target, 0 when the 7-mer
 // already reaches it, len when even the whole primer stays below.  One thread per primer.
+constexpr uint64_t PCR_MIN_PRIMER = 7;  // minimalPrimerLength, pcr.go:35 (15 is only designedMinimalPrimerLength, pcr.go:38)
 __global__ void __launch_bounds__(256)
 minimal_primer_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ off, uint64_t n, double target,
                       uint32_t *__restrict__ min_len, int32_t *__restrict__ status) {
@@ -168,10 +169,10 @@ minimal_primer_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restr
     bool ascii = true;
     for (uint64_t j = 0; j < len; ++j) ascii &= __ldg(s + j) < 0x80;
     if (!ascii) { status[i] = PG_ITEM_UNSUPPORTED; return; }
-    if (len < 15) { status[i] = PG_ITEM_PANIC; return; }  // primer[len(primer)-15:] out of range
+    if (len < PCR_MIN_PRIMER) { status[i] = PG_ITEM_PANIC; return; }  // primer[len(primer)-7:] out of range
     const double cp = 500e-9, na = 50e-3, mg = 0.0;        // MeltingTemp defaults, primers.go:122-124
     uint32_t minimal = 0;
-    for (uint64_t index = 15;; ++index) {
+    for (uint64_t index = PCR_MIN_PRIMER;; ++index) {
         const uint8_t *suffix = s + (len - index);
         const double tm = santalucia_core([suffix](uint64_t j) { return upper(__ldg(suffix + j)); }, index, cp, na, mg, nullptr, nullptr);
         if (!(tm < target)) break;

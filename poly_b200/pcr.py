@@ -76,7 +76,7 @@ def DesignPrimers(sequence: BytesLike, targetTm: float) -> Tuple[str, str]:
     return DesignPrimersWithOverhangs(sequence, "", "", targetTm)
 
 
-minimalPrimerLength = 15  # pcr.go:41
+minimalPrimerLength = 7  # pcr.go:35 (designedMinimalPrimerLength = 15, pcr.go:38, is only for DesignPrimers)
 
 
 def _upper_ascii(b: bytes) -> bytes:
@@ -138,7 +138,7 @@ def SimulateSimple(sequences: Sequence[BytesLike], targetTm: float, circular: bo
         return []
     ml, st = minimal_primer_lengths(prim, targetTm) if prim else (np.zeros(0, np.uint32), np.zeros(0, np.int32))
     if (st == _lib.PG_ITEM_PANIC).any():
-        raise GoPanic("slice bounds out of range (primer shorter than 15 nt)")   # primer[len(primer)-index:]
+        raise GoPanic("slice bounds out of range (primer shorter than 7 nt)")   # primer[len(primer)-index:]
     minimal: List[Optional[bytes]] = [None] * len(prim)              # minimalPrimers, "" in Go where unset
     patterns, owner = [], []
     for i, p in enumerate(prim):

@@ -23,9 +23,9 @@ def occurrences(text: bytes, pat: bytes):
 
 def minimal_length(primer: bytes, target: float) -> int:
     """pcr.go:93-100; raises IndexError where Go panics."""
-    if len(primer) < 15:
+    if len(primer) < 7:            # minimalPrimerLength, pcr.go:35
         raise IndexError("slice bounds out of range")
-    minimal, index = 0, 15
+    minimal, index = 0, 7
     while o.melting_temp(primer[len(primer) - index:]) < target:
         minimal = index
         if index == len(primer):
@@ -72,7 +72,7 @@ def simulate_simple(sequences, target, circular, primer_list):
 
 
 def simulate(sequences, target, circular, primer_list):
-    if any(len(p) < 15 for p in primer_list):
+    if any(len(p) < 7 for p in primer_list):      # pcr.go:174-178
         return None, "Primers are too short."
     first = simulate_simple(sequences, target, circular, primer_list)
     second = simulate_simple(sequences, target, circular, list(primer_list) + [f.encode() for f in first])

@@ -31,9 +31,13 @@ def test_minimal_length_quirks():
     # the loop keeps the last length that FAILED the test: Tm(minimal primer) < target <= Tm(one base more)
     import oracle_ffi as o
     ml = P.minimal_length(P.FWD, 55.0)
-    assert 15 <= ml < len(P.FWD)
+    assert 7 <= ml < len(P.FWD)
     assert o.melting_temp(P.FWD[len(P.FWD) - ml:]) < 55.0 <= o.melting_temp(P.FWD[len(P.FWD) - ml - 1:])
     assert P.minimal_length(b"CTGCAGGTCGACTCTAG", 55.0) == 17           # whole primer below target: ignored (pcr.go:103)
-    assert P.minimal_length(b"G" * 15 + b"C" * 15, 20.0) == 0            # the 15-mer already reaches the target
+    assert P.minimal_length(b"G" * 15 + b"C" * 15, 20.0) == 0            # the 7-mer already reaches the target
+    # a GC-rich primer whose 15-nt suffix is already above the target still has a minimal part of 7..14 nt
+    gc = b"GCGGCCGCGGGCCCGCGGCCGC"
+    assert o.melting_temp(gc[-15:]) >= 55.0 and 7 <= P.minimal_length(gc, 55.0) < 15
+    assert P.minimal_length(b"ACGTACG", 55.0) == 7                       # 7 nt is legal (pcr.go:35), whole primer below target
     with pytest.raises(IndexError):
         P.minimal_length(b"ACGT", 55.0)

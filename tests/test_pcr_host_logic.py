@@ -14,7 +14,7 @@ def cpu_blocks(monkeypatch):
         ml, st = np.zeros(len(primers), np.uint32), np.zeros(len(primers), np.int32)
         for i, p in enumerate(primers):
             p = bytes(p)
-            if len(p) < 15:
+            if len(p) < 7:
                 st[i] = _lib.PG_ITEM_PANIC
             else:
                 ml[i] = P.minimal_length(p.upper(), target)
@@ -42,5 +42,5 @@ def test_primer_list_is_upper_cased_in_place_and_short_primers_panic(cpu_blocks)
     assert pcr.SimulateSimple([P.GENE.decode()], 55.0, False, primers) == [P.FULL_AMPLICON]
     assert primers[0] == P.FWD.decode()                       # pcr.go:76-78
     with pytest.raises(_lib.GoPanic):
-        pcr.SimulateSimple([P.GENE], 55.0, False, [b"ACGT"])  # primer[len(primer)-15:]
+        pcr.SimulateSimple([P.GENE], 55.0, False, [b"ACGT"])  # primer[len(primer)-7:]
     assert pcr.SimulateSimple([], 55.0, False, [P.FWD]) == []
