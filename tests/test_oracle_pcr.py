@@ -34,7 +34,8 @@ def test_minimal_length_quirks():
     assert 7 <= ml < len(P.FWD)
     assert o.melting_temp(P.FWD[len(P.FWD) - ml:]) < 55.0 <= o.melting_temp(P.FWD[len(P.FWD) - ml - 1:])
     assert P.minimal_length(b"CTGCAGGTCGACTCTAG", 55.0) == 17           # whole primer below target: ignored (pcr.go:103)
-    assert P.minimal_length(b"G" * 15 + b"C" * 15, 20.0) == 0            # the 7-mer already reaches the target
+    assert P.minimal_length(b"G" * 15 + b"C" * 15, 15.0) == 0            # the 7-mer (Tm 19.6) already reaches the target
+    assert P.minimal_length(b"G" * 15 + b"C" * 15, 20.0) == 7            # ... and just misses this one
     # a GC-rich primer whose 15-nt suffix is already above the target still has a minimal part of 7..14 nt
     gc = b"GCGGCCGCGGGCCCGCGGCCGC"
     assert o.melting_temp(gc[-15:]) >= 55.0 and 7 <= P.minimal_length(gc, 55.0) < 15
