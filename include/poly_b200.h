@@ -46,9 +46,21 @@ extern "C" {
 
 /* ---- library / device management -------------------------------------------- */
 int pg_version(void);
-/* Bind the calling process to CUDA device `device` (one process per GPU).  Optional:
- * the first compute call initialises device 0 (or the current device). */
+/* Choose the process-default CUDA device (one process per GPU layout).  Optional: the first
+ * compute call initialises the current CUDA device (device 0 unless the caller changed it).
+ * The library keeps one context per device and serves any number of devices from one process:
+ *   - pg_thread_device(d) binds the CALLING THREAD's later calls to device d (-1: back to the
+ *     process default) -- for hosts that drive several GPUs themselves (Go: after
+ *     runtime.LockOSThread());
+ *   - the *_multi entry points shard one batch over several devices on their own.
+ * Entry points are safe to call concurrently from many threads: host-pointer entry points are
+ * serialised per device, *_dev entry points only enqueue work on the caller's stream. */
 int pg_init(int device);
+int pg_thread_device(int device);
+/* Move the calling thread to the CPUs of the NUMA node the device is attached to and prefer that
+ * node for memory it allocates afterwards (call before pg_host_alloc).  Best effort; *node (may be
+ * NULL) receives the node or -1 when nothing was done. */
+int pg_numa_bind_thread(int device, int *node);
 int pg_shutdown(void);
 const char *pg_last_error(void);
 int pg_device_count(int *count);
@@ -105,8 +117,8 @@ int pg_mash_sketch_uniform_dev(const uint8_t *d_bases, uint64_t n_reads, uint32_
  * rank*n_local (TMA bulk stores to peer addresses in the fill regime), so the transfer overlaps
  * the hashing tile by tile and no separate collective pass runs.  Rows are compact
  * (row stride = min(max(read_len-k,0), s) words).  The caller must synchronise the stream and
- * barrier across ranks before reading its gathered buffer.  n_local must be the same on all
- * ranks; world <= 8. */
+ * barrier across ranks before reading its gathered buffer.  n_local MUST be the same on all
+ * ranks (the row offset is rank*n_local; use the _scatter_dev variant for unequal shards); world <= 8. */
 #define PG_MAX_PEERS 8
 #define PG_IPC_HANDLE_BYTES 64
 int pg_ipc_export(void *dptr, uint8_t handle[PG_IPC_HANDLE_BYTES]);
@@ -115,6 +127,37 @@ int pg_ipc_close(void *dptr);
 int pg_mash_sketch_uniform_gather_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len,
                                       int32_t k, int32_t s, void *const *gathered_ptrs,
                                       int32_t world, int32_t rank, void *stream);
+/* The same with an explicit row offset: the n_local sketches go to rows [row_offset, row_offset +
+ * n_local) of each of the n_dst buffers (dst_ptrs[self] is the local one).  Shards may then differ
+ * in size; any k, any n_local (rows the TMA path does not take are stored by the generic kernels). */
+int pg_mash_sketch_uniform_scatter_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len,
+                                       int32_t k, int32_t s, void *const *dst_ptrs, int32_t n_dst,
+                                       int32_t self, uint64_t row_offset, void *stream);
+
+/* ---- single-process multi-GPU (SURVEY.md 8b "multi-GPU variants taking a device count", 8e) ----
+ * What a Go host calls to reach all GPUs of the box with ONE call: reads are independent
+ * (mash.go:68-104 touches only its receiver), so the batch is cut into contiguous shards, one per
+ * device, each driven by its own host thread through the pipelined host path -- no data-path
+ * collective.  devices == NULL: the first n_devices visible devices (n_devices <= 0: all of them);
+ * otherwise the listed ordinals.  Arguments and results are exactly those of pg_mash_sketch_uniform /
+ * pg_mash_sketch_batch; host buffers may be pageable or pinned (pg_host_alloc). */
+int pg_mash_sketch_uniform_multi(const uint8_t *bases, uint64_t n_reads, uint32_t read_len, int32_t k,
+                                 int32_t s, uint32_t flags, uint32_t *out, uint64_t row_stride,
+                                 int32_t *status, const int32_t *devices, int32_t n_devices);
+int pg_mash_sketch_batch_multi(const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads,
+                               int32_t k, int32_t s, uint32_t flags, uint32_t *out,
+                               uint64_t row_stride, uint32_t *count, int32_t *status,
+                               const int32_t *devices, int32_t n_devices);
+/* mash.Sketch of every read followed by all-pairs Similarity/Distance (mash.go:68-104, 107-140) on
+ * several devices: device r sketches its shard and the sketch kernel itself stores every finished
+ * tile / row into the gathered buffer of EVERY device (in-process peer access over NVLink: the
+ * all-gather is fused into the kernel), then computes row block r of the pair matrix.  Outputs (host,
+ * each may be NULL): sketches n x s (full Go arrays, zero tail included), same n x n uint32,
+ * distance n x n double; receiver = row.  Without peer access the exchange uses peer copies. */
+int pg_mash_sketch_distance_multi(const uint8_t *bases, uint64_t n_reads, uint32_t read_len, int32_t k,
+                                  int32_t s, const int32_t *devices, int32_t n_devices,
+                                  uint32_t *sketches, uint32_t *same, double *distance);
+
 /* Name of the kernel the last uniform call on this thread dispatched to and how many
  * kernels it launched (bench.py's gpu_launches evidence). */
 const char *pg_last_kernel(void);

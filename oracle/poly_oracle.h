@@ -103,6 +103,15 @@ int po_santalucia(const uint8_t *seq, int64_t len, double cp, double na, double 
 /* primers/primers.go:121-128. */
 int po_melting_temp(const uint8_t *seq, int64_t len, double *tm);
 
+/* ---- batch drivers (batch_drivers.c): a static parallel-for of per-item calls, for bench.py's
+ * CPU legs only.  checksum (may be NULL) receives a digest so that the work cannot be elided. */
+int po_sw_score_batch(const uint8_t *queries, const uint64_t *offsets, uint64_t n, const uint8_t *templ, int64_t templ_len,
+                      const int16_t *lut_a, const int16_t *lut_b, const int64_t *table, int n_b, int64_t gap, int nthreads,
+                      int64_t *score, uint64_t *checksum);
+int po_melting_temp_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n, int nthreads, double *tm, uint64_t *checksum);
+int po_mash_similarity_block(const uint32_t *sk, uint64_t n, int s, uint64_t row_lo, uint64_t row_hi, uint64_t col_lo,
+                             uint64_t col_hi, int nthreads, uint32_t *same, uint64_t *checksum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,8 @@ _u8p, _u32p, _u64p, _i64p, _i32p, _i16p, _f64p = (C.c_void_p,) * 7  # raw addres
 _SIGS = {
     "pg_version": (C.c_int, []),
     "pg_init": (C.c_int, [C.c_int]),
+    "pg_thread_device": (C.c_int, [C.c_int]),
+    "pg_numa_bind_thread": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "pg_shutdown": (C.c_int, []),
     "pg_last_error": (C.c_char_p, []),
     "pg_last_kernel": (C.c_char_p, []),
@@ -53,6 +55,10 @@ _SIGS = {
     "pg_ipc_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "pg_ipc_close": (C.c_int, [C.c_void_p]),
     "pg_mash_sketch_uniform_gather_dev": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
+    "pg_mash_sketch_uniform_scatter_dev": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
+    "pg_mash_sketch_uniform_multi": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, C.c_uint32, _u32p, C.c_uint64, _i32p, _i32p, C.c_int32]),
+    "pg_mash_sketch_batch_multi": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_int32, C.c_int32, C.c_uint32, _u32p, C.c_uint64, _u32p, _i32p, _i32p, C.c_int32]),
+    "pg_mash_sketch_distance_multi": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int32, _i32p, C.c_int32, _u32p, _u32p, _f64p]),
     "pg_mash_similarity_pairs": (C.c_int, [_u32p, _u64p, C.c_uint64, _u32p, _u32p, C.c_uint64, _i64p, _f64p, _f64p, _i32p]),
     "pg_mash_similarity_pairs_dev": (C.c_int, [_u32p, _u64p, C.c_uint64, _u32p, _u32p, C.c_uint64, _i64p, _f64p, _f64p, _i32p, C.c_void_p]),
     "pg_mash_distance_block": (C.c_int, [_u32p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _u32p, _f64p]),

@@ -7,7 +7,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cctype>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
+#include <unordered_map>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -17,89 +25,8 @@ namespace pg {
 static thread_local char t_err[512] = "";
 static thread_local const char *t_last_kernel = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::mutex g_mu;         // serialises the host-pointer entry points
-static int g_device = -1;       // bound device (-1: not initialised)
-static int g_sms = 0;
-static cudaStream_t g_streams[3] = {nullptr, nullptr, nullptr};
 
-void set_error(const char *fmt, ...) {
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(t_err, sizeof t_err, fmt, ap);
-    va_end(ap);
-}
-int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
-    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
-    return PG_ERR_CUDA;
-}
-void note_launch(const char *name) {
-    t_last_kernel = name;
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-}
-int sm_count() { return g_sms > 0 ? g_sms : 148; }
-
-static int init_locked(int device) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        set_error("no CUDA device available (%s); libpolyb200 has no CPU fallback",
-                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-        cudaGetLastError();
-        return PG_ERR_NO_DEVICE;
-    }
-    if (device < 0) {
-        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
-    }
-    if (device >= n) {
-        set_error("device %d out of range (count %d)", device, n);
-        return PG_ERR_ARG;
-    }
-    cudaDeviceProp prop;
-    PG_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        set_error("device %d is sm_%d%d; libpolyb200 is built for sm_100a only", device, prop.major,
-                  prop.minor);
-        return PG_ERR_NO_DEVICE;
-    }
-    PG_CUDA(cudaSetDevice(device));
-    if (g_device != device) {
-        for (int i = 0; i < 3; ++i) {
-            if (g_streams[i]) { cudaStreamDestroy(g_streams[i]); g_streams[i] = nullptr; }
-        }
-    }
-    for (int i = 0; i < 3; ++i) {
-        if (!g_streams[i]) PG_CUDA(cudaStreamCreateWithFlags(&g_streams[i], cudaStreamNonBlocking));
-    }
-    {   // Stream-ordered temporaries (cudaMallocAsync) are freed at the end of every call and most calls
-        // synchronise: with the default release threshold of 0 the pool would hand its memory back to the
-        // driver each time.  Keep up to 1 GiB cached so that small calls do not pay a driver allocation.
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = 1ull << 30, cur = 0;
-            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        cudaGetLastError();
-    }
-    g_device = device;
-    g_sms = prop.multiProcessorCount;
-    return PG_OK;
-}
-
-// every entry point: make sure a device is bound and current on this thread
-static int ensure_device() {
-    if (g_device < 0) {
-        std::lock_guard<std::mutex> lk(g_mu);
-        if (g_device < 0) {
-            int rc = init_locked(-1);
-            if (rc != PG_OK) return rc;
-        }
-    }
-    PG_CUDA(cudaSetDevice(g_device));
-    return PG_OK;
-}
-
-// grow-only device scratch used by the host-pointer entry points (under g_mu)
+// grow-only device scratch used by the host-pointer entry points (under the context's mutex)
 struct Scratch {
     void *p = nullptr;
     size_t cap = 0;
@@ -123,7 +50,136 @@ struct Scratch {
         cap = 0;
     }
 };
-static Scratch g_in[3], g_out[3], g_aux[3], g_st[3];
+
+// One context per CUDA device of the process.  The library serves any number of devices from one
+// process (pg_*_multi shard a batch over them; pg_thread_device binds a thread to one) as well as
+// the one-process-per-GPU layout (pg_init(device) picks the process default).
+constexpr int MAX_DEVICES = 32;
+constexpr int N_SLOTS = 3;  // stream/buffer slots of the pipelined host path
+struct DevCtx {
+    int device = -1;
+    int sms = 0;
+    std::atomic<bool> ready{false};
+    cudaStream_t streams[N_SLOTS] = {nullptr, nullptr, nullptr};
+    Scratch in[N_SLOTS], out[N_SLOTS], aux[N_SLOTS], st[N_SLOTS];
+    std::mutex mu;   // serialises the host-pointer entry points on this device
+    std::mutex fmu;  // guards func_smem
+    std::unordered_map<const void *, size_t> func_smem;  // largest dynamic smem configured per kernel
+};
+static DevCtx g_ctx[MAX_DEVICES];
+static std::mutex g_init_mu;                 // context creation / default-device changes
+static std::atomic<int> g_default_device{-1};  // process default (pg_init), -1: not chosen yet
+static thread_local int t_bound_device = -1;   // pg_thread_device override for this thread
+static thread_local DevCtx *t_ctx = nullptr;   // context the current entry point runs on
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof t_err, fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return PG_ERR_CUDA;
+}
+void note_launch(const char *name) {
+    t_last_kernel = name;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+}
+int sm_count() { return t_ctx && t_ctx->sms > 0 ? t_ctx->sms : 148; }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel, size class): function
+// attributes live in the device's context, so the cache is per device and lock-protected (several
+// host threads may drive the same device through the *_dev entry points).
+int func_smem(const void *fn, size_t bytes) {
+    DevCtx *c = t_ctx;
+    if (!c) { set_error("internal: no device context bound"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(c->fmu);
+    size_t &cur = c->func_smem[fn];
+    if (bytes > cur) {
+        PG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return PG_OK;
+}
+
+// create (once) the context of `device`; g_init_mu held
+static int ctx_create_locked(int device) {
+    DevCtx &c = g_ctx[device];
+    if (c.ready.load(std::memory_order_acquire)) return PG_OK;
+    cudaDeviceProp prop;
+    PG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; libpolyb200 is built for sm_100a only", device, prop.major, prop.minor);
+        return PG_ERR_NO_DEVICE;
+    }
+    PG_CUDA(cudaSetDevice(device));
+    for (int i = 0; i < N_SLOTS; ++i)
+        if (!c.streams[i]) PG_CUDA(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
+    {   // Stream-ordered temporaries (cudaMallocAsync) are freed at the end of every call and most calls
+        // synchronise: with the default release threshold of 0 the pool would hand its memory back to the
+        // driver each time.  Keep up to 1 GiB cached so that small calls do not pay a driver allocation.
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = 1ull << 30, cur = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
+    c.device = device;
+    c.sms = prop.multiProcessorCount;
+    c.ready.store(true, std::memory_order_release);
+    return PG_OK;
+}
+
+static int device_count_checked(int *n) {
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess || *n == 0) {
+        set_error("no CUDA device available (%s); libpolyb200 has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return PG_ERR_NO_DEVICE;
+    }
+    if (*n > MAX_DEVICES) *n = MAX_DEVICES;
+    return PG_OK;
+}
+
+// make `device` usable and current on the calling thread; t_ctx = its context
+static int use_device(int device) {
+    int n = 0, rc = device_count_checked(&n);
+    if (rc != PG_OK) return rc;
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (count %d)", device, n);
+        return PG_ERR_ARG;
+    }
+    if (!g_ctx[device].ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        if ((rc = ctx_create_locked(device)) != PG_OK) return rc;
+    }
+    PG_CUDA(cudaSetDevice(device));
+    t_ctx = &g_ctx[device];
+    return PG_OK;
+}
+
+// every entry point: the thread's bound device (pg_thread_device), else the process default
+// (pg_init), else the current CUDA device / device 0
+static int ensure_device() {
+    int device = t_bound_device;
+    if (device < 0) device = g_default_device.load(std::memory_order_acquire);
+    if (device < 0) {
+        int n = 0, rc = device_count_checked(&n);
+        if (rc != PG_OK) return rc;
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        device = g_default_device.load();
+        if (device < 0) {
+            if (cudaGetDevice(&device) != cudaSuccess || device >= n) device = 0;
+            if ((rc = ctx_create_locked(device)) != PG_OK) return rc;
+            g_default_device.store(device, std::memory_order_release);
+        }
+    }
+    return use_device(device);
+}
 
 static inline uint64_t kmers_of(uint64_t len, int k) { return len > (uint64_t)k ? len - (uint64_t)k : 0; }
 
@@ -154,21 +210,42 @@ extern "C" {
 int pg_version(void) { return 100; }
 
 int pg_init(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    return init_locked(device);
+    if (device < 0) {
+        g_default_device.store(-1);
+        return ensure_device();
+    }
+    int rc = use_device(device);
+    if (rc == PG_OK) g_default_device.store(device, std::memory_order_release);
+    return rc;
+}
+
+int pg_thread_device(int device) {
+    if (device < 0) { t_bound_device = -1; return PG_OK; }
+    int rc = use_device(device);
+    if (rc == PG_OK) t_bound_device = device;
+    return rc;
 }
 
 int pg_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device >= 0) {
-        cudaSetDevice(g_device);
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        DevCtx &c = g_ctx[d];
+        if (!c.ready.load()) continue;
+        std::lock_guard<std::mutex> lk2(c.mu);
+        cudaSetDevice(d);
         cudaDeviceSynchronize();
-        for (int i = 0; i < 3; ++i) {
-            g_in[i].release(); g_out[i].release(); g_aux[i].release(); g_st[i].release();
-            if (g_streams[i]) { cudaStreamDestroy(g_streams[i]); g_streams[i] = nullptr; }
+        for (int i = 0; i < N_SLOTS; ++i) {
+            c.in[i].release(); c.out[i].release(); c.aux[i].release(); c.st[i].release();
+            if (c.streams[i]) { cudaStreamDestroy(c.streams[i]); c.streams[i] = nullptr; }
         }
+        {
+            std::lock_guard<std::mutex> lk3(c.fmu);
+            c.func_smem.clear();
+        }
+        c.ready.store(false);
     }
-    g_device = -1;
+    g_default_device.store(-1);
+    t_ctx = nullptr;
     return PG_OK;
 }
 
@@ -187,7 +264,53 @@ int pg_device_sm_count(int *sms) {
     if (!sms) return PG_ERR_ARG;
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
-    *sms = g_sms;
+    *sms = t_ctx->sms;
+    return PG_OK;
+}
+
+// Put the calling thread on the CPUs of the NUMA node `device` hangs off, and prefer that node for
+// the pages it allocates from now on (pinned buffers included): PCIe traffic of 8 GPUs otherwise
+// funnels through one socket's memory controllers / the inter-socket link.  Best effort: every
+// failure (no sysfs, container without the syscall, single-node host) leaves the thread as it was.
+int pg_numa_bind_thread(int device, int *node_out) {
+    if (node_out) *node_out = -1;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); set_error("device %d out of range", device); return PG_ERR_ARG; }
+    char bus[64] = "";
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return PG_OK; }
+    for (char *c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE *f = fopen(path, "r")) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+    if (node < 0) return PG_OK;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    cpu_set_t want, cur, both;
+    CPU_ZERO(&want);
+    if (FILE *f = fopen(path, "r")) {
+        int a, b;
+        for (;;) {
+            if (fscanf(f, "%d", &a) != 1) break;
+            b = a;
+            int ch = fgetc(f);
+            if (ch == '-') { if (fscanf(f, "%d", &b) != 1) break; ch = fgetc(f); }
+            for (int c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(c, &want);
+            if (ch != ',') break;
+        }
+        fclose(f);
+    }
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+        CPU_AND(&both, &cur, &want);
+        if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof both, &both);
+    }
+#ifdef SYS_set_mempolicy
+    if (node < 1024) {
+        unsigned long mask[16] = {0};
+        mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+        (void)syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, (unsigned long)(sizeof mask * 8));
+    }
+#endif
+    if (node_out) *node_out = node;
     return PG_OK;
 }
 
@@ -195,7 +318,8 @@ int pg_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) return PG_ERR_ARG;
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
-    PG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    // portable: pinned for every device context of the process (the *_multi entry points)
+    PG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
     return PG_OK;
 }
 int pg_host_free(void *ptr) {
@@ -292,25 +416,39 @@ int pg_ipc_close(void *dptr) {
     return PG_OK;
 }
 
+// rows [row_offset, row_offset + n_local) of every destination buffer (compact rows of cnt words)
+static int sketch_scatter_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len, int32_t k, int32_t s,
+                              void *const *dst_ptrs, int32_t n_dst, int32_t self, uint64_t row_offset, cudaStream_t st) {
+    int rc;
+    if ((rc = check_ks(k, s)) != PG_OK) return rc;
+    if (n_dst < 1 || n_dst > PG_MAX_PEERS || self < 0 || self >= n_dst || !dst_ptrs) {
+        set_error("bad destination set (%d buffers, own index %d; at most %d)", n_dst, self, PG_MAX_PEERS);
+        return PG_ERR_ARG;
+    }
+    const uint64_t cnt = std::min<uint64_t>(kmers_of(read_len, k), (uint64_t)s);
+    SketchDst dst;
+    dst.n = n_dst;
+    for (int p = 0; p < n_dst; ++p) {
+        if (!dst_ptrs[p]) { set_error("null gathered pointer for rank %d", p); return PG_ERR_ARG; }
+        dst.ptr[p] = (uint32_t *)dst_ptrs[p] + row_offset * cnt;  // this rank's row block
+    }
+    return launch_sketch_uniform(d_bases, n_local, read_len, k, s, 0, dst.ptr[self], cnt, nullptr, st, &dst);
+}
+
 int pg_mash_sketch_uniform_gather_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len,
                                       int32_t k, int32_t s, void *const *gathered_ptrs,
                                       int32_t world, int32_t rank, void *stream) {
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
-    if ((rc = check_ks(k, s)) != PG_OK) return rc;
-    if (world < 1 || world > PG_MAX_PEERS || rank < 0 || rank >= world || !gathered_ptrs) {
-        set_error("bad world/rank (%d/%d)", world, rank);
-        return PG_ERR_ARG;
-    }
-    const uint64_t cnt = std::min<uint64_t>(kmers_of(read_len, k), (uint64_t)s);
-    SketchDst dst;
-    dst.n = world;
-    for (int p = 0; p < world; ++p) {
-        if (!gathered_ptrs[p]) { set_error("null gathered pointer for rank %d", p); return PG_ERR_ARG; }
-        dst.ptr[p] = (uint32_t *)gathered_ptrs[p] + (uint64_t)rank * n_local * cnt;  // this rank's row block
-    }
-    return launch_sketch_uniform(d_bases, n_local, read_len, k, s, 0, dst.ptr[rank], cnt, nullptr,
-                                 (cudaStream_t)stream, &dst);
+    return sketch_scatter_dev(d_bases, n_local, read_len, k, s, gathered_ptrs, world, rank, (uint64_t)(rank < 0 ? 0 : rank) * n_local,
+                              (cudaStream_t)stream);
+}
+
+int pg_mash_sketch_uniform_scatter_dev(const uint8_t *d_bases, uint64_t n_local, uint32_t read_len, int32_t k, int32_t s,
+                                       void *const *dst_ptrs, int32_t n_dst, int32_t self, uint64_t row_offset, void *stream) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    return sketch_scatter_dev(d_bases, n_local, read_len, k, s, dst_ptrs, n_dst, self, row_offset, (cudaStream_t)stream);
 }
 
 // Pipelined host path shared by the uniform and ragged entry points: chunks of reads
@@ -323,7 +461,7 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
     if ((rc = check_ks(k, s)) != PG_OK) return rc;
     if (n_reads == 0) return PG_OK;
     if (!bases || !out) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
     const bool want_status = status != nullptr || s <= 1;
     const uint64_t target_bytes = 192ull << 20;  // input bytes per chunk
     bool any_panic = false;
@@ -334,7 +472,7 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
     std::vector<int32_t> st_slot[3];
     auto drain = [&](int sl) -> int {
         if (!pend[sl].used) return PG_OK;
-        PG_CUDA(cudaStreamSynchronize(g_streams[sl]));
+        PG_CUDA(cudaStreamSynchronize(t_ctx->streams[sl]));
         if (want_status) {
             for (uint64_t i = 0; i < pend[sl].nr; ++i) {
                 if (st_slot[sl][i] != PG_ITEM_OK) any_panic = true;
@@ -375,18 +513,18 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
         if (row_stride < dev_stride) { set_error("row_stride %llu < %llu", (unsigned long long)row_stride, (unsigned long long)dev_stride); return PG_ERR_ARG; }
 
         if ((rc = drain(slot)) != PG_OK) return rc;
-        cudaStream_t stx = g_streams[slot];
+        cudaStream_t stx = t_ctx->streams[slot];
         const uint64_t in_bytes = end - beg;
-        if ((rc = g_in[slot].reserve(in_bytes + 64)) != PG_OK) return rc;
-        if ((rc = g_out[slot].reserve(std::max<uint64_t>(nr * dev_stride * 4, 16))) != PG_OK) return rc;
-        uint8_t *d_in = (uint8_t *)g_in[slot].p;
-        uint32_t *d_out = (uint32_t *)g_out[slot].p;
+        if ((rc = t_ctx->in[slot].reserve(in_bytes + 64)) != PG_OK) return rc;
+        if ((rc = t_ctx->out[slot].reserve(std::max<uint64_t>(nr * dev_stride * 4, 16))) != PG_OK) return rc;
+        uint8_t *d_in = (uint8_t *)t_ctx->in[slot].p;
+        uint32_t *d_out = (uint32_t *)t_ctx->out[slot].p;
         int32_t *d_status = nullptr;
         uint32_t *d_count = nullptr;
         uint64_t *d_off = nullptr;
         if (want_status) {
-            if ((rc = g_st[slot].reserve(nr * 4)) != PG_OK) return rc;
-            d_status = (int32_t *)g_st[slot].p;
+            if ((rc = t_ctx->st[slot].reserve(nr * 4)) != PG_OK) return rc;
+            d_status = (int32_t *)t_ctx->st[slot].p;
             PG_CUDA(cudaMemsetAsync(d_status, 0, nr * 4, stx));
             st_slot[slot].assign(nr, 0);
         }
@@ -394,8 +532,8 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
         if (uniform) {
             rc = launch_sketch_uniform(d_in, nr, (uint32_t)maxlen, k, s, flags, d_out, dev_stride, d_status, stx);
         } else {
-            if ((rc = g_aux[slot].reserve((nr + 1) * 8 + nr * 4)) != PG_OK) return rc;
-            d_off = (uint64_t *)g_aux[slot].p;
+            if ((rc = t_ctx->aux[slot].reserve((nr + 1) * 8 + nr * 4)) != PG_OK) return rc;
+            d_off = (uint64_t *)t_ctx->aux[slot].p;
             d_count = (uint32_t *)(d_off + nr + 1);
             PG_CUDA(cudaMemcpyAsync(d_off, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, stx));
             // kernels index bases with absolute offsets: shift the base pointer
@@ -443,6 +581,265 @@ int pg_mash_sketch_uniform(const uint8_t *bases, uint64_t n_reads, uint32_t read
 }
 
 // ---------------------------------------------------------------------------------
+// Single-process multi-GPU entry points (SURVEY.md 8b "multi-GPU variants taking a device
+// count", 8e): one host thread per device, reads sharded in contiguous blocks, no data-path
+// collective for Sketch; Sketch+Distance exchanges the finished sketches by peer stores issued
+// from the sketch kernels themselves (in-process peer access, no IPC).
+// ---------------------------------------------------------------------------------
+namespace pg {
+namespace {
+
+struct WorkerResult {
+    int rc = PG_OK;
+    std::string msg;
+};
+
+// worst result of the workers, message copied to the caller's thread-local slot.  A reference panic
+// (PG_ERR_PANIC: per-item statuses are still complete) ranks below real failures.
+static int fold_results(const std::vector<WorkerResult> &res) {
+    int worst = PG_OK;
+    const std::string *msg = nullptr;
+    for (const WorkerResult &r : res) {
+        if (r.rc == PG_OK) continue;
+        const bool soft = r.rc == PG_ERR_PANIC, worst_soft = worst == PG_ERR_PANIC || worst == PG_OK;
+        if (worst == PG_OK || (!soft && worst_soft)) { worst = r.rc; msg = &r.msg; }
+    }
+    if (msg) set_error("%s", msg->c_str());
+    return worst;
+}
+
+static int resolve_devices(const int32_t *devices, int32_t n_devices, std::vector<int> *out) {
+    int n = 0, rc = device_count_checked(&n);
+    if (rc != PG_OK) return rc;
+    out->clear();
+    if (!devices) {
+        const int cnt = n_devices > 0 ? std::min<int>(n_devices, n) : n;
+        for (int i = 0; i < cnt; ++i) out->push_back(i);
+    } else {
+        if (n_devices <= 0) { set_error("device list given with n_devices = %d", n_devices); return PG_ERR_ARG; }
+        for (int i = 0; i < n_devices; ++i) {
+            if (devices[i] < 0 || devices[i] >= n) { set_error("device %d out of range (count %d)", devices[i], n); return PG_ERR_ARG; }
+            for (int j = 0; j < i; ++j)
+                if (devices[j] == devices[i]) { set_error("device %d listed twice", devices[i]); return PG_ERR_ARG; }
+            out->push_back(devices[i]);
+        }
+    }
+    if (out->size() > (size_t)PG_MAX_PEERS) out->resize(PG_MAX_PEERS);
+    return PG_OK;
+}
+
+// reusable barrier for the device threads of one call
+class Rendezvous {
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int n_, waiting_ = 0;
+    uint64_t gen_ = 0;
+public:
+    explicit Rendezvous(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        const uint64_t g = gen_;
+        if (++waiting_ == n_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen_ != g; });
+    }
+};
+
+}  // namespace
+}  // namespace pg
+
+static int sketch_multi(const uint8_t *bases, const uint64_t *offsets, uint32_t ulen, uint64_t n_reads, int32_t k, int32_t s,
+                        uint32_t flags, uint32_t *out, uint64_t row_stride, uint32_t *count, int32_t *status,
+                        const int32_t *devices, int32_t n_devices) {
+    int rc;
+    if ((rc = check_ks(k, s)) != PG_OK) return rc;
+    std::vector<int> dev;
+    if ((rc = resolve_devices(devices, n_devices, &dev)) != PG_OK) return rc;
+    if (n_reads == 0) return PG_OK;
+    if (!bases || !out) { set_error("null buffer"); return PG_ERR_ARG; }
+    const int P = (int)dev.size();
+    // contiguous shards; boundaries on K1 tile boundaries (32 reads).  Ragged batches balance bytes.
+    std::vector<uint64_t> cut(P + 1, n_reads);
+    cut[0] = 0;
+    if (!offsets) {
+        uint64_t per = (n_reads + P - 1) / P;
+        per = (per + 31) & ~31ull;
+        for (int r = 1; r < P; ++r) cut[r] = std::min(n_reads, (uint64_t)r * per);
+    } else {
+        const uint64_t b0 = offsets[0], total = offsets[n_reads] - b0;
+        for (int r = 1; r < P; ++r) {
+            const uint64_t want = b0 + total / P * r;
+            uint64_t i = std::lower_bound(offsets, offsets + n_reads + 1, want) - offsets;
+            i = std::min<uint64_t>((i + 31) & ~31ull, n_reads);
+            cut[r] = std::max(i, cut[r - 1]);
+        }
+    }
+    std::vector<WorkerResult> res(P);
+    std::vector<std::thread> th;
+    for (int r = 0; r < P; ++r) {
+        const uint64_t lo = cut[r], hi = cut[r + 1];
+        if (hi <= lo) continue;
+        th.emplace_back([=, &res] {
+            t_bound_device = dev[r];  // this worker's entry points run on its device
+            pg_numa_bind_thread(dev[r], nullptr);  // best effort: staging copies from the GPU's NUMA node
+            const int wrc = offsets ? sketch_host(bases, offsets + lo, 0, hi - lo, k, s, flags, out + lo * row_stride, row_stride,
+                                                  count ? count + lo : nullptr, status ? status + lo : nullptr)
+                                    : sketch_host(bases + lo * (uint64_t)ulen, nullptr, ulen, hi - lo, k, s, flags, out + lo * row_stride,
+                                                  row_stride, nullptr, status ? status + lo : nullptr);
+            res[r].rc = wrc;
+            if (wrc != PG_OK) res[r].msg = t_err;
+        });
+    }
+    for (std::thread &t : th) t.join();
+    return fold_results(res);
+}
+
+extern "C" int pg_mash_sketch_uniform_multi(const uint8_t *bases, uint64_t n_reads, uint32_t read_len, int32_t k, int32_t s,
+                                            uint32_t flags, uint32_t *out, uint64_t row_stride, int32_t *status,
+                                            const int32_t *devices, int32_t n_devices) {
+    return sketch_multi(bases, nullptr, read_len, n_reads, k, s, flags, out, row_stride, nullptr, status, devices, n_devices);
+}
+
+extern "C" int pg_mash_sketch_batch_multi(const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int32_t k, int32_t s,
+                                          uint32_t flags, uint32_t *out, uint64_t row_stride, uint32_t *count, int32_t *status,
+                                          const int32_t *devices, int32_t n_devices) {
+    if (n_reads && !offsets) { set_error("null offsets"); return PG_ERR_ARG; }
+    return sketch_multi(bases, offsets, 0, n_reads, k, s, flags, out, row_stride, count, status, devices, n_devices);
+}
+
+// Sketch + all-pairs distance over several devices of this process (cfg3 / cfg4 pipeline):
+//   1. device r takes reads [lo_r, hi_r), copies them in and runs the sketch kernel, whose finished
+//      tiles / rows are stored straight into the gathered buffer of EVERY device (peer access
+//      enabled in-process): sketching and the all-gather are one kernel;
+//   2. after a rendezvous every device holds all n sketches and computes row block r of the pair
+//      matrix (receiver = row) with the same kernels as pg_mash_distance_block.
+// Without peer access between two of the devices the exchange falls back to cudaMemcpyPeerAsync pulls.
+extern "C" int pg_mash_sketch_distance_multi(const uint8_t *bases, uint64_t n_reads, uint32_t read_len, int32_t k, int32_t s,
+                                             const int32_t *devices, int32_t n_devices, uint32_t *sketches, uint32_t *same,
+                                             double *distance) {
+    int rc;
+    if ((rc = check_ks(k, s)) != PG_OK) return rc;
+    std::vector<int> dev;
+    if ((rc = resolve_devices(devices, n_devices, &dev)) != PG_OK) return rc;
+    if (n_reads == 0) return PG_OK;
+    if (!bases) { set_error("null buffer"); return PG_ERR_ARG; }
+    if (s <= 0) { set_error("distance over sketches of size %d: the reference panics", s); return PG_ERR_PANIC; }
+    const uint64_t n = n_reads, L = read_len;
+    const uint64_t cnt = std::min<uint64_t>(kmers_of(L, k), (uint64_t)s);
+    int P = (int)std::min<uint64_t>(dev.size(), (n + 31) / 32);
+    dev.resize(P);
+    std::vector<uint64_t> cut(P + 1, n);
+    cut[0] = 0;
+    {
+        uint64_t per = (n + P - 1) / P;
+        per = (per + 31) & ~31ull;
+        for (int r = 1; r < P; ++r) cut[r] = std::min(n, (uint64_t)r * per);
+    }
+    // peer access available between every pair?
+    bool fused = true;
+    for (int a = 0; a < P && fused; ++a)
+        for (int b = 0; b < P && fused; ++b) {
+            int can = 1;
+            if (a != b && cudaDeviceCanAccessPeer(&can, dev[a], dev[b]) != cudaSuccess) can = 0;
+            fused = fused && can;
+        }
+    cudaGetLastError();
+    std::vector<void *> gathered(P, nullptr);  // [n][cnt] compact rows on every device
+    std::vector<WorkerResult> res(P);
+    std::atomic<bool> failed{false};
+    Rendezvous meet(P);
+    auto worker = [&](int r) {
+        WorkerResult &my = res[r];
+        auto fail = [&](int code) { my.rc = code; my.msg = t_err; failed.store(true); };
+        auto step = [&](auto &&fn) { if (!failed.load()) { const int c = fn(); if (c != PG_OK) fail(c); } };
+        t_bound_device = dev[r];
+        pg_numa_bind_thread(dev[r], nullptr);
+        const uint64_t lo = cut[r], hi = cut[r + 1], nl = hi - lo;
+        uint8_t *d_reads = nullptr;
+        uint32_t *d_full = nullptr;  // [n][s] full Go arrays (== gathered when cnt == s)
+        cudaStream_t st = nullptr;
+        step([&]() -> int {
+            int c = ensure_device();
+            if (c != PG_OK) return c;
+            st = t_ctx->streams[0];
+            if (fused)
+                for (int p = 0; p < P; ++p)
+                    if (p != r) {
+                        cudaError_t e = cudaDeviceEnablePeerAccess(dev[p], 0);
+                        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+                        cudaGetLastError();
+                    }
+            PG_CUDA(cudaMalloc(&gathered[r], std::max<uint64_t>(n * cnt * 4, 16)));
+            PG_CUDA(cudaMalloc(&d_reads, std::max<uint64_t>(nl * L, 16) + 64));
+            return PG_OK;
+        });
+        meet.wait();  // every buffer exists, peer access is on
+        step([&]() -> int {
+            if (nl) PG_CUDA(cudaMemcpyAsync(d_reads, bases + lo * L, nl * L, cudaMemcpyHostToDevice, st));
+            int c;
+            if (fused) {
+                c = sketch_scatter_dev(d_reads, nl, read_len, k, s, gathered.data(), P, r, lo, st);
+            } else {
+                void *own = gathered[r];
+                c = sketch_scatter_dev(d_reads, nl, read_len, k, s, &own, 1, 0, lo, st);
+            }
+            if (c != PG_OK) return c;
+            PG_CUDA(cudaStreamSynchronize(st));
+            return PG_OK;
+        });
+        meet.wait();  // all sketches computed (fused: and stored everywhere)
+        step([&]() -> int {
+            if (!fused)  // pull the other devices' row blocks
+                for (int p = 0; p < P; ++p)
+                    if (p != r && cut[p + 1] > cut[p])
+                        PG_CUDA(cudaMemcpyPeerAsync((uint32_t *)gathered[r] + cut[p] * cnt, dev[r], (uint32_t *)gathered[p] + cut[p] * cnt, dev[p],
+                                                    (cut[p + 1] - cut[p]) * cnt * 4, st));
+            if (cnt == (uint64_t)s) {
+                d_full = (uint32_t *)gathered[r];
+            } else {  // the zero tail of a fresh Mash is materialised after the exchange
+                PG_CUDA(cudaMalloc(&d_full, n * (uint64_t)s * 4));
+                PG_CUDA(cudaMemsetAsync(d_full, 0, n * (uint64_t)s * 4, st));
+                if (cnt) PG_CUDA(cudaMemcpy2DAsync(d_full, (size_t)s * 4, gathered[r], cnt * 4, cnt * 4, n, cudaMemcpyDeviceToDevice, st));
+            }
+            if (sketches && nl) PG_CUDA(cudaMemcpyAsync(sketches + lo * (uint64_t)s, d_full + lo * (uint64_t)s, nl * (uint64_t)s * 4, cudaMemcpyDeviceToHost, st));
+            if ((same || distance) && nl) {
+                DistancePlan plan;
+                int c = distance_plan_create(d_full, n, s, st, &plan);
+                const uint64_t rows_per = std::max<uint64_t>(8, ((64ull << 20) / n) & ~7ull);
+                for (uint64_t rb = lo; rb < hi && c == PG_OK; rb += rows_per) {
+                    const uint64_t re = std::min(hi, rb + rows_per);
+                    Tmp d_same(st), d_dist(st);
+                    if (same && (c = d_same.alloc((re - rb) * n * 4))) break;
+                    if (distance && (c = d_dist.alloc((re - rb) * n * 8))) break;
+                    c = distance_plan_rows(plan, rb, re, same ? d_same.as<uint32_t>() : nullptr, distance ? d_dist.as<double>() : nullptr, st);
+                    if (c != PG_OK) break;
+                    cudaError_t e = cudaSuccess;
+                    if (same) e = cudaMemcpyAsync(same + rb * n, d_same.p, (re - rb) * n * 4, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess && distance) e = cudaMemcpyAsync(distance + rb * n, d_dist.p, (re - rb) * n * 8, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                    if (e != cudaSuccess) c = cuda_fail(e, "distance block copy", __FILE__, __LINE__);
+                }
+                distance_plan_destroy(plan, st);
+                if (c != PG_OK) return c;
+            }
+            PG_CUDA(cudaStreamSynchronize(st));
+            return PG_OK;
+        });
+        meet.wait();  // nobody reads a peer buffer any more
+        if (t_ctx) {
+            cudaSetDevice(dev[r]);
+            if (d_full && d_full != gathered[r]) cudaFree(d_full);
+            if (d_reads) cudaFree(d_reads);
+            if (gathered[r]) cudaFree(gathered[r]);
+            cudaGetLastError();
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < P; ++r) th.emplace_back(worker, r);
+    for (std::thread &t : th) t.join();
+    return fold_results(res);
+}
+
+// ---------------------------------------------------------------------------------
 // Similarity / Distance
 // ---------------------------------------------------------------------------------
 int pg_mash_similarity_pairs_dev(const uint32_t *d_sketches, const uint64_t *d_sk_offsets,
@@ -465,8 +862,8 @@ int pg_mash_similarity_pairs(const uint32_t *sketches, const uint64_t *sk_offset
     if (rc != PG_OK) return rc;
     if (n_pairs == 0) return PG_OK;
     if (!sk_offsets || !pair_a || !pair_b) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t words = sk_offsets[n_sketches];
     Tmp d_sk(st), d_off(st), d_a(st), d_b(st), d_same(st), d_sim(st), d_dist(st), d_st(st);
     if ((rc = d_sk.alloc(words * 4)) || (rc = d_off.alloc((n_sketches + 1) * 8)) ||
@@ -513,8 +910,8 @@ int pg_mash_distance_block(const uint32_t *sketches, uint64_t n, int32_t s, uint
     if (row_end > n || row_begin > row_end) { set_error("bad row range"); return PG_ERR_ARG; }
     if (row_end == row_begin || n == 0) return PG_OK;
     if (s <= 0) { set_error("distance over sketches of size %d: the reference panics", s); return PG_ERR_PANIC; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     Tmp d_sk(st);
     if ((rc = d_sk.alloc(n * (uint64_t)s * 4))) return rc;
     PG_CUDA(cudaMemcpyAsync(d_sk.p, sketches, n * (uint64_t)s * 4, cudaMemcpyHostToDevice, st));
@@ -564,8 +961,8 @@ static int align_score_host(int global, const uint8_t *queries, const uint64_t *
     if (rc != PG_OK) return rc;
     if (n_queries == 0) return PG_OK;
     if (!q_offsets || !score || !lut_a || !lut_b || !table) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t q0 = q_offsets[0], qbytes = q_offsets[n_queries] - q0;
     uint64_t maxq = 0;
     for (uint64_t i = 0; i < n_queries; ++i) maxq = std::max(maxq, q_offsets[i + 1] - q_offsets[i]);
@@ -631,8 +1028,8 @@ static int align_strings_host(int global, const uint8_t *queries, const uint64_t
         set_error("null buffer");
         return PG_ERR_ARG;
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t q0 = q_offsets[0], qbytes = q_offsets[n_queries] - q0;
     uint64_t maxq = 0;
     for (uint64_t i = 0; i < n_queries; ++i) maxq = std::max(maxq, q_offsets[i + 1] - q_offsets[i]);
@@ -698,8 +1095,8 @@ int pg_tm_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n, doubl
     if (rc != PG_OK) return rc;
     if (n == 0) return PG_OK;
     if (!offsets) { set_error("null offsets"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t b0 = offsets[0], nbytes = offsets[n] - b0;
     Tmp d_b(st), d_off(st), d_tm(st), d_dh(st), d_ds(st), d_st(st);
     if ((rc = d_b.alloc(nbytes)) || (rc = d_off.alloc((n + 1) * 8)) || (rc = d_tm.alloc(n * 8)) ||
@@ -736,8 +1133,8 @@ int pg_design_primers_batch(const uint8_t *bases, const uint64_t *offsets, uint6
     if (rc != PG_OK) return rc;
     if (n == 0) return PG_OK;
     if (!offsets || !fwd_len || !rev_len) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t b0 = offsets[0], nbytes = offsets[n] - b0;
     Tmp d_b(st), d_off(st), d_f(st), d_r(st), d_st(st);
     if ((rc = d_b.alloc(nbytes)) || (rc = d_off.alloc((n + 1) * 8)) || (rc = d_f.alloc(n * 4)) ||
@@ -770,8 +1167,8 @@ int pg_pcr_minimal_primer_batch(const uint8_t *bases, const uint64_t *offsets, u
     if (rc != PG_OK) return rc;
     if (n == 0) return PG_OK;
     if (!offsets || !min_len) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t b0 = offsets[0], nbytes = offsets[n] - b0;
     Tmp d_b(st), d_off(st), d_m(st), d_st(st);
     if ((rc = d_b.alloc(nbytes)) || (rc = d_off.alloc((n + 1) * 8)) || (rc = d_m.alloc(n * 4)) || (rc = d_st.alloc(n * 4))) return rc;
@@ -803,8 +1200,8 @@ int pg_find_sites_batch(const uint8_t *seqs, const uint64_t *seq_offsets, uint64
     *n_hits = 0;
     if (n_seq == 0 || n_pat == 0) return PG_OK;
     if (!seq_offsets || !pat_offsets || (hits_cap && (!hit_seq || !hit_pos || !hit_pat))) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     const uint64_t s0 = seq_offsets[0], sbytes = seq_offsets[n_seq] - s0, p0 = pat_offsets[0], pbytes = pat_offsets[n_pat] - p0;
     std::vector<uint64_t> poff(n_pat + 1);
     for (uint32_t q = 0; q <= n_pat; ++q) poff[q] = pat_offsets[q] - p0;  // the kernel stages patterns from offset 0
@@ -854,8 +1251,8 @@ int pg_fastq_ingest(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
     if (!n_records || !total_bases || !err_code || !err_line || !offsets) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     Tmp d_text(st), d_bases(st), d_off(st);
     if ((rc = d_text.alloc(nbytes + 16)) || (rc = d_bases.alloc(bases_cap + 16)) || (rc = d_off.alloc((records_cap + 1) * 8)))
         return rc;
@@ -890,8 +1287,8 @@ int pg_fasta_ingest(const uint8_t *text, uint64_t nbytes, uint32_t max_line_size
     if (!n_records || !total_bases || !total_name_bytes || !err_code || !err_line || !offsets) { set_error("null buffer"); return PG_ERR_ARG; }
     const bool want_names = names != nullptr || name_offsets != nullptr;
     if (want_names && (!names || !name_offsets)) { set_error("names and name_offsets must be given together"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(g_mu);
-    cudaStream_t st = g_streams[0];
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
     Tmp d_text(st), d_bases(st), d_off(st), d_names(st), d_noff(st);
     if ((rc = d_text.alloc(nbytes + 16)) || (rc = d_bases.alloc(bases_cap + 16)) || (rc = d_off.alloc((records_cap + 1) * 8)))
         return rc;

@@ -27,6 +27,8 @@ void note_launch(const char *kernel_name);
     } while (0)
 
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) cached per (device, kernel); thread-safe (api.cu)
+int func_smem(const void *kernel, size_t bytes);
 
 // Stream-ordered temporaries that are released together when the scope ends -- also on the early
 // returns of PG_CUDA -- with cudaFreeAsync on the stream they were allocated on.

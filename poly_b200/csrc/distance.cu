@@ -248,11 +248,7 @@ int distance_plan_rows(const DistancePlan &plan, uint64_t row_begin, uint64_t ro
         set_error("sketch size %d too large for the all-pairs tile kernel", s);
         return PG_ERR_UNSUPPORTED;
     }
-    static size_t configured = 0;
-    if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(distance_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_ = func_smem((const void *)distance_block_kernel, smem); if (rc_ != PG_OK) return rc_; }
     const uint64_t gy_total = (rows + BT - 1) / BT;
     const uint64_t gx = (n + BT - 1) / BT;
     if (gx > 0x7fffffffull) { set_error("too many sketches"); return PG_ERR_ARG; }

@@ -211,11 +211,7 @@ int join_emit(const JoinIndex &ix, uint64_t row_begin, uint64_t row_end, uint32_
     const uint64_t rows = row_end - row_begin;
     const unsigned sms = (unsigned)sm_count();
     PG_CUDA(cudaMemsetAsync(d_same, 0, rows * ix.n * 4, st));
-    static bool configured = false;
-    if (!configured) {
-        PG_CUDA(cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, JOIN_CAP * 8));
-        configured = true;
-    }
+    { const int rc_ = func_smem((const void *)bucket_join_kernel, JOIN_CAP * 8); if (rc_ != PG_OK) return rc_; }
     bucket_join_kernel<<<(unsigned)std::min<uint64_t>(ix.nb, (uint64_t)sms * 12), JOIN_THREADS, JOIN_CAP * 8, st>>>(
         ix.entries, ix.start, (uint32_t)ix.nb, ix.n, row_begin, row_end, d_same);
     PG_LAUNCH_CHECK("bucket_join_kernel");

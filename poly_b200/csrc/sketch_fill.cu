@@ -245,7 +245,7 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
                            uint32_t uniform_len, uint64_t n_reads, uint64_t first_read, uint32_t k,
                            uint32_t s, uint32_t flags, uint32_t *__restrict__ out,
                            uint64_t row_stride, uint32_t *__restrict__ count,
-                           int32_t *__restrict__ status) {
+                           int32_t *__restrict__ status, const SketchDst extra) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t r = (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < n_reads;
@@ -263,13 +263,22 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
         if (n >= s && !(n == 0 && s == 0)) continue;  // select regime (incl. s in {0,1} panics)
         const uint8_t *seq = bases + beg;
         uint32_t *dst = out + row * row_stride;
-        for (uint64_t i = lane; i < n; i += 32) {
-            const uint8_t *p = seq + i;
-            dst[i] = mm3_bytes([p](uint32_t j) { return __ldg(p + j); }, k);
+        for (uint64_t i = lane; i < row_stride; i += 32) {
+            // hash, then the zero tail of a fresh Mash as far as the caller's row reaches (at least s
+            // words with PG_SKETCH_PAD_ZERO): rows are fully defined whichever kernel produced them
+            uint32_t h = 0u;
+            if (i < n) {
+                const uint8_t *p = seq + i;
+                h = mm3_bytes([p](uint32_t j) { return __ldg(p + j); }, k);
+            }
+            if (extra.n == 0) {
+                dst[i] = h;
+            } else {  // fused all-gather: the row goes to every destination (out is one of them)
+#pragma unroll
+                for (int pr = 0; pr < PG_MAX_PEERS; ++pr)
+                    if (pr < extra.n) extra.ptr[pr][row * row_stride + i] = h;
+            }
         }
-        // the zero tail of a fresh Mash, as far as the caller's row reaches (at least s words with
-        // PG_SKETCH_PAD_ZERO): rows are fully defined whichever kernel produced them
-        for (uint64_t i = n + lane; i < row_stride; i += 32) dst[i] = 0u;
         if (lane == 0) {
             if (count) count[row] = (uint32_t)n;
             if (status) status[row] = PG_ITEM_OK;
@@ -282,12 +291,7 @@ template <int K, int R>
 static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
                      const SketchDst &dst, cudaStream_t st) {
     const size_t smem = (size_t)(R / 32) * (k1_in_bytes(32, L) + (size_t)32 * nk * 4);
-    static size_t configured = 0;  // per instantiation (one process = one device)
-    if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(sketch_fill_uniform_kernel<K, R>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_ = func_smem((const void *)sketch_fill_uniform_kernel<K, R>, smem); if (rc_ != PG_OK) return rc_; }
     sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, dst, L, nk, 4u);
     PG_LAUNCH_CHECK("sketch_fill_uniform_kernel");
     return PG_OK;
@@ -314,12 +318,15 @@ constexpr int K1_WARPS = 1;
 static int launch_fill_generic(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t ulen,
                                uint64_t n_reads, uint64_t first_read, int k, int s, uint32_t flags,
                                uint32_t *d_out, uint64_t row_stride, uint32_t *d_count,
-                               int32_t *d_status, cudaStream_t st) {
+                               int32_t *d_status, cudaStream_t st, const SketchDst *extra = nullptr) {
     if (n_reads == 0) return PG_OK;
     const uint64_t blocks = std::min<uint64_t>((n_reads + 7) / 8, (uint64_t)sm_count() * 32);
+    SketchDst ex;
+    ex.n = 0;
+    if (extra) ex = *extra;
     sketch_fill_generic_kernel<<<(unsigned)blocks, 256, 0, st>>>(
         d_bases, d_offsets, ulen, n_reads, first_read, (uint32_t)k, (uint32_t)s, flags, d_out,
-        row_stride, d_count, d_status);
+        row_stride, d_count, d_status, ex);
     PG_LAUNCH_CHECK("sketch_fill_generic_kernel");
     return PG_OK;
 }
@@ -365,14 +372,9 @@ int launch_sketch_uniform(const uint8_t *d_bases, uint64_t n_reads, uint32_t L, 
             if (d_status) PG_CUDA(cudaMemsetAsync(d_status, 0, done * sizeof(int32_t), st));
         }
     }
-    if (done < n_reads) {
-        if (extra) {
-            set_error("fused sketch+gather needs the TMA fast path (k instantiated, n_local %% 32 == 0, 16-byte aligned buffers)");
-            return PG_ERR_UNSUPPORTED;
-        }
+    if (done < n_reads)  // rows the TMA fast path does not take (k not instantiated, < 32 rows left, unaligned buffers)
         return launch_fill_generic(d_bases, nullptr, L, n_reads - done, done, k, s, flags, d_out,
-                                   row_stride, nullptr, d_status, st);
-    }
+                                   row_stride, nullptr, d_status, st, extra);
     return PG_OK;
 }
 
@@ -380,11 +382,7 @@ template <int K>
 static int launch_k1r(const uint8_t *d_bases, const uint64_t *d_offsets, uint64_t n_tiles, uint32_t stride,
                       uint32_t in_cap, uint32_t *d_out, uint32_t *d_count, int32_t *d_status, cudaStream_t st) {
     const size_t smem = (size_t)in_cap + (size_t)32 * stride * 4;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(sketch_fill_ragged_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_ = func_smem((const void *)sketch_fill_ragged_kernel<K>, smem); if (rc_ != PG_OK) return rc_; }
     sketch_fill_ragged_kernel<K><<<(unsigned)n_tiles, 32, smem, st>>>(d_bases, d_offsets, d_out, stride, in_cap, d_count, d_status, 4u);
     PG_LAUNCH_CHECK("sketch_fill_ragged_kernel");
     return PG_OK;

@@ -699,11 +699,7 @@ static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets,
     const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + SELW_ROOM) + 3u) & ~3u;
     const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + 2 * SELW_STAGE_WORDS + (SEL_NBK + 1) + 16;
     const size_t smem = words * 4;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(sketch_select_walk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_ = func_smem((const void *)sketch_select_walk_kernel<K>, smem); if (rc_ != PG_OK) return rc_; }
     int per_sm = 1;
     PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_select_walk_kernel<K>, SELW_THREADS, smem));
     const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * std::max(per_sm, 1));
@@ -777,11 +773,7 @@ static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, 
     if (rc == PG_OK) {
         const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + 2 * SELM_CHUNK) + 3u) & ~3u;
         const size_t smem = ((size_t)cap + s + SEL_NBK + 64 + SEL_NBK + 1 + 8) * 4;
-        static size_t configured = 0;
-        if (smem > configured) {
-            PG_CUDA(cudaFuncSetAttribute(select_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        { const int rc_ = func_smem((const void *)select_merge_kernel, smem); if (rc_ != PG_OK) return rc_; }
         const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * 2);
         select_merge_kernel<<<(unsigned)blocks, SELM_THREADS, smem, st>>>(d_part, d_row0, n_reads, (uint32_t)s, P, cap, d_out, row_stride,
                                                                          d_count, d_status);
@@ -844,12 +836,7 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + (SEL_CHUNK + SEL_LOOKAHEAD) +
                          2 * SEL_STAGE_WORDS + (SEL_NBK + 1) + 8;
     const size_t smem = words * 4;
-    static size_t configured = 0;
-    if (smem > configured) {
-        PG_CUDA(cudaFuncSetAttribute(sketch_select_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { const int rc_ = func_smem((const void *)sketch_select_kernel, smem); if (rc_ != PG_OK) return rc_; }
     int per_sm = 1;
     PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_select_kernel, SEL_THREADS, smem));
     const uint64_t blocks = std::min<uint64_t>(n_reads, (uint64_t)sm_count() * std::max(per_sm, 1));  // one wave, grid-stride over rows

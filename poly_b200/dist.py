@@ -114,17 +114,18 @@ def sharded_sketch_distance(local_reads: torch.Tensor, plan: ShardPlan, read_len
 
 # ---- fused sketch + all-gather over NVLink peer memory ------------------------------------
 class GatheredBuffer:
-    """A cudaMalloc'ed [world*n_local, cnt] uint32 buffer on this rank, exported to / mapped from
-    every peer process through CUDA IPC handles exchanged over torch.distributed."""
+    """A cudaMalloc'ed [n_total, cnt] uint32 buffer on this rank, exported to / mapped from every
+    peer process through CUDA IPC handles exchanged over torch.distributed.  Every rank sizes its
+    buffer from plan.n_total and rank r owns rows [plan.lo, plan.hi): shards may differ in size."""
 
-    def __init__(self, n_local: int, cnt: int, plan: ShardPlan, group=None):
+    def __init__(self, plan: ShardPlan, cnt: int, group=None):
         import ctypes as C
 
         from . import _lib
 
-        self._lib, self.plan, self.n_local, self.cnt = _lib, plan, n_local, cnt
+        self._lib, self.plan, self.cnt = _lib, plan, cnt
         L = _lib.lib()
-        self.nbytes = plan.world * n_local * max(cnt, 1) * 4
+        self.nbytes = max(plan.n_total * max(cnt, 1) * 4, 16)
         p = C.c_void_p()
         _lib.check(L.pg_dev_alloc(C.byref(p), self.nbytes))
         self.ptr = p.value
@@ -148,9 +149,18 @@ class GatheredBuffer:
                 self.peer_ptrs.append(q.value)
         self._arr = (C.c_void_p * plan.world)(*self.peer_ptrs)
 
+    def as_tensor(self) -> torch.Tensor:
+        """Zero-copy int32 view [n_total, cnt] of this rank's gathered buffer."""
+        class _Iface:
+            pass
+
+        h = _Iface()
+        h.__cuda_array_interface__ = {"shape": (self.plan.n_total, max(self.cnt, 1)), "typestr": "<i4", "data": (self.ptr, False), "version": 2}
+        return torch.as_tensor(h, device=torch.device("cuda", torch.cuda.current_device()))[:, : self.cnt]
+
     def to_numpy(self) -> np.ndarray:
-        out = np.empty((self.plan.world * self.n_local, max(self.cnt, 1)), dtype=np.uint32)
-        self._lib.check(self._lib.lib().pg_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, None))
+        out = np.empty((self.plan.n_total, max(self.cnt, 1)), dtype=np.uint32)
+        self._lib.check(self._lib.lib().pg_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes, None))
         self._lib.check(self._lib.lib().pg_stream_sync(None))
         return out[:, : self.cnt]
 
@@ -165,16 +175,17 @@ class GatheredBuffer:
         L.pg_dev_free(self.ptr)
 
 
-def fused_sketch_gather(d_bases: torch.Tensor, n_local: int, read_len: int, k: int, s: int, gathered: GatheredBuffer, group=None):
-    """ONE kernel sketches the local reads and stores every finished tile into the gathered
-    buffer of every rank (TMA bulk stores to peer-mapped addresses): the all-gather overlaps
-    the hashing tile by tile.  Returns after a stream sync + barrier, i.e. when this rank's
-    gathered buffer is complete."""
+def fused_sketch_gather(d_bases: torch.Tensor, read_len: int, k: int, s: int, gathered: GatheredBuffer, group=None, sync: bool = True):
+    """ONE kernel sketches this rank's reads [plan.lo, plan.hi) and stores every finished tile / row
+    into rows [plan.lo, plan.hi) of the gathered buffer of every rank (TMA bulk stores to peer-mapped
+    addresses in the fill regime): the all-gather overlaps the hashing tile by tile.  With sync it
+    returns after a stream sync + barrier, i.e. when this rank's gathered buffer is complete."""
     from . import _lib
 
     plan = gathered.plan
-    _lib.check(_lib.lib().pg_mash_sketch_uniform_gather_dev(d_bases.data_ptr(), n_local, read_len, k, s, gathered._arr, plan.world, plan.rank,
-                                                             torch.cuda.current_stream().cuda_stream))
-    torch.cuda.synchronize()
-    if plan.world > 1:
-        dist.barrier(group=group)
+    _lib.check(_lib.lib().pg_mash_sketch_uniform_scatter_dev(d_bases.data_ptr(), plan.hi - plan.lo, read_len, k, s, gathered._arr, plan.world,
+                                                              plan.rank, plan.lo, torch.cuda.current_stream().cuda_stream))
+    if sync:
+        torch.cuda.synchronize()
+        if plan.world > 1:
+            dist.barrier(group=group)

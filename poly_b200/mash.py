@@ -192,3 +192,63 @@ def DistanceMatrix(mashes: Sequence[Mash]) -> np.ndarray:
         raise ValueError("DistanceMatrix needs one common SketchSize; use similarity_pairs for mixed sizes")
     sk = np.stack([np.ascontiguousarray(m.Sketches[:s], dtype=np.uint32) for m in mashes])
     return distance_block(sk)[1]
+
+
+# ---- single-process multi-GPU additions (pg_*_multi) ----------------------------
+def _device_list(devices):
+    if devices is None:
+        return None, 0
+    arr = np.ascontiguousarray(devices, dtype=np.int32)
+    return arr, len(arr)
+
+
+def sketch_uniform_multi(bases: np.ndarray, n_reads: int, read_len: int, k: int, s: int, devices=None, out: Optional[np.ndarray] = None) -> np.ndarray:
+    """sketch_uniform with the batch sharded over several GPUs of this process (all visible ones
+    by default): one call, no data-path collective."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8) if not hasattr(bases, "data_ptr") else bases
+    cnt = min(max(read_len - k, 0), s)
+    if out is None:
+        out = np.zeros((n_reads, max(cnt, 1)), dtype=np.uint32)
+    dev, nd = _device_list(devices)
+    rc = _lib.lib().pg_mash_sketch_uniform_multi(_lib.ptr(bases), n_reads, read_len, k, s, 0, _lib.ptr(out), max(cnt, 1), None,
+                                                 _lib.ptr(dev), nd)
+    if rc == _lib.PG_ERR_PANIC:
+        raise GoPanic("index out of range [-1]")
+    _lib.check(rc)
+    return out[:, :cnt] if isinstance(out, np.ndarray) else out
+
+
+def sketch_arrays_multi(bases: np.ndarray, offsets: np.ndarray, k: int, s: int, pad_zero: bool = False, devices=None):
+    """sketch_arrays (ragged reads) sharded over several GPUs of this process."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    lens = np.diff(offsets.astype(np.int64)) if n else np.zeros(0, np.int64)
+    maxn = int(max(int(lens.max()) - k, 0)) if n else 0
+    stride = s if pad_zero else min(maxn, s)
+    out = np.zeros((n, max(stride, 1)), dtype=np.uint32)
+    count = np.zeros(n, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    dev, nd = _device_list(devices)
+    rc = _lib.lib().pg_mash_sketch_batch_multi(bases.ctypes.data, offsets.ctypes.data, n, k, s, _lib.PG_SKETCH_PAD_ZERO if pad_zero else 0,
+                                               out.ctypes.data, max(stride, 1), count.ctypes.data, status.ctypes.data, _lib.ptr(dev), nd)
+    _lib.check(rc, allow=(_lib.PG_ERR_PANIC,))
+    return out, count, status
+
+
+def sketch_distance_multi(bases: np.ndarray, n_reads: int, read_len: int, k: int, s: int, devices=None, want_sketches: bool = True,
+                          want_same: bool = True, want_distance: bool = False):
+    """Sketch every read and compute the all-pairs matrix on several GPUs of this process: the sketch
+    kernels store their results into every device's gathered buffer (fused all-gather over peer
+    memory), device r then computes row block r.  Returns (sketches [n, s], same [n, n], distance [n, n])."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    sk = np.zeros((n_reads, s), dtype=np.uint32) if want_sketches else None
+    same = np.zeros((n_reads, n_reads), dtype=np.uint32) if want_same else None
+    dist = np.zeros((n_reads, n_reads), dtype=np.float64) if want_distance else None
+    dev, nd = _device_list(devices)
+    rc = _lib.lib().pg_mash_sketch_distance_multi(bases.ctypes.data, n_reads, read_len, k, s, _lib.ptr(dev), nd, _lib.ptr(sk), _lib.ptr(same),
+                                                  _lib.ptr(dist))
+    if rc == _lib.PG_ERR_PANIC:
+        raise GoPanic("index out of range [-1]")
+    _lib.check(rc)
+    return sk, same, dist

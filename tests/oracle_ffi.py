@@ -19,10 +19,23 @@ PO_OK, PO_PANIC, PO_UNSUPPORTED = 0, -1, -2
 
 
 def build(force: bool = False) -> str:
+    """Compile oracle/liboracle.so when missing or stale.  Several ranks of a torchrun job may get here
+    at once: the build runs under an exclusive file lock and replaces the library atomically."""
+    import fcntl
+
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mash_oracle.c", "align_primers_oracle.c", "poly_oracle.h")]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "CC=gcc"])
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("mash_oracle.c", "align_primers_oracle.c", "fasta_oracle.c", "batch_drivers.c", "poly_oracle.h")]
+
+    def stale():
+        return force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+
+    if stale():
+        with open(os.path.join(ORACLE_DIR, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if stale():  # nobody built it while we waited
+                tmp = f"liboracle.{os.getpid()}.tmp.so"
+                subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "CC=gcc", f"OUT={tmp}"])
+                os.replace(os.path.join(ORACLE_DIR, tmp), so)
     return so
 
 
@@ -64,6 +77,13 @@ def lib():
         L.po_santalucia.argtypes = [C.c_char_p, C.c_int64, C.c_double, C.c_double, C.c_double] + [C.POINTER(C.c_double)] * 3
         L.po_melting_temp.restype = C.c_int
         L.po_melting_temp.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_double)]
+        L.po_sw_score_batch.restype = C.c_int
+        L.po_sw_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int64, C.c_int, C.c_void_p, u64p]
+        L.po_melting_temp_batch.restype = C.c_int
+        L.po_melting_temp_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, u64p]
+        L.po_mash_similarity_block.restype = C.c_int
+        L.po_mash_similarity_block.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p, u64p]
         _LIB = L
     return _LIB
 
@@ -218,3 +238,32 @@ def melting_temp(seq) -> float:
     if rc != PO_OK:
         raise ValueError("unsupported input")
     return tm
+
+
+# ---- batch drivers (bench.py's CPU legs) ---------------------------------------------------------
+def sw_score_batch(queries: np.ndarray, offsets: np.ndarray, templ: np.ndarray, lut_a, lut_b, table, gap: int, nthreads: int = 1):
+    queries = np.ascontiguousarray(queries, dtype=np.uint8); offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    templ = np.ascontiguousarray(templ, dtype=np.uint8)
+    lut_a = np.ascontiguousarray(lut_a, dtype=np.int16); lut_b = np.ascontiguousarray(lut_b, dtype=np.int16)
+    table = np.ascontiguousarray(table, dtype=np.int64)
+    n = len(offsets) - 1
+    score = np.zeros(n, dtype=np.int64)
+    rc = lib().po_sw_score_batch(queries.ctypes.data, offsets.ctypes.data, n, templ.ctypes.data, len(templ), lut_a.ctypes.data, lut_b.ctypes.data,
+                                 table.ctypes.data, table.shape[1], gap, nthreads, score.ctypes.data, None)
+    return rc, score
+
+
+def melting_temp_batch(bases: np.ndarray, offsets: np.ndarray, nthreads: int = 1):
+    bases = np.ascontiguousarray(bases, dtype=np.uint8); offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    tm = np.zeros(n, dtype=np.float64)
+    rc = lib().po_melting_temp_batch(bases.ctypes.data, offsets.ctypes.data, n, nthreads, tm.ctypes.data, None)
+    return rc, tm
+
+
+def similarity_block(sk: np.ndarray, row_lo: int, row_hi: int, col_lo: int, col_hi: int, nthreads: int = 1):
+    sk = np.ascontiguousarray(sk, dtype=np.uint32)
+    n, s = sk.shape
+    same = np.zeros((row_hi - row_lo, col_hi - col_lo), dtype=np.uint32)
+    rc = lib().po_mash_similarity_block(sk.ctypes.data, n, s, row_lo, row_hi, col_lo, col_hi, nthreads, same.ctypes.data, None)
+    return rc, same

@@ -48,7 +48,7 @@ def test_sharded_pipeline_matches_oracle(pg, oracle, n, L, k, s, family):
             assert got[i - plan.lo, j] == a.SimilarityCount(b)[0]
 
 
-@pytest.mark.parametrize("n_local,L,k,s", [(64, 150, 21, 1000), (96, 151, 17, 500), (20, 3000, 21, 128)])
+@pytest.mark.parametrize("n_local,L,k,s", [(64, 150, 21, 1000), (96, 151, 17, 500), (20, 3000, 21, 128), (45, 150, 21, 1000), (33, 150, 22, 64)])
 def test_fused_sketch_gather_equals_allgather(pg, oracle, n_local, L, k, s):
     """pg_mash_sketch_uniform_gather_dev: every rank's gathered buffer == all-gather of the
     per-rank sketches == the oracle on the concatenated reads (fill regime via TMA bulk stores
@@ -56,15 +56,16 @@ def test_fused_sketch_gather_equals_allgather(pg, oracle, n_local, L, k, s):
     from poly_b200.dist import GatheredBuffer, fused_sketch_gather
 
     rank, world = pg
-    n = n_local * world
+    n = n_local * world + (world > 1)          # uneven shards when there is more than one rank
     plan = ShardPlan(n, rank, world)
     dev = torch.device("cuda", torch.cuda.current_device())
     reads_all = synth.family_reads(n, L, family=5)
     local_reads = torch.from_numpy(reads_all[plan.lo * L: plan.hi * L]).to(dev)
     cnt = min(max(L - k, 0), s)
-    buf = GatheredBuffer(n_local, cnt, plan)
-    fused_sketch_gather(local_reads, n_local, L, k, s, buf)
+    buf = GatheredBuffer(plan, cnt)
+    fused_sketch_gather(local_reads, L, k, s, buf)
     got = buf.to_numpy()
+    assert np.array_equal(buf.as_tensor().cpu().numpy().view(np.uint32), got)
     buf.close()
     rc, want = oracle.sketch_batch(reads_all, synth.uniform_offsets(n, L), k, s, variant=1)
     assert rc == 0 and np.array_equal(got, want[:, :cnt])
