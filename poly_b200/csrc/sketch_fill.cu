@@ -421,7 +421,7 @@ int launch_sketch_ragged(const uint8_t *d_bases, const uint64_t *d_offsets, uint
         if (rc != PG_OK) return rc;
         if (nmax >= (uint64_t)s && nmax > 0)  // some read may be in the select regime
             return launch_sketch_select(d_bases, d_offsets, 0, n_reads, k, s, flags, d_out, row_stride,
-                                        d_count, d_status, st);
+                                        d_count, d_status, st, nullptr, max_read_len);
     }
     return PG_OK;
 }

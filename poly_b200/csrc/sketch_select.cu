@@ -19,6 +19,7 @@
 //            bitonic sort in shared memory.
 // Nothing but the read bytes and the s output words touches HBM.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -151,14 +152,15 @@ __device__ void bitonic_sort(uint32_t *x, uint32_t P) {
 // Writes the ascending bottom-s to dst and returns true, or returns false (nothing written) if
 // the buckets up to the threshold bucket do not fit the scratch area.  All threads must call.
 template <int NT>
-__device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, uint32_t *__restrict__ dst) {
+__device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, uint32_t *__restrict__ dst,
+                                  const uint32_t bshift = SEL_BSHIFT) {
     const uint32_t tid = threadIdx.x;
     uint32_t *bstart = m.hist;  // counts, then exclusive starts; [SEL_NBK] = total
     uint32_t *tmp = m.keep;
     for (uint32_t i = tid; i <= SEL_NBK; i += NT) bstart[i] = 0;
     if (tid == 0) { m.misc[6] = 0xffffffffu; m.misc[7] = 0; }
     __syncthreads();
-    for (uint32_t i = tid; i < cnt; i += NT) atomicAdd(&bstart[m.cand[i] >> SEL_BSHIFT], 1u);
+    for (uint32_t i = tid; i < cnt; i += NT) atomicAdd(&bstart[m.cand[i] >> bshift], 1u);
     __syncthreads();
     // exclusive scan: 4 buckets per thread, warp scan, then the 16 warp totals
     constexpr int PER = SEL_NBK / NT;
@@ -194,13 +196,13 @@ __device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, ui
     for (uint32_t i = tid; i <= bt; i += NT) cursor[i] = 0;
     __syncthreads();
     for (uint32_t i = tid; i < cnt; i += NT) {
-        const uint32_t e = m.cand[i], b = e >> SEL_BSHIFT;
+        const uint32_t e = m.cand[i], b = e >> bshift;
         if (b <= bt) tmp[bstart[b] + atomicAdd(&cursor[b], 1u)] = e;
     }
     __syncthreads();
     // rank inside the bucket -> final position (ties keep distinct slots via the index tie-break)
     for (uint32_t p = tid; p < need; p += NT) {
-        const uint32_t e = tmp[p], b = e >> SEL_BSHIFT;
+        const uint32_t e = tmp[p], b = e >> bshift;
         const uint32_t lo = bstart[b], hi = bstart[b + 1];
         uint32_t r = 0;
         for (uint32_t q = lo; q < hi; ++q) {
@@ -408,7 +410,8 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
                           uint32_t *__restrict__ out, uint64_t row_stride, uint32_t *__restrict__ count,
                           int32_t *__restrict__ status, const SketchDst extra, uint32_t lut_stride,
                           const uint64_t *__restrict__ slice_beg, const uint32_t *__restrict__ slice_n,
-                          unsigned long long *__restrict__ next_row) {
+                          unsigned long long *__restrict__ next_row, const uint32_t *__restrict__ row_list,
+                          const uint32_t *__restrict__ n_list) {
     constexpr int NB = K / 4;
     constexpr int TAIL = K % 4;
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
@@ -451,8 +454,12 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     for (;;) {
         if (tid == 0) s_row = atomicAdd(next_row, 1ull);
         __syncthreads();
-        const uint64_t row = s_row;
+        uint64_t row = s_row;
         __syncthreads();
+        if (row_list) {  // only the listed rows (the threshold path's retries); the list length lives on the device
+            if (row >= *n_list) break;
+            row = row_list[row];
+        }
         if (row >= n_reads) break;
         uint64_t beg, n;
         if (slice_beg) {  // `row` is a slice of a long sequence: k-mer positions [beg, beg + n)
@@ -691,11 +698,263 @@ select_merge_kernel(const uint32_t *__restrict__ part, const uint32_t *__restric
     }
 }
 
+// ---- K2t: the select regime by a value threshold -------------------------------------------------
+// The bottom-s multiset of n hashes is contained in {h < T} as soon as that set has >= s members.  For
+// hash values that behave like uniform draws (murmur3 of distinct k-mers) T = mu/n * 2^32 with
+// mu = s + 8 sqrt(s) + 64 admits mu hashes on average and fewer than s only 8 standard deviations below
+// the mean -- and whether it did is CHECKED, never assumed: a row whose admitted count is < s (few
+// distinct k-mers) or exceeds its buffer (heavy duplication below T) is redone by the exact streaming
+// kernel above (retry list built on the device, no host round trip).  So:
+//   A. sketch_thresh_walk_kernel<K>: one WARP per work item (<= 8 chunks of 32 x 68 positions of one
+//      row; long sequences become many items, so there is no host-side slicing and no merge pass).
+//      Chunks arrive by double-buffered 1-D TMA bulk copies; lane l walks 68 consecutive k-mers with
+//      the register ring of kmer_walk.cuh (lanes read 17 words apart: bank-conflict free; one ring
+//      prologue per 68 k-mers instead of per 20) and drops the hashes below T into its private strip
+//      column -- a compare, a predicated store and a predicated add: no vote, no atomic, no barrier.
+//      After the chunk the strips are compacted row by row with ballots into the row's candidate list
+//      in global memory (one global atomic per warp-chunk reserves the space; coalesced stores).
+//   B. sketch_thresh_select_kernel: one CTA per row loads the ~mu candidates and runs the exact
+//      bucket sort-select (ties counted) -> ascending bottom-s, stored to every destination.
+// Extra HBM traffic: mu words per row written and read once (cfg3: 2 x 1 GB next to 1.8 GB algorithmic).
+constexpr int SELT_SEG = 68;
+constexpr int SELT_CHUNK = 32 * SELT_SEG;  // 2176 k-mer positions per warp chunk
+constexpr int SELT_ITEM_CHUNKS = 8;
+constexpr int SELT_STAGE_BYTES = (15 + SELT_CHUNK + 32 + 48 + 15) / 16 * 16;  // head + chunk + k + over-read pad
+constexpr int SELT_SEL_THREADS = 256;
+static_assert(SELT_SEG % 4 == 0 && (SELT_SEG / 4) % 2 == 1, "whole word steps, odd word distance between lanes");
+
+__device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
+    if ((uint64_t)mu >= n) return 0xffffffffu;  // every hash is a candidate
+    const uint64_t t = ((uint64_t)mu << 32) / n;
+    return t ? (uint32_t)(t - 1) : 0u;
+}
+
+#define PG_EMIT_STRIP(R_, H_) \
+    if ((H_) <= tm1) { my_strip[c * 32u] = (H_); ++c; }
+
+template <int K>
+__global__ void __launch_bounds__(32)
+sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets, uint32_t uniform_len,
+                          uint64_t row0, uint64_t n_rows, uint32_t items_per_row, uint32_t s, uint32_t mu, uint32_t cap,
+                          uint32_t *__restrict__ gcand, uint32_t *__restrict__ gcnt, uint32_t lut_stride) {
+    constexpr int NB = K / 4;
+    constexpr int TAIL = K % 4;
+    constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
+    constexpr bool LUT = TAIL == 1;
+    constexpr uint32_t k = K;
+    static_assert(NB >= 1 && K <= 32, "walk path: 4 <= k <= 32");
+
+    extern __shared__ __align__(128) uint8_t smem[];  // 2 stage buffers | strip [SELT_SEG][32]
+    __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
+    __shared__ __align__(8) uint64_t s_bar[3];
+    const uint32_t lane = threadIdx.x;
+    const uint64_t item = blockIdx.x;
+    const uint64_t lrow = item / items_per_row;  // row within this launch group
+    if (lrow >= n_rows) return;
+    const uint64_t row = row0 + lrow;
+    uint64_t beg, len;
+    if (offsets) {
+        beg = offsets[row];
+        len = offsets[row + 1] - beg;
+    } else {
+        beg = row * (uint64_t)uniform_len;
+        len = uniform_len;
+    }
+    const uint64_t n = len > k ? len - k : 0;
+    if (n < s || n == 0) return;  // fill regime: other kernel
+    const uint64_t p0 = (item % items_per_row) * (uint64_t)(SELT_ITEM_CHUNKS * SELT_CHUNK);
+    if (p0 >= n) return;
+    const uint64_t p1 = min(n, p0 + (uint64_t)(SELT_ITEM_CHUNKS * SELT_CHUNK));
+    const uint8_t *seq = bases + beg;
+    const uint32_t tm1 = selt_threshold_m1(n, mu);
+    uint32_t *my_cand = gcand + lrow * (uint64_t)cap;
+    uint32_t *strip = reinterpret_cast<uint32_t *>(smem + 2 * SELT_STAGE_BYTES);
+    uint32_t *my_strip = strip + lane;
+
+    if (lane == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
+        fence_mbar_init();
+        if (LUT) {
+            mbar_expect_tx(&s_bar[2], 1024u);
+            bulk_g2s(s_lut, &g_kmix_byte, 1024u, &s_bar[2]);
+        }
+    }
+    __syncwarp();
+    const uint32_t lut_base = smem_u32(s_lut);
+
+    // A chunk that is not the last of its row may over-read up to 15 bytes (they belong to the same
+    // sequence): the whole stage is then one TMA copy.  Otherwise the 16-byte aligned body comes by
+    // TMA and the tail by plain loads.
+    auto tail_by_tma = [&](uint64_t c0, uint32_t ch) { return n - (c0 + ch) >= 16; };
+    auto issue_stage = [&](uint64_t c0, uint32_t buf) {
+        const uint32_t ch = (uint32_t)min((uint64_t)SELT_CHUNK, p1 - c0);
+        const uint32_t nbytes = ch + k;
+        const uint8_t *src = seq + c0;
+        const uint32_t head = (uint32_t)((uintptr_t)src & 15u);
+        const bool all_tma = tail_by_tma(c0, ch);
+        const uint32_t body = all_tma ? (head + nbytes + 15u) & ~15u : (head + nbytes) & ~15u;
+        uint8_t *sb8 = smem + buf * SELT_STAGE_BYTES;
+        if (lane == 0) {
+            mbar_expect_tx(&s_bar[buf], body);
+            if (body) bulk_g2s(sb8, src - head, body, &s_bar[buf]);
+        }
+        if (!all_tma)
+            for (uint32_t i = body + lane; i < head + nbytes + 32; i += 32)  // tail + over-read pad
+                sb8[i] = i < head + nbytes ? __ldg(src - head + i) : (uint8_t)0;
+    };
+    issue_stage(p0, 0);
+    if (LUT) mbar_wait(&s_bar[2], 0);
+    uint32_t par0 = 0u, par1 = 0u, chunk_idx = 0;
+    for (uint64_t c0 = p0; c0 < p1; c0 += SELT_CHUNK, ++chunk_idx) {
+        const uint32_t ch = (uint32_t)min((uint64_t)SELT_CHUNK, p1 - c0);
+        const uint32_t buf = chunk_idx & 1u;
+        __syncwarp();  // every lane is done with the other buffer (chunk c-1) before it is refilled
+        if (c0 + SELT_CHUNK < p1) issue_stage(c0 + SELT_CHUNK, buf ^ 1u);
+        const uint32_t head = (uint32_t)((uintptr_t)(seq + c0) & 15u);
+        const uint8_t *stage = smem + buf * SELT_STAGE_BYTES;
+        if (buf == 0) { mbar_wait(&s_bar[0], par0); par0 ^= 1u; }
+        else          { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
+        if (!tail_by_tma(c0, ch)) __syncwarp();  // plain-store part of this stage
+
+        uint32_t c = 0;  // hashes this lane admitted in this chunk
+        const uint32_t seg = lane * SELT_SEG;
+        if (seg < ch) {
+            const uint32_t nk = min((uint32_t)SELT_SEG, ch - seg);
+            const uint32_t b0 = head + seg;
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (b0 >> 2);
+            const uint8_t *sb = stage + b0 + 4 * NB;
+            const uint32_t sh = (b0 & 3u) * 8u;
+            uint32_t raw_a = sw[0], raw_b = sw[1];
+            uint32_t w_cur = __funnelshift_r(raw_a, raw_b, sh);
+            raw_a = raw_b; raw_b = sw[2];
+            uint32_t w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+            raw_a = raw_b; raw_b = sw[3];
+            const uint32_t *swp = sw + 4;
+            uint32_t ring[4][NB];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                ring[0][q] = mm3_kmix(w_cur);
+                ring[1][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 8));
+                ring[2][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 16));
+                ring[3][q] = mm3_kmix(__funnelshift_r(w_cur, w_nxt, 24));
+                w_cur = w_nxt;
+                w_nxt = __funnelshift_r(raw_a, raw_b, sh);
+                raw_a = raw_b;
+                raw_b = *swp++;
+            }
+            uint32_t i = 0;
+            if (nk == SELT_SEG) {
+#pragma unroll
+                for (int q = 0; q < SELT_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, PG_EMIT_STRIP)
+            } else {
+#pragma unroll 1
+                for (int q0 = 0; q0 < SELT_SEG / 4; q0 += NB) {
+#pragma unroll
+                    for (int u = 0; u < NB; ++u) {
+                        if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_STRIP)
+                    }
+                }
+            }
+        }
+        // flush: compact the strip columns into the row's candidate list (order is irrelevant: a multiset)
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += y;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&gcnt[lrow], tot);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((uint64_t)base + tot <= cap) {  // otherwise the count alone tells stage B that the row overflowed
+                const uint32_t maxc = __reduce_max_sync(0xffffffffu, c);
+                const uint32_t below = (1u << lane) - 1u;
+                uint32_t off = base;
+                for (uint32_t j = 0; j < maxc; ++j) {
+                    const bool v = j < c;
+                    const uint32_t b = __ballot_sync(0xffffffffu, v);
+                    if (v) my_cand[off + __popc(b & below)] = my_strip[j * 32u];
+                    off += __popc(b);
+                }
+            }
+        }
+    }
+}
+#undef PG_EMIT_STRIP
+
+// Stage B: exact bottom-s of the admitted candidates of one row (cnt <= cap by construction; rows whose
+// count is < s or > cap go onto the retry list).
+__global__ void __launch_bounds__(SELT_SEL_THREADS)
+sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint64_t *__restrict__ offsets, uint32_t uniform_len,
+                            uint64_t row0, uint64_t n_rows, uint32_t k, uint32_t s, uint32_t P, uint32_t mu, uint32_t cap,
+                            const uint32_t *__restrict__ gcand, const uint32_t *__restrict__ gcnt, uint32_t *__restrict__ out,
+                            uint64_t row_stride, uint32_t *__restrict__ count, int32_t *__restrict__ status, const SketchDst extra,
+                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry) {
+    extern __shared__ __align__(16) uint32_t smem_w[];
+    SelSmem m;
+    m.cand = smem_w;                                 // [max(cap, P)]
+    m.keep = m.cand + ((max(cap, P) + 3u) & ~3u);    // scratch of the final stage: s + ties + one cursor per bucket
+    m.kv = nullptr;
+    m.bytes = nullptr;
+    m.hist = m.keep + s + SEL_NBK + 64;
+    m.misc = m.hist + SEL_NBK + 1;
+    m.tmpcap = (uint32_t)(m.hist - m.keep);
+    const uint32_t tid = threadIdx.x;
+    for (uint64_t lrow = blockIdx.x; lrow < n_rows; lrow += gridDim.x) {
+        const uint64_t row = row0 + lrow;
+        uint64_t len;
+        if (offsets) len = offsets[row + 1] - offsets[row];
+        else len = uniform_len;
+        const uint64_t n = len > k ? len - k : 0;
+        if (n < s || n == 0) continue;  // fill regime: other kernel
+        const uint32_t cnt = gcnt[lrow];
+        if (cnt < s || cnt > cap) {  // the estimate did not hold for this row: exact streaming kernel redoes it
+            if (tid == 0) retry_rows[atomicAdd(n_retry, 1u)] = (uint32_t)row;
+            continue;
+        }
+        const uint32_t *src = gcand + lrow * (uint64_t)cap;
+        for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) m.cand[i] = __ldg(src + i);
+        __syncthreads();
+        uint32_t *dst = out + row * row_stride;
+        // candidates are < T: spread them over the 2048 value buckets of the final stage
+        const uint32_t tm1 = selt_threshold_m1(n, mu);
+        const uint32_t bits = 32u - __clz(tm1 | 1u);
+        const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
+        if (!final_bucket_sort<SELT_SEL_THREADS>(m, cnt, s, dst, bshift)) {
+            if (cnt > s) prune_to_s<SELT_SEL_THREADS>(m, cnt, s);
+            for (uint32_t i = s + tid; i < P; i += SELT_SEL_THREADS) m.cand[i] = 0xffffffffu;
+            __syncthreads();
+            bitonic_sort<SELT_SEL_THREADS>(m.cand, P);
+            for (uint32_t i = tid; i < s; i += SELT_SEL_THREADS) dst[i] = m.cand[i];
+        }
+        if (extra.n > 0) {  // fused all-gather: replicate the finished row into every rank's buffer
+            __syncthreads();
+#pragma unroll
+            for (int pr = 0; pr < PG_MAX_PEERS; ++pr) {
+                if (pr >= extra.n) continue;
+                uint32_t *peer = extra.ptr[pr] + row * row_stride;
+                if (peer == dst) continue;
+                for (uint32_t i = tid; i < s; i += SELT_SEL_THREADS) peer[i] = dst[i];
+            }
+        }
+        if (tid == 0) {
+            if (status) status[row] = PG_ITEM_OK;
+            if (count) count[row] = s;
+        }
+        __syncthreads();
+    }
+}
+
 template <int K>
 static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
                               uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
                               cudaStream_t st, const SketchDst &ex, const uint64_t *d_slice_beg = nullptr,
-                              const uint32_t *d_slice_n = nullptr) {
+                              const uint32_t *d_slice_n = nullptr, const uint32_t *d_row_list = nullptr,
+                              const uint32_t *d_n_list = nullptr) {
     const uint32_t cap = (std::max<uint32_t>(P, (uint32_t)s + SELW_ROOM) + 3u) & ~3u;
     const size_t words = (size_t)cap + (((size_t)s + 3) & ~(size_t)3) + 4 + 2 * SELW_STAGE_WORDS + (SEL_NBK + 1) + 16;
     const size_t smem = words * 4;
@@ -709,7 +968,7 @@ static int launch_select_walk(const uint8_t *d_bases, const uint64_t *d_offsets,
     PG_CUDA(cudaMemsetAsync(d_next, 0, 8, st));
     sketch_select_walk_kernel<K><<<(unsigned)blocks, SELW_THREADS, smem, st>>>(d_bases, d_offsets, read_len, n_reads, (uint32_t)s, P, cap,
                                                                               d_out, row_stride, d_count, d_status, ex, 4u, d_slice_beg,
-                                                                              d_slice_n, d_next);
+                                                                              d_slice_n, d_next, d_row_list, d_n_list);
     PG_LAUNCH_CHECK("sketch_select_walk_kernel");
     return PG_OK;
 }
@@ -785,11 +1044,75 @@ static int try_select_sliced(const uint8_t *d_bases, const uint64_t *d_offsets, 
     return rc;
 }
 
+// K2t launcher.  *handled = false: not applicable (the caller takes the streaming path).
 template <int K>
-static int launch_select_auto(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int s,
+static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t max_read_len,
+                                uint64_t n_reads, int s, uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count,
+                                int32_t *d_status, cudaStream_t st, const SketchDst &ex, bool *handled) {
+    *handled = false;
+    const uint64_t len_max = d_offsets ? max_read_len : read_len;
+    if (s < 2 || len_max <= (uint64_t)K || n_reads > 0xffffffffull) return PG_OK;  // s == 1 needs the positional panic rule
+    const uint64_t nmax = len_max - K;
+    const uint64_t item_len = (uint64_t)SELT_ITEM_CHUNKS * SELT_CHUNK;
+    const uint64_t ipr = (nmax + item_len - 1) / item_len;
+    if (ipr > 0xffffffffull) return PG_OK;
+    // ragged batches map items as row x ipr (rows shorter than the longest leave empty items): bounded waste only
+    if (d_offsets && ipr > 1 && n_reads * ipr > (4ull << 20)) return PG_OK;
+    const uint32_t mu = (uint32_t)s + 8u * (uint32_t)ceil(sqrt((double)s)) + 64u;
+    uint32_t cap = mu + 8u * (uint32_t)ceil(sqrt((double)mu)) + 96u;
+    cap = (cap + 3u) & ~3u;
+    const size_t smem_a = 2 * (size_t)SELT_STAGE_BYTES + (size_t)SELT_SEG * 32 * 4;
+    const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + (size_t)s + 2 * SEL_NBK + 64 + 1 + 16;
+    const size_t smem_b = words_b * 4;
+    if (smem_b > 220 * 1024) return PG_OK;
+    { const int rc_ = func_smem((const void *)sketch_thresh_walk_kernel<K>, smem_a); if (rc_ != PG_OK) return rc_; }
+    { const int rc_ = func_smem((const void *)sketch_thresh_select_kernel, smem_b); if (rc_ != PG_OK) return rc_; }
+    int per_sm = 1;
+    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_thresh_select_kernel, SELT_SEL_THREADS, smem_b));
+    // candidate lists: cap words per row, rows in groups of <= 1.5 GiB of temporaries
+    uint64_t rows_per_group = std::max<uint64_t>(1, std::min<uint64_t>((3ull << 28) / cap, 0x7fffffffull / ipr));
+    if (const char *e = getenv("PG_K2T_GROUP_ROWS"))  // test knob: force several launch groups
+        if (atoll(e) > 0) rows_per_group = std::min<uint64_t>(rows_per_group, (uint64_t)atoll(e));
+    const uint64_t group = std::min(n_reads, rows_per_group);
+    StreamScratch tmp(st);
+    uint32_t *d_cand = nullptr, *d_cnt = nullptr, *d_retry = nullptr, *d_nretry = nullptr;
+    PG_CUDA(tmp.alloc(&d_cand, group * cap));
+    PG_CUDA(tmp.alloc(&d_cnt, group));
+    PG_CUDA(tmp.alloc(&d_retry, n_reads));
+    PG_CUDA(tmp.alloc(&d_nretry, 1));
+    PG_CUDA(cudaMemsetAsync(d_nretry, 0, 4, st));
+    for (uint64_t r0 = 0; r0 < n_reads; r0 += group) {
+        const uint64_t rows = std::min(group, n_reads - r0);
+        PG_CUDA(cudaMemsetAsync(d_cnt, 0, rows * 4, st));
+        sketch_thresh_walk_kernel<K><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)ipr,
+                                                                                 (uint32_t)s, mu, cap, d_cand, d_cnt, 4u);
+        PG_LAUNCH_CHECK("sketch_thresh_walk_kernel");
+        const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
+        sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)K,
+                                                                                         (uint32_t)s, P, mu, cap, d_cand, d_cnt, d_out, row_stride,
+                                                                                         d_count, d_status, ex, d_retry, d_nretry);
+        PG_LAUNCH_CHECK("sketch_thresh_select_kernel");
+    }
+    // rows the estimate failed on (few distinct k-mers, heavy duplication): exact streaming kernel, device-side list
+    int rc = launch_select_walk<K>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex, nullptr, nullptr,
+                                   d_retry, d_nretry);
+    if (rc != PG_OK) return rc;
+    *handled = true;
+    return PG_OK;
+}
+
+template <int K>
+static int launch_select_auto(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t max_read_len, uint64_t n_reads, int s,
                               uint32_t P, uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
                               cudaStream_t st, const SketchDst &ex) {
     static const bool no_slices = [] { const char *e = getenv("PG_K2_NO_SLICES"); return e && atoi(e) != 0; }();
+    static const bool no_thresh = [] { const char *e = getenv("PG_K2_NO_THRESH"); return e && atoi(e) != 0; }();  // A/B knob
+    if (!no_thresh) {
+        bool handled = false;
+        const int rc = launch_select_thresh<K>(d_bases, d_offsets, read_len, max_read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st,
+                                               ex, &handled);
+        if (rc != PG_OK || handled) return rc;
+    }
     if (ex.n == 0 && !no_slices) {
         bool sliced = false;
         const int rc = try_select_sliced<K>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, &sliced);
@@ -803,7 +1126,7 @@ static int launch_select_auto(const uint8_t *d_bases, const uint64_t *d_offsets,
 int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len,
                          uint64_t n_reads, int k, int s, uint32_t flags, uint32_t *d_out,
                          uint64_t row_stride, uint32_t *d_count, int32_t *d_status,
-                         cudaStream_t st, const SketchDst *extra) {
+                         cudaStream_t st, const SketchDst *extra, uint64_t max_read_len) {
     if (n_reads == 0) return PG_OK;
     SketchDst ex;
     ex.n = 0;
@@ -824,7 +1147,7 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     if (!force_generic && (size_t)s * 8 + 56 * 1024 <= 227 * 1024) {  // shared memory of the walk kernel
         switch (k) {
 #define PG_K2W_CASE(KK) \
-    case KK: return launch_select_auto<KK>(d_bases, d_offsets, read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex);
+    case KK: return launch_select_auto<KK>(d_bases, d_offsets, read_len, max_read_len, n_reads, s, P, d_out, row_stride, d_count, d_status, st, ex);
             PG_K2W_CASE(11) PG_K2W_CASE(13) PG_K2W_CASE(15) PG_K2W_CASE(16) PG_K2W_CASE(17) PG_K2W_CASE(19)
             PG_K2W_CASE(21) PG_K2W_CASE(23) PG_K2W_CASE(24) PG_K2W_CASE(25) PG_K2W_CASE(27) PG_K2W_CASE(29)
             PG_K2W_CASE(31) PG_K2W_CASE(32)

@@ -426,3 +426,31 @@ def test_ragged_fast_path(gpu, oracle, k):
         assert rc == 0 and not status.any()
         assert np.array_equal(count, np.minimum(np.maximum(lens - k, 0), s if not pad else 256))
         assert np.array_equal(out, want[:, : out.shape[1]]), (k, pad)
+
+
+def test_select_threshold_path(gpu, oracle, monkeypatch):
+    """K2t (value-threshold walk + exact select): rows of one and of several work items, several launch
+    groups, and rows on which the estimate must fail -- homopolymers / short repeats (fewer than s
+    distinct hashes below the threshold, or far more than the buffer holds) -- which the device-side
+    retry list hands to the exact streaming kernel.  Everything bit-exact against the oracle."""
+    rng = np.random.default_rng(77)
+    monkeypatch.setenv("PG_K2T_GROUP_ROWS", "7")
+    for k, s, L, n in [(21, 1000, 40_000, 20), (31, 2000, 10_000, 40), (16, 64, 5_000, 33), (21, 1000, 1021 + 21, 9), (21, 1000, 1300, 9),
+                       (24, 5000, 30_000, 5), (32, 3, 9_000, 12), (11, 500, 2176 * 8 + 11 + 1, 6)]:
+        reads = rng.choice(list(b"ACGT"), size=n * L).astype(np.uint8).reshape(n, L)
+        reads[1] = ord("A")                                                   # homopolymer: one distinct hash
+        reads[2] = np.frombuffer((b"ACG" * (L // 3 + 1))[:L], dtype=np.uint8)  # period 3: three distinct hashes
+        reads[3] = rng.choice(list(b"AC"), size=L).astype(np.uint8)           # low complexity
+        reads[4, : L // 2] = reads[4, L // 2: 2 * (L // 2)]                    # every k-mer of one half twice
+        got = mash.sketch_uniform(reads.reshape(-1), n, L, k, s)
+        rc, want = oracle.sketch_batch(reads.reshape(-1), synth.uniform_offsets(n, L), k, s, variant=1)
+        assert rc == 0
+        cnt = min(L - k, s)
+        assert np.array_equal(got, want[:, :cnt]), (k, s, L, n, [i for i in range(n) if not np.array_equal(got[i], want[i, :cnt])])
+    # ragged batch whose longest read spans several items: row x item mapping with empty items
+    lens = [int(x) for x in rng.integers(1200, 50_000, 30)] + [0, 5, 1021, 1022, 1023]
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=l).astype(np.uint8)) for l in lens] + [b"T" * 30_000]
+    bases, offsets = mash.flatten(seqs)
+    out, count, status = mash.sketch_arrays(bases, offsets, 21, 1000, pad_zero=True)
+    rc, want = oracle.sketch_batch(bases, offsets, 21, 1000, variant=1)
+    assert rc == 0 and not status.any() and np.array_equal(out, want)
