@@ -1142,6 +1142,10 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     uint32_t P = 1;
     while (P < (uint32_t)std::max(s, 1)) P <<= 1;
     if (P < 2) P = 2;
+    // rows wider than s: the header promises zeros in [count, row_stride) -- the select kernels write
+    // exactly s words, so clear the tail columns first (fill-regime rows of a ragged batch zero their own)
+    if (row_stride > (uint64_t)s)
+        PG_CUDA(cudaMemset2DAsync(d_out + s, row_stride * 4, 0, (row_stride - (uint64_t)s) * 4, n_reads, st));
     // K2w (register-ring walk) for the instantiated k; PG_K2_GENERIC=1 forces the generic kernel (A/B knob)
     static const bool force_generic = [] { const char *e = getenv("PG_K2_GENERIC"); return e && atoi(e) != 0; }();
     if (!force_generic && (size_t)s * 8 + 56 * 1024 <= 227 * 1024) {  // shared memory of the walk kernel

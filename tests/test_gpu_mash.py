@@ -454,3 +454,20 @@ def test_select_threshold_path(gpu, oracle, monkeypatch):
     out, count, status = mash.sketch_arrays(bases, offsets, 21, 1000, pad_zero=True)
     rc, want = oracle.sketch_batch(bases, offsets, 21, 1000, variant=1)
     assert rc == 0 and not status.any() and np.array_equal(out, want)
+
+
+def test_select_rows_wider_than_s_are_zero_filled(gpu, oracle):
+    """include/poly_b200.h: words [count, row_stride) of every row are zeros -- also in the select regime
+    and for device-pointer callers that hand in a dirty buffer."""
+    import torch
+
+    n, L, k, s, stride = 40, 3000, 21, 100, 131
+    reads = synth.independent_reads(n, L)
+    dev = torch.device("cuda", 0)
+    d_in = torch.from_numpy(reads).to(dev)
+    d_out = torch.full((n, stride), -1, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gpu.check(gpu.lib().pg_mash_sketch_uniform_dev(d_in.data_ptr(), n, L, k, s, 0, d_out.data_ptr(), stride, None, st))
+    got = d_out.cpu().numpy().view(np.uint32)
+    rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=1)
+    assert rc == 0 and np.array_equal(got[:, :s], want) and not got[:, s:].any()
