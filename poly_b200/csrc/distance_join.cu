@@ -24,7 +24,8 @@ namespace pg {
 
 namespace {
 
-constexpr int JOIN_CAP = 8192;      // entries a bucket CTA can hold (64 KB of keys)
+constexpr int JOIN_CAP = 4096;      // entries a bucket CTA can hold (32 KB of keys + 24 KB of run tables)
+constexpr int JOIN_SMEM = JOIN_CAP * (8 + 3 * 2);
 constexpr int JOIN_THREADS = 256;
 
 __device__ __forceinline__ uint32_t bucket_of(uint32_t v, uint64_t scale /* = B * 2^32 / (vmax+1) */) {
@@ -96,10 +97,20 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ sk, uint64_t total, 
     }
 }
 
+// One CTA per value bucket: sort the bucket's (value, id) keys, then every value run of g >= 2 distinct
+// ids contributes min(c_a, c_b) to same[a][b] for its ordered pairs a != b (the diagonal is s for every
+// ascending sketch and is written by diag_kernel).  Emission is warp-cooperative: for one row a the lanes
+// run ALONG the run, i.e. along row a of the matrix, so the reductions of one instruction fall into
+// neighbouring words (ids of a run are ascending; related sketches tend to have neighbouring ids) and
+// coalesce into few L2 transactions instead of 32.
 __global__ void __launch_bounds__(JOIN_THREADS)
 bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restrict__ start, uint32_t nbuckets,
                    uint64_t n, uint64_t row_begin, uint64_t row_end, uint32_t *__restrict__ same) {
-    extern __shared__ __align__(16) uint64_t key[];  // [JOIN_CAP]
+    extern __shared__ __align__(16) uint64_t key[];                  // [JOIN_CAP] sorted (value << 32 | id)
+    uint16_t *rs = reinterpret_cast<uint16_t *>(key + JOIN_CAP);     // [JOIN_CAP] first position of my value run
+    uint16_t *re = rs + JOIN_CAP;                                    // [JOIN_CAP] one past its last position
+    uint16_t *mult = re + JOIN_CAP;                                  // [JOIN_CAP] multiplicity at a (value, id) head, 0 elsewhere
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t b = blockIdx.x; b < nbuckets; b += gridDim.x) {
         const uint64_t lo = start[b];
         const uint32_t m = (uint32_t)(start[b + 1] - lo);
@@ -119,30 +130,51 @@ bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restr
                 __syncthreads();
             }
         }
-        // entry i heads a (value, id) group if it differs from its predecessor; its multiplicity is
-        // the group length.  Each group head a adds min(c_a, c_b) to same[a][b] for every group b of
-        // the same value (including itself: the diagonal gets c_a).
+        // run bounds and (value, id) multiplicities: the thread at the first position of a value run walks it
         for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) {
-            const uint64_t ka = key[i];
-            if (i > 0 && key[i - 1] == ka) continue;
-            const uint32_t ida = (uint32_t)ka, va = (uint32_t)(ka >> 32);
-            if (ida < row_begin || ida >= row_end) continue;
-            uint32_t ca = 1;
-            while (i + ca < m && key[i + ca] == ka) ++ca;
-            // walk left to the start of the value run, then right over the whole run
-            uint32_t j = i;
-            while (j > 0 && (uint32_t)(key[j - 1] >> 32) == va) --j;
-            uint32_t *row = same + (ida - row_begin) * n;
-            while (j < m && (uint32_t)(key[j] >> 32) == va) {
-                const uint64_t kb = key[j];
-                uint32_t cb = 1;
-                while (j + cb < m && key[j + cb] == kb) ++cb;
-                atomicAdd(row + (uint32_t)kb, min(ca, cb));
-                j += cb;
+            const uint32_t v = (uint32_t)(key[i] >> 32);
+            if (i > 0 && (uint32_t)(key[i - 1] >> 32) == v) continue;
+            uint32_t e = i + 1;
+            while (e < m && (uint32_t)(key[e] >> 32) == v) ++e;
+            uint32_t head = i;
+            for (uint32_t j = i; j < e; ++j) {
+                rs[j] = (uint16_t)i;
+                re[j] = (uint16_t)e;
+                if (j > i && key[j] == key[j - 1]) { mult[j] = 0; ++mult[head]; }
+                else { head = j; mult[j] = 1; }
+            }
+        }
+        __syncthreads();
+        // emission: 32 positions per warp step; those that head a (value, id) group of the row block inside a
+        // run with other members are served one after the other by the whole warp
+        for (uint32_t a0 = warp * 32u; a0 < m; a0 += (JOIN_THREADS / 32) * 32u) {
+            const uint32_t a = a0 + lane;
+            bool mine = false;
+            if (a < m && mult[a] != 0) {
+                const uint32_t ida = (uint32_t)key[a];
+                mine = ida >= row_begin && ida < row_end && (uint32_t)(re[a] - rs[a]) > mult[a];  // anybody else in the run?
+            }
+            uint32_t todo = __ballot_sync(0xffffffffu, mine);
+            while (todo) {
+                const uint32_t src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t pa = a0 + src;
+                const uint32_t ca = mult[pa], r0 = rs[pa], r1 = re[pa];
+                uint32_t *row = same + ((uint32_t)key[pa] - row_begin) * n;
+                for (uint32_t j = r0 + lane; j < r1; j += 32) {
+                    const uint32_t cb = mult[j];
+                    if (cb != 0 && (j < pa || j >= pa + ca)) atomicAdd(row + (uint32_t)key[j], min(ca, cb));
+                }
             }
         }
         __syncthreads();
     }
+}
+
+// same[a][a] = s: the walk of a sketch against itself matches every element (ascending sketches only)
+__global__ void diag_kernel(uint32_t *__restrict__ same, uint64_t n, uint64_t row_begin, uint64_t row_end, uint32_t s) {
+    for (uint64_t r = row_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < row_end; r += (uint64_t)gridDim.x * blockDim.x)
+        same[(r - row_begin) * n + r] = s;
 }
 
 __global__ void same_to_distance_kernel(const uint32_t *__restrict__ same, uint64_t count, uint32_t s,
@@ -211,10 +243,12 @@ int join_emit(const JoinIndex &ix, uint64_t row_begin, uint64_t row_end, uint32_
     const uint64_t rows = row_end - row_begin;
     const unsigned sms = (unsigned)sm_count();
     PG_CUDA(cudaMemsetAsync(d_same, 0, rows * ix.n * 4, st));
-    { const int rc_ = func_smem((const void *)bucket_join_kernel, JOIN_CAP * 8); if (rc_ != PG_OK) return rc_; }
-    bucket_join_kernel<<<(unsigned)std::min<uint64_t>(ix.nb, (uint64_t)sms * 12), JOIN_THREADS, JOIN_CAP * 8, st>>>(
+    { const int rc_ = func_smem((const void *)bucket_join_kernel, JOIN_SMEM); if (rc_ != PG_OK) return rc_; }
+    bucket_join_kernel<<<(unsigned)std::min<uint64_t>(ix.nb, (uint64_t)sms * 16), JOIN_THREADS, JOIN_SMEM, st>>>(
         ix.entries, ix.start, (uint32_t)ix.nb, ix.n, row_begin, row_end, d_same);
     PG_LAUNCH_CHECK("bucket_join_kernel");
+    diag_kernel<<<(unsigned)std::min<uint64_t>((rows + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(d_same, ix.n, row_begin, row_end, (uint32_t)ix.s);
+    PG_LAUNCH_CHECK("diag_kernel");
     if (d_dist) {
         same_to_distance_kernel<<<sms * 8, 256, 0, st>>>(d_same, rows * ix.n, (uint32_t)ix.s, d_dist);
         PG_LAUNCH_CHECK("same_to_distance_kernel");
