@@ -15,11 +15,20 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"runtime"
 	"unsafe"
 )
 
 // ErrPanic is returned where the pure-Go reference would panic (index out of range).
 var ErrPanic = errors.New("poly: reference panics on this input (index out of range)")
+
+// locked runs one C ABI call with the goroutine pinned to its OS thread, so that pg_last_error()
+// (a thread-local string) is read on the thread that produced it.
+func locked(call func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	return check(call())
+}
 
 func check(rc C.int) error {
 	switch rc {
@@ -58,10 +67,51 @@ func SketchBatch(bases []byte, offsets []uint64, k, s int, rowStride int) (out [
 	out = make([]uint32, n*rowStride+1)
 	count = make([]uint32, n+1)
 	status = make([]int32, n+1)
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_mash_sketch_batch((*C.uint8_t)(unsafe.Pointer(&bases[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n),
 		C.int32_t(k), C.int32_t(s), 0, (*C.uint32_t)(unsafe.Pointer(&out[0])), C.uint64_t(rowStride),
 		(*C.uint32_t)(unsafe.Pointer(&count[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
 	return out, count, status, check(rc)
+}
+
+func devicePtr(devices []int32) (*C.int32_t, C.int32_t) {
+	if len(devices) == 0 {
+		return nil, 0 // all visible GPUs
+	}
+	return (*C.int32_t)(unsafe.Pointer(&devices[0])), C.int32_t(len(devices))
+}
+
+// SketchBatchMulti wraps pg_mash_sketch_batch_multi: the batch is cut into contiguous shards, one per
+// GPU of this process (devices == nil: every visible GPU), each driven by its own host thread inside the
+// library.  Same results as SketchBatch.
+func SketchBatchMulti(bases []byte, offsets []uint64, k, s int, rowStride int, devices []int32) (out []uint32, count []uint32, status []int32, err error) {
+	n := len(offsets) - 1
+	out = make([]uint32, n*rowStride+1)
+	count = make([]uint32, n+1)
+	status = make([]int32, n+1)
+	dp, dn := devicePtr(devices)
+	err = locked(func() C.int {
+		return C.pg_mash_sketch_batch_multi((*C.uint8_t)(unsafe.Pointer(&bases[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n),
+			C.int32_t(k), C.int32_t(s), 0, (*C.uint32_t)(unsafe.Pointer(&out[0])), C.uint64_t(rowStride),
+			(*C.uint32_t)(unsafe.Pointer(&count[0])), (*C.int32_t)(unsafe.Pointer(&status[0])), dp, dn)
+	})
+	return out, count, status, err
+}
+
+// SketchDistanceMulti wraps pg_mash_sketch_distance_multi for fixed-length reads stored back to back:
+// sketches (n x s full arrays), matching counts and distances (n x n), computed on all listed GPUs with
+// the all-gather of the sketches fused into the sketch kernels.
+func SketchDistanceMulti(bases []byte, n, readLen, k, s int, devices []int32) (sketches []uint32, same []uint32, dist []float64, err error) {
+	sketches = make([]uint32, n*s+1)
+	same = make([]uint32, n*n+1)
+	dist = make([]float64, n*n+1)
+	dp, dn := devicePtr(devices)
+	err = locked(func() C.int {
+		return C.pg_mash_sketch_distance_multi((*C.uint8_t)(unsafe.Pointer(&bases[0])), C.uint64_t(n), C.uint32_t(readLen), C.int32_t(k), C.int32_t(s),
+			dp, dn, (*C.uint32_t)(unsafe.Pointer(&sketches[0])), (*C.uint32_t)(unsafe.Pointer(&same[0])), (*C.double)(unsafe.Pointer(&dist[0])))
+	})
+	return sketches[:n*s], same[:n*n], dist[:n*n], err
 }
 
 // SimilarityPairs wraps pg_mash_similarity_pairs.
@@ -72,6 +122,8 @@ func SimilarityPairs(sketches []uint32, skOffsets []uint64, pairA, pairB []uint3
 	if len(sketches) == 0 {
 		sketches = make([]uint32, 1)
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_mash_similarity_pairs((*C.uint32_t)(unsafe.Pointer(&sketches[0])), (*C.uint64_t)(unsafe.Pointer(&skOffsets[0])),
 		C.uint64_t(len(skOffsets)-1), (*C.uint32_t)(unsafe.Pointer(&pairA[0])), (*C.uint32_t)(unsafe.Pointer(&pairB[0])), C.uint64_t(np),
 		(*C.int64_t)(unsafe.Pointer(&same[0])), (*C.double)(unsafe.Pointer(&sim[0])), (*C.double)(unsafe.Pointer(&dist[0])),
@@ -83,6 +135,8 @@ func SimilarityPairs(sketches []uint32, skOffsets []uint64, pairA, pairB []uint3
 func DistanceBlock(sketches []uint32, n, s int, rowBegin, rowEnd int) (same []uint32, dist []float64, err error) {
 	rows := rowEnd - rowBegin
 	same, dist = make([]uint32, rows*n+1), make([]float64, rows*n+1)
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_mash_distance_block((*C.uint32_t)(unsafe.Pointer(&sketches[0])), C.uint64_t(n), C.int32_t(s), C.uint64_t(rowBegin),
 		C.uint64_t(rowEnd), (*C.uint32_t)(unsafe.Pointer(&same[0])), (*C.double)(unsafe.Pointer(&dist[0])))
 	return same[:rows*n], dist[:rows*n], check(rc)
@@ -101,6 +155,8 @@ func SWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA b
 	if queryIsA {
 		qa = 1
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_sw_score_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
 		(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
 		(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
@@ -121,6 +177,8 @@ func NWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA b
 	if queryIsA {
 		qa = 1
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_nw_score_batch((*C.uint8_t)(unsafe.Pointer(&queries[0])), (*C.uint64_t)(unsafe.Pointer(&qOffsets[0])), C.uint64_t(n),
 		(*C.uint8_t)(unsafe.Pointer(&t[0])), C.uint64_t(len(template)), qa, (*C.int16_t)(unsafe.Pointer(&lutA[0])),
 		(*C.int16_t)(unsafe.Pointer(&lutB[0])), (*C.int64_t)(unsafe.Pointer(&table[0])), C.int32_t(nA), C.int32_t(nB), C.int64_t(gap),
@@ -198,6 +256,8 @@ func alignBatch(global bool, queries []byte, qOffsets []uint64, template string,
 func TmBatch(bases []byte, offsets []uint64, cp, na, mg float64) (tm, dH, dS []float64, status []int32, err error) {
 	n := len(offsets) - 1
 	tm, dH, dS, status = make([]float64, n+1), make([]float64, n+1), make([]float64, n+1), make([]int32, n+1)
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_tm_batch((*C.uint8_t)(unsafe.Pointer(&bases[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n),
 		C.double(cp), C.double(na), C.double(mg), (*C.double)(unsafe.Pointer(&tm[0])), (*C.double)(unsafe.Pointer(&dH[0])),
 		(*C.double)(unsafe.Pointer(&dS[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
@@ -226,6 +286,8 @@ func FastaIngest(text []byte, maxLineSize int, bufioAlias bool) (seq []byte, seq
 	if bufioAlias {
 		flags = C.PG_FASTA_BUFIO_ALIAS
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_fasta_ingest((*C.uint8_t)(unsafe.Pointer(&text[0])), C.uint64_t(len(text)), C.uint32_t(maxLineSize), flags,
 		(*C.uint8_t)(unsafe.Pointer(&seq[0])), C.uint64_t(len(seq)), (*C.uint64_t)(unsafe.Pointer(&seqOff[0])),
 		(*C.uint8_t)(unsafe.Pointer(&names[0])), C.uint64_t(len(names)), (*C.uint64_t)(unsafe.Pointer(&nameOff[0])),
@@ -245,6 +307,8 @@ func DesignPrimersBatch(bases []byte, offsets []uint64, targetTm float64) (fwdLe
 	if len(bases) > 0 {
 		base = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_design_primers_batch(base, (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n), C.double(targetTm),
 		(*C.uint32_t)(unsafe.Pointer(&fwdLen[0])), (*C.uint32_t)(unsafe.Pointer(&revLen[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
 	return fwdLen[:n], revLen[:n], status[:n], check(rc)
@@ -258,6 +322,8 @@ func MinimalPrimerBatch(bases []byte, offsets []uint64, targetTm float64) (minLe
 	if len(bases) > 0 {
 		base = (*C.uint8_t)(unsafe.Pointer(&bases[0]))
 	}
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 	rc := C.pg_pcr_minimal_primer_batch(base, (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n), C.double(targetTm),
 		(*C.uint32_t)(unsafe.Pointer(&minLen[0])), (*C.int32_t)(unsafe.Pointer(&status[0])))
 	return minLen[:n], status[:n], check(rc)
@@ -281,6 +347,8 @@ func FindSites(seqs []byte, seqOff []uint64, patterns []byte, patOff []uint64) (
 	for {
 		hs, hp, hq := make([]uint32, capHits), make([]uint64, capHits), make([]uint32, capHits)
 		var n C.uint64_t
+		runtime.LockOSThread()
+		defer runtime.UnlockOSThread() // pg_last_error() is thread-local: read it on the calling thread
 		rc := C.pg_find_sites_batch((*C.uint8_t)(unsafe.Pointer(&seqs[0])), (*C.uint64_t)(unsafe.Pointer(&seqOff[0])), C.uint64_t(nSeq),
 			(*C.uint8_t)(unsafe.Pointer(&patterns[0])), (*C.uint64_t)(unsafe.Pointer(&patOff[0])), C.uint32_t(nPat), 0,
 			(*C.uint32_t)(unsafe.Pointer(&hs[0])), (*C.uint64_t)(unsafe.Pointer(&hp[0])), (*C.uint32_t)(unsafe.Pointer(&hq[0])),

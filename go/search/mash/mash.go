@@ -63,7 +63,8 @@ func (mash *Mash) Similarity(other *Mash) float64 { s, _ := mash.pair(other); re
 // Distance returns the Jaccard distance between two sketches (mash.go:138-140).
 func (mash *Mash) Distance(other *Mash) float64 { _, d := mash.pair(other); return d }
 
-// SketchBatch is New(kmerSize, sketchSize) + Sketch(seq) for every sequence, one GPU pass.
+// SketchBatch is New(kmerSize, sketchSize) + Sketch(seq) for every sequence: one call, sharded over every
+// GPU of the box (reads are independent, mash.go:68-104; no collective is involved).
 func SketchBatch(sequences []string, kmerSize, sketchSize int) []*Mash {
 	bases, offsets := polyb200.Flatten(sequences)
 	maxn := 0
@@ -79,7 +80,7 @@ func SketchBatch(sequences []string, kmerSize, sketchSize int) []*Mash {
 	if stride < 1 {
 		stride = 1
 	}
-	out, count, status, err := polyb200.SketchBatch(bases, offsets, kmerSize, sketchSize, stride)
+	out, count, status, err := polyb200.SketchBatchMulti(bases, offsets, kmerSize, sketchSize, stride, nil)
 	if err != nil && !errors.Is(err, polyb200.ErrPanic) {
 		panic(err)
 	}

@@ -11,14 +11,20 @@
 //           search/align/align.go:73-95,171-203
 //   poly::primers::SantaLucia / MeltingTemp <- primers/primers.go:70-105,121-128
 //   poly::fasta::Parse / ParseAll            <- io/fasta/fasta.go:72-77,89-118,149-243
+//   poly::pcr::DesignPrimers* / SimulateSimple / Simulate <- primers/pcr/pcr.go:44-186
+//   poly::mash::ToJSON / FromJSON (the encoding/json shape of mash.Mash) and the PGSKETCH container
 // A Go panic surfaces as poly::GoPanic; align's alphabet.Error as poly::align::AlphabetError.
 // The Go package in go/ (cgo) is the real drop-in; this header is what the tests in this
 // repository can compile and run (tests/test_gpu_hostcpp.py).  No compute happens here.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../include/poly_b200.h"
@@ -100,15 +106,17 @@ inline Mash New(int kmerSize, int sketchSize) {
     return Mash{kmerSize, sketchSize, std::vector<uint32_t>((size_t)sketchSize, 0u)};
 }
 
-// batched addition: []string -> []Mash, each == New(k, s) + Sketch(seq)
-inline std::vector<Mash> SketchBatch(const std::vector<std::string> &seqs, int k, int s) {
+// batched addition: []string -> []Mash, each == New(k, s) + Sketch(seq).  One call, sharded over the
+// GPUs of this process (devices empty: every visible GPU; reads are independent, mash.go:68-104).
+inline std::vector<Mash> SketchBatch(const std::vector<std::string> &seqs, int k, int s, const std::vector<int32_t> &devices = {}) {
     Flat f(seqs);
     size_t maxlen = 0;
     for (auto &q : seqs) maxlen = std::max(maxlen, q.size());
     const uint64_t stride = std::max<int64_t>(1, std::min<int64_t>((int64_t)maxlen - k, s));
     std::vector<uint32_t> out(seqs.size() * stride), count(seqs.size());
     std::vector<int32_t> status(seqs.size());
-    int rc = pg_mash_sketch_batch(f.bases.data(), f.offsets.data(), seqs.size(), k, s, 0, out.data(), stride, count.data(), status.data());
+    int rc = pg_mash_sketch_batch_multi(f.bases.data(), f.offsets.data(), seqs.size(), k, s, 0, out.data(), stride, count.data(), status.data(),
+                                        devices.empty() ? nullptr : devices.data(), (int32_t)devices.size());
     if (rc != PG_OK && rc != PG_ERR_PANIC) check(rc);
     std::vector<Mash> res;
     res.reserve(seqs.size());
@@ -119,6 +127,165 @@ inline std::vector<Mash> SketchBatch(const std::vector<std::string> &seqs, int k
         res.push_back(std::move(m));
     }
     return res;
+}
+
+// batched addition: sketches of fixed-length reads + the all-pairs matrix on several GPUs of this process
+// (sketch kernels store into every device's gathered buffer: fused all-gather; device r computes row block r)
+struct SketchDistance {
+    std::vector<uint32_t> sketches;  // n x s, full Go arrays
+    std::vector<uint32_t> same;      // n x n matching counts, receiver = row
+    std::vector<double> distance;    // n x n, 1 - same/s (mash.go:134,139)
+};
+inline SketchDistance SketchDistanceMulti(const std::string &reads, uint64_t n, uint32_t readLen, int k, int s,
+                                          const std::vector<int32_t> &devices = {}) {
+    SketchDistance r;
+    r.sketches.resize(n * (uint64_t)s);
+    r.same.resize(n * n);
+    r.distance.resize(n * n);
+    int rc = pg_mash_sketch_distance_multi(reinterpret_cast<const uint8_t *>(reads.data()), n, readLen, k, s,
+                                           devices.empty() ? nullptr : devices.data(), (int32_t)devices.size(), r.sketches.data(), r.same.data(),
+                                           r.distance.data());
+    if (rc == PG_ERR_PANIC) throw GoPanic("index out of range [-1]");
+    check(rc);
+    return r;
+}
+
+// ---- sketch persistence -----------------------------------------------------------
+// encoding/json of mash.Mash (mash.go:52-56): exported fields in declaration order, no spaces -- byte for
+// byte what Go's json.Marshal emits, so single sketches interoperate with the reference.
+inline std::string ToJSON(const Mash &m) {
+    std::string out = "{\"KmerSize\":" + std::to_string(m.KmerSize) + ",\"SketchSize\":" + std::to_string(m.SketchSize) + ",\"Sketches\":";
+    if (m.Sketches.empty() && m.SketchSize != 0) return out + "null}";  // nil slice
+    out += "[";
+    for (size_t i = 0; i < m.Sketches.size(); ++i) out += (i ? "," : "") + std::to_string(m.Sketches[i]);
+    return out + "]}";
+}
+inline Mash FromJSON(const std::string &text) {
+    auto number_after = [&](const char *key) -> long long {
+        const size_t p = text.find(key);
+        if (p == std::string::npos) throw std::invalid_argument(std::string("missing ") + key);
+        return std::stoll(text.substr(p + std::strlen(key)));
+    };
+    Mash m{(int)number_after("\"KmerSize\":"), (int)number_after("\"SketchSize\":"), {}};
+    size_t p = text.find("\"Sketches\":");
+    if (p == std::string::npos) throw std::invalid_argument("missing Sketches");
+    p += 11;
+    if (text.compare(p, 4, "null") == 0) return m;
+    if (text[p] != '[') throw std::invalid_argument("Sketches is not an array");
+    ++p;
+    while (p < text.size() && text[p] != ']') {
+        size_t used = 0;
+        m.Sketches.push_back((uint32_t)std::stoull(text.substr(p), &used));
+        p += used;
+        if (p < text.size() && text[p] == ',') ++p;
+    }
+    return m;
+}
+
+// PGSKETCH v1 container for sketch SETS (layout: poly_b200/sketchfile.py; little endian):
+//   "PGSKETCH" | version 1 | KmerSize | SketchSize | flags (bit 0: dense) | n (u64) | words (u64) |
+//   count[n] (absent when dense) | the informative words of sketch 0, 1, ... | CRC-32 of everything before
+struct SketchSet {
+    int KmerSize = 0, SketchSize = 0;
+    std::vector<uint32_t> count;               // informative words per sketch
+    std::vector<std::vector<uint32_t>> rows;   // rows[i].size() == count[i]
+};
+namespace detail {
+inline uint32_t crc32(const uint8_t *p, size_t n, uint32_t crc = 0) {  // zlib's CRC-32 (reflected 0xEDB88320)
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    crc = ~crc;
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return ~crc;
+}
+template <typename T>
+inline void put(std::vector<uint8_t> &b, T v) {
+    for (size_t i = 0; i < sizeof(T); ++i) b.push_back((uint8_t)(v >> (8 * i)));
+}
+template <typename T>
+inline T get(const std::vector<uint8_t> &b, size_t &pos) {
+    if (pos + sizeof(T) > b.size()) throw std::invalid_argument("truncated sketch file");
+    T v = 0;
+    for (size_t i = 0; i < sizeof(T); ++i) v |= (T)b[pos + i] << (8 * i);
+    pos += sizeof(T);
+    return v;
+}
+}  // namespace detail
+inline std::vector<uint8_t> EncodeSketchSet(const SketchSet &set) {
+    std::vector<uint8_t> b;
+    const uint64_t n = set.rows.size();
+    bool dense = n > 0;
+    uint64_t words = 0;
+    for (auto &r : set.rows) { dense = dense && (int)r.size() == set.SketchSize; words += r.size(); }
+    b.insert(b.end(), {'P', 'G', 'S', 'K', 'E', 'T', 'C', 'H'});
+    detail::put<uint32_t>(b, 1);
+    detail::put<uint32_t>(b, (uint32_t)set.KmerSize);
+    detail::put<uint32_t>(b, (uint32_t)set.SketchSize);
+    detail::put<uint32_t>(b, dense ? 1u : 0u);
+    detail::put<uint64_t>(b, n);
+    detail::put<uint64_t>(b, words);
+    if (!dense)
+        for (auto &r : set.rows) detail::put<uint32_t>(b, (uint32_t)r.size());
+    for (auto &r : set.rows)
+        for (uint32_t w : r) detail::put<uint32_t>(b, w);
+    detail::put<uint32_t>(b, detail::crc32(b.data(), b.size()));
+    return b;
+}
+inline SketchSet DecodeSketchSet(const std::vector<uint8_t> &b) {
+    if (b.size() < 44 || std::memcmp(b.data(), "PGSKETCH", 8) != 0) throw std::invalid_argument("not a PGSKETCH file");
+    size_t tail = b.size() - 4, pos = 8;
+    if (detail::crc32(b.data(), tail) != detail::get<uint32_t>(b, tail)) throw std::invalid_argument("sketch file checksum mismatch");
+    if (detail::get<uint32_t>(b, pos) != 1) throw std::invalid_argument("not a PGSKETCH v1 file");
+    SketchSet set;
+    set.KmerSize = (int)detail::get<uint32_t>(b, pos);
+    set.SketchSize = (int)detail::get<uint32_t>(b, pos);
+    const uint32_t flags = detail::get<uint32_t>(b, pos);
+    const uint64_t n = detail::get<uint64_t>(b, pos), words = detail::get<uint64_t>(b, pos);
+    set.count.assign(n, (uint32_t)set.SketchSize);
+    if (!(flags & 1u))
+        for (uint64_t i = 0; i < n; ++i) set.count[i] = detail::get<uint32_t>(b, pos);
+    uint64_t total = 0;
+    for (uint32_t c : set.count) total += c;
+    if (total != words || pos + 4 * words + 4 != b.size()) throw std::invalid_argument("sketch file is inconsistent");
+    set.rows.resize(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        set.rows[i].resize(set.count[i]);
+        for (uint32_t j = 0; j < set.count[i]; ++j) set.rows[i][j] = detail::get<uint32_t>(b, pos);
+    }
+    return set;
+}
+inline void SaveSketchSet(const std::string &path, const SketchSet &set) {
+    auto b = EncodeSketchSet(set);
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f || std::fwrite(b.data(), 1, b.size(), f) != b.size()) { if (f) std::fclose(f); throw std::runtime_error("cannot write " + path); }
+    std::fclose(f);
+}
+inline SketchSet LoadSketchSet(const std::string &path) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot read " + path);
+    std::vector<uint8_t> b;
+    uint8_t buf[65536];
+    for (size_t got; (got = std::fread(buf, 1, sizeof buf, f)) > 0;) b.insert(b.end(), buf, buf + got);
+    std::fclose(f);
+    return DecodeSketchSet(b);
+}
+// the set as Mash values (zero tail of a fresh Mash re-materialised)
+inline std::vector<Mash> MashesOf(const SketchSet &set) {
+    std::vector<Mash> out;
+    for (auto &r : set.rows) {
+        Mash m = New(set.KmerSize, set.SketchSize);
+        std::copy(r.begin(), r.end(), m.Sketches.begin());
+        out.push_back(std::move(m));
+    }
+    return out;
 }
 
 }  // namespace mash
@@ -317,6 +484,152 @@ inline std::vector<double> MeltingTemps(const std::vector<std::string> &seqs) {
 }
 
 }  // namespace primers
+
+namespace transform {
+// transform.ReverseComplement, transform/transform.go:15-23,78-109: bytes outside the table become 0
+inline std::string ReverseComplement(const std::string &seq) {
+    static const char *from = "ABCDGHKMNRSTVWYabcdghkmnrstvwy", *to = "TVGHCDMKNYSABWRtvghcdmknysabwr";
+    uint8_t table[256] = {0};
+    for (int i = 0; from[i]; ++i) table[(uint8_t)from[i]] = (uint8_t)to[i];
+    std::string out(seq.size(), '\0');
+    for (size_t i = 0; i < seq.size(); ++i) out[i] = (char)table[(uint8_t)seq[seq.size() - 1 - i]];
+    return out;
+}
+}  // namespace transform
+
+// primers/pcr (primers/pcr/pcr.go): the Tm searches (pcr.go:44-60, 93-100) and the binding-site search the
+// reference does with a suffix array (pcr.go:87,110-115) run on the GPU; the fragment bookkeeping
+// (pcr.go:117-166,181-195) is host work, as in the reference.
+namespace pcr {
+
+inline std::string upper_ascii(const std::string &s) {
+    std::string u = s;
+    for (char &c : u) {
+        if ((uint8_t)c >= 0x80) throw std::invalid_argument("byte >= 0x80: strings.ToUpper on non-ASCII input is unsupported");
+        if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+    }
+    return u;
+}
+
+// pcr.DesignPrimersWithOverhangs, pcr.go:44-60
+inline std::pair<std::string, std::string> DesignPrimersWithOverhangs(const std::string &sequence, const std::string &forwardOverhang,
+                                                                       const std::string &reverseOverhang, double targetTm) {
+    const std::string templ = upper_ascii(sequence);
+    const uint64_t off[2] = {0, templ.size()};
+    uint32_t fwd = 0, rev = 0;
+    int32_t st = 0;
+    int rc = pg_design_primers_batch(reinterpret_cast<const uint8_t *>(templ.data()), off, 1, targetTm, &fwd, &rev, &st);
+    if (rc == PG_ERR_PANIC || st == PG_ITEM_PANIC) throw GoPanic("slice bounds out of range");  // the reference slices past the end
+    check(rc);
+    return {forwardOverhang + templ.substr(0, fwd), transform::ReverseComplement(reverseOverhang) + transform::ReverseComplement(templ.substr(templ.size() - rev))};
+}
+// pcr.DesignPrimers, pcr.go:62-66
+inline std::pair<std::string, std::string> DesignPrimers(const std::string &sequence, double targetTm) {
+    return DesignPrimersWithOverhangs(sequence, "", "", targetTm);
+}
+
+// pcr.SimulateSimple, pcr.go:73-169.  Like the reference it upper-cases primerList in place.
+inline std::vector<std::string> SimulateSimple(const std::vector<std::string> &sequences, double targetTm, bool circular,
+                                               std::vector<std::string> &primerList) {
+    for (auto &p : primerList) p = upper_ascii(p);  // pcr.go:76-78
+    std::vector<std::string> fragments;
+    if (sequences.empty()) return fragments;
+    std::vector<std::string> templates;
+    for (auto &q : sequences) templates.push_back(upper_ascii(q));  // pcr.go:82
+    // GPU pass 1: the minimal binding part of every primer (pcr.go:93-103)
+    std::vector<std::string> minimal(primerList.size());
+    std::vector<std::string> patterns;
+    std::vector<std::pair<int, bool>> owner;  // (primer, is reverse complement)
+    if (!primerList.empty()) {
+        Flat f(primerList);
+        std::vector<uint32_t> ml(primerList.size());
+        std::vector<int32_t> st(primerList.size());
+        int rc = pg_pcr_minimal_primer_batch(f.bases.data(), f.offsets.data(), primerList.size(), targetTm, ml.data(), st.data());
+        for (int32_t x : st)
+            if (x == PG_ITEM_PANIC) throw GoPanic("slice bounds out of range");  // primer shorter than 7 nt (pcr.go:35,96)
+        if (rc != PG_ERR_PANIC) check(rc);
+        for (size_t p = 0; p < primerList.size(); ++p) {
+            const std::string part = primerList[p].substr(primerList[p].size() - ml[p]);
+            if (part == primerList[p]) continue;  // pcr.go:103: ignored
+            minimal[p] = part;
+            patterns.push_back(part);
+            owner.emplace_back((int)p, false);
+            patterns.push_back(transform::ReverseComplement(part));
+            owner.emplace_back((int)p, true);
+        }
+    }
+    // GPU pass 2: every occurrence of every pattern in every template (pcr.go:110,113)
+    struct Hit { uint32_t seq; uint64_t pos; uint32_t pat; };
+    std::vector<Hit> hits;
+    if (!patterns.empty()) {
+        Flat ft(templates), fp(patterns);
+        uint64_t cap = 1024, found = 0;
+        for (;;) {
+            std::vector<uint32_t> hs(cap), hq(cap);
+            std::vector<uint64_t> hp(cap);
+            int rc = pg_find_sites_batch(ft.bases.data(), ft.offsets.data(), templates.size(), fp.bases.data(), fp.offsets.data(),
+                                         (uint32_t)patterns.size(), 0, hs.data(), hp.data(), hq.data(), cap, &found);
+            if (rc == PG_ERR_ARG && found > cap) { cap = found; continue; }
+            check(rc);
+            for (uint64_t i = 0; i < found; ++i) hits.push_back({hs[i], hp[i], hq[i]});
+            break;
+        }
+        // the order in which the reference fills its maps: by template, then primer (forward lookup first), then position
+        std::sort(hits.begin(), hits.end(), [](const Hit &a, const Hit &b) {
+            if (a.seq != b.seq) return a.seq < b.seq;
+            if (a.pat != b.pat) return a.pat < b.pat;
+            return a.pos < b.pos;
+        });
+    }
+    size_t cursor = 0;
+    for (size_t t = 0; t < templates.size(); ++t) {
+        const std::string &templ = templates[t];
+        std::map<uint64_t, std::vector<int>> fwd, rev;  // position -> primers bound there, in primer-list order; keys ascending
+        for (; cursor < hits.size() && hits[cursor].seq == t; ++cursor)
+            (owner[hits[cursor].pat].second ? rev : fwd)[hits[cursor].pos].push_back(owner[hits[cursor].pat].first);
+        auto emit = [&](const std::string &text, uint64_t from, uint64_t to, const std::vector<int> &fps, const std::vector<int> &rps) {
+            for (int fp : fps)      // generatePcrFragments, pcr.go:181-195
+                for (int rp : rps)
+                    fragments.push_back(primerList[fp].substr(0, primerList[fp].size() - minimal[fp].size()) + text.substr(from, to - from) +
+                                        transform::ReverseComplement(primerList[rp]));
+        };
+        for (auto f = fwd.begin(); f != fwd.end(); ++f) {
+            auto next = std::next(f);
+            auto r = rev.upper_bound(f->first);  // reverse sites strictly to the right
+            if (next != fwd.end()) {             // pcr.go:133-143: the first reverse site before the next forward site
+                if (r != rev.end() && r->first < next->first) emit(templ, f->first, r->first, f->second, r->second);
+                continue;
+            }
+            const bool found = r != rev.end();
+            for (; r != rev.end(); ++r) emit(templ, f->first, r->first, f->second, r->second);  // pcr.go:146-151
+            if (circular && !found) {            // pcr.go:153-164: look across the origin
+                const std::string rotated = templ.substr(f->first) + templ.substr(0, f->first);
+                for (auto q = rev.begin(); q != rev.end() && q->first < fwd.begin()->first; ++q)
+                    emit(rotated, 0, templ.size() - f->first + q->first, f->second, q->second);
+            }
+        }
+    }
+    return fragments;
+}
+
+// pcr.Simulate, pcr.go:171-186: (fragments, error message; empty = nil)
+struct Simulation {
+    std::vector<std::string> fragments;
+    bool hasFragments = true;  // false: the reference returns nil
+    std::string error;
+};
+inline Simulation Simulate(const std::vector<std::string> &sequences, double targetTm, bool circular, std::vector<std::string> &primerList) {
+    for (auto &p : primerList)
+        if (p.size() < 7) return {{}, false, "Primers are too short."};  // minimalPrimerLength, pcr.go:35,174-178
+    Simulation sim;
+    sim.fragments = SimulateSimple(sequences, targetTm, circular, primerList);
+    std::vector<std::string> again = primerList;
+    again.insert(again.end(), sim.fragments.begin(), sim.fragments.end());
+    if (SimulateSimple(sequences, targetTm, circular, again).size() != sim.fragments.size()) sim.error = "Concatemerization detected in PCR.";
+    return sim;
+}
+
+}  // namespace pcr
 
 namespace fasta {
 

@@ -2,7 +2,7 @@
 // host mirror (hostcpp/poly_b200.hpp) so that they read like the originals:
 //   search/mash/mash_test.go:9-62, search/mash/example_test.go:9-22,
 //   search/align/align_test.go:139-292, search/align/example_test.go:49-111,
-//   primers/primers_test.go:29-84.
+//   primers/primers_test.go:29-84, primers/pcr/pcr_test.go:12-101, primers/pcr/example_test.go:10-69.
 // Needs a B200: every call below lands in libpolyb200.so.  Run by tests/test_gpu_hostcpp.py.
 #include <cmath>
 #include <cstdio>
@@ -122,12 +122,114 @@ static void TestFastaParser() {  // io/fasta/fasta_test.go:135-170,199-237
     }
 }
 
-int main() {
+
+static const std::string kGene = "aataattacaccgagataacacatcatggataaaccgatactcaaagattctatgaagctatttgaggcacttggtacgatcaagtcgcgctcaatgtttggtggcttcggacttttcgctgatgaaacgatgtttgcactggttgtgaatgatcaacttcacatacgagcagaccagcaaacttcatctaacttcgagaagcaagggctaaaaccgtacgtttataaaaagcgtggttttccagtcgttactaagtactacgcgatttccgacgacttgtgggaatccagtgaacgcttgatagaagtagcgaagaagtcgttagaacaagccaatttggaaaaaaagcaacaggcaagtagtaagcccgacaggttgaaagacctgcctaacttacgactagcgactgaacgaatgcttaagaaagctggtataaaatcagttgaacaacttgaagagaaaggtgcattgaatgcttacaaagcgatacgtgactctcactccgcaaaagtaagtattgagctactctgggctttagaaggagcgataaacggcacgcactggagcgtcgttcctcaatctcgcagagaagagctggaaaatgcgctttcttaa";
+static const std::string kBadFragment = "ATGACCATGATTACGCCAAGCTTGCATGCCTGCAGGTCGACTCTAGAGGATCCCCGGGTACCGAGCTCGAATTCACTGGCCGTCGTTTTACAACGTCGTGACTGGGAAAACCCTGGCGTTACCCAACTTAATCGCCTTGCAGCACATCCCCCTTTCGCCAGCTGGCGTAATAGCGAAGAGGCCCGCACCGATCGCCCTTCCCAACAGTTGCGCAGCCTGAATGGCGAATGGCGCCTGATGCGGTATTTTCTCCTTACGCATCTGTGCGGTATTTCACACCGCATATGGTGCACTCTCAGTACAATCTGCTCTGATGCCGCATAG";
+static const std::string kFullAmplicon = "TTATAGGTCTCATACTAATAATTACACCGAGATAACACATCATGGATAAACCGATACTCAAAGATTCTATGAAGCTATTTGAGGCACTTGGTACGATCAAGTCGCGCTCAATGTTTGGTGGCTTCGGACTTTTCGCTGATGAAACGATGTTTGCACTGGTTGTGAATGATCAACTTCACATACGAGCAGACCAGCAAACTTCATCTAACTTCGAGAAGCAAGGGCTAAAACCGTACGTTTATAAAAAGCGTGGTTTTCCAGTCGTTACTAAGTACTACGCGATTTCCGACGACTTGTGGGAATCCAGTGAACGCTTGATAGAAGTAGCGAAGAAGTCGTTAGAACAAGCCAATTTGGAAAAAAAGCAACAGGCAAGTAGTAAGCCCGACAGGTTGAAAGACCTGCCTAACTTACGACTAGCGACTGAACGAATGCTTAAGAAAGCTGGTATAAAATCAGTTGAACAACTTGAAGAGAAAGGTGCATTGAATGCTTACAAAGCGATACGTGACTCTCACTCCGCAAAAGTAAGTATTGAGCTACTCTGGGCTTTAGAAGGAGCGATAAACGGCACGCACTGGAGCGTCGTTCCTCAATCTCGCAGAGAAGAGCTGGAAAATGCGCTTTCTTAAATGAAGAGACCATATA";
+static const std::string kCircularTarget = "ACTCTGGGCTTTAGAAGGAGCGATAAACGGCACGCACTGGAGCGTCGTTCCTCAATCTCGCAGAGAAGAGCTGGAAAATGCGCTTTCTTAAAATAATTACACCGAGATAACACATCATGGATAAACCGATACTCAAAGATTCTATGAAGCTATTTGAGGCACTT";
+
+static void TestPcr() {  // primers/pcr/pcr_test.go:12-101, example_test.go:10-69
+    using pcr::Simulate;
+    // ExampleDesignPrimers / ExampleDesignPrimersWithOverhangs (example_test.go:39-55)
+    auto pr = pcr::DesignPrimers(kGene, 55.0);
+    EXPECT(pr.first == "AATAATTACACCGAGATAACACATCATGG" && pr.second == "TTAAGAAAGCGCATTTTCCAGC");
+    auto po = pcr::DesignPrimersWithOverhangs(kGene, "TTATAGGTCTCATACT", "ATGAAGAGACCATATA", 55.0);
+    EXPECT(po.first == "TTATAGGTCTCATACTAATAATTACACCGAGATAACACATCATGG" && po.second == "TATATGGTCTCTTCATTTAAGAAAGCGCATTTTCCAGC");
+    // ExampleSimulate / TestIssue279PCRBug
+    std::vector<std::string> primers = {po.first, po.second};
+    auto sim = Simulate({kGene}, 55.0, false, primers);
+    EXPECT(sim.error.empty() && sim.fragments == std::vector<std::string>({kFullAmplicon}));
+    // Example_basic: the second template adds nothing
+    primers = {po.first, po.second};
+    EXPECT(Simulate({kGene, kBadFragment}, 55.0, false, primers).fragments.size() == 1);
+    // TestSimulatePrimerRejection: CTGCAGGTCGACTCTAG never reaches the target Tm and is ignored
+    primers = {"TATATGGTCTCTTCATTTAAGAAAGCGCATTTTCCAGC", "TTATAGGTCTCATACTAATAATTACACCGAGATAACACATCATGG", "CTGCAGGTCGACTCTAG"};
+    EXPECT(Simulate({kGene}, 55.0, false, primers).fragments.size() == 1);
+    // TestSimulateMoreThanOneForward
+    primers = {"gatactcaaagattctatgaagctatttgaggcacttggtacg", "tatcgctttgtaagcattcaatgcacctttctcttcaagttg", "gtcgttcctcaatctcgcagagaagagctggaaaatg"};
+    EXPECT(Simulate({kGene}, 55.0, false, primers).fragments.size() == 1);
+    EXPECT(primers[0] == "GATACTCAAAGATTCTATGAAGCTATTTGAGGCACTTGGTACG");  // upper-cased in place, pcr.go:76-78
+    // TestSimulateCircular
+    primers = {"actctgggctttagaaggagcgataaacggc", "aagtgcctcaaatagcttcatagaatctttgagtatcgg"};
+    sim = Simulate({kGene}, 55.0, true, primers);
+    EXPECT(!sim.fragments.empty() && sim.fragments[0] == kCircularTarget);
+    // TestSimulateConcatemerization
+    primers = {"AATAATTACACCGAGATAACACATCATGG", "CCATGATGTGTTATCTCGGTGTAATTATTTTAAGAAAGCGCATTTTCCAGC"};
+    EXPECT(Simulate({kGene}, 55.0, false, primers).error == "Concatemerization detected in PCR.");
+    // pcr.go:174-178: shorter than minimalPrimerLength (7)
+    primers = {po.first, "ACGT"};
+    sim = Simulate({kGene}, 55.0, false, primers);
+    EXPECT(!sim.hasFragments && sim.error == "Primers are too short.");
+    primers = {po.first, "ACGTACG"};  // exactly 7 nt is legal; its whole length stays below the target and it is ignored
+    EXPECT(Simulate({kGene}, 55.0, false, primers).error.empty());
+    bool panicked = false;
+    try { primers = {"ACGT"}; pcr::SimulateSimple({kGene}, 55.0, false, primers); } catch (const GoPanic &) { panicked = true; }
+    EXPECT(panicked);
+}
+
+static void TestSketchPersistenceAndMulti(const char *out_path) {  // SURVEY.md 8f.4 + the *_multi entry points
+    const std::string A = "ATGCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGA";
+    auto m = mash::New(17, 10); m.Sketch(A);
+    const std::string js = mash::ToJSON(m);
+    EXPECT(js.rfind("{\"KmerSize\":17,\"SketchSize\":10,\"Sketches\":[", 0) == 0 && js.back() == '}' && js.find(' ') == std::string::npos);
+    auto back = mash::FromJSON(js);
+    EXPECT(back.KmerSize == 17 && back.SketchSize == 10 && back.Sketches == m.Sketches);
+    EXPECT(mash::FromJSON("{\"KmerSize\":3,\"SketchSize\":2,\"Sketches\":null}").Sketches.empty());
+    // a set: fill-regime (compact) and select-regime rows together
+    std::vector<std::string> reads;
+    std::string flat;
+    for (int i = 0; i < 40; ++i) {
+        std::string r(300, 'A');
+        uint64_t x = 0x9E3779B97F4A7C15ull * (uint64_t)(i / 4 + 1);
+        for (int j = 0; j < 300; ++j) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            r[j] = "ACGT"[(x >> 11) & 3];
+        }
+        if (i % 4) r[17 * (i % 4)] = 'N';  // family of 4: three mutated copies
+        reads.push_back(r);
+        flat += r;
+    }
+    auto batch = mash::SketchBatch(reads, 21, 64);                 // sharded over every visible GPU
+    auto one_gpu = mash::SketchBatch(reads, 21, 64, {0});
+    for (size_t i = 0; i < reads.size(); ++i) {
+        auto single = mash::New(21, 64); single.Sketch(reads[i]);
+        EXPECT(batch[i].Sketches == single.Sketches && one_gpu[i].Sketches == single.Sketches);
+    }
+    mash::SketchSet set;
+    set.KmerSize = 21; set.SketchSize = 64;
+    for (auto &b : batch) set.rows.push_back(b.Sketches);
+    set.rows.push_back({1u, 2u, 3u});                              // a compact (fill-regime) row: 3 informative words
+    auto blob = mash::EncodeSketchSet(set);
+    auto dec = mash::DecodeSketchSet(blob);
+    EXPECT(dec.KmerSize == 21 && dec.SketchSize == 64 && dec.rows == set.rows && dec.count.back() == 3);
+    blob[50] ^= 1;
+    bool rejected = false;
+    try { mash::DecodeSketchSet(blob); } catch (const std::invalid_argument &) { rejected = true; }
+    EXPECT(rejected);
+    if (out_path) mash::SaveSketchSet(out_path, set);             // read back by the Python implementation in the pytest
+    // fused sketch + all-gather + row-block distance on all GPUs == per-pair API
+    auto sd = mash::SketchDistanceMulti(flat, reads.size(), 300, 21, 64);
+    const size_t n = reads.size();
+    bool ok = true;
+    for (size_t i = 0; i < n; ++i) {
+        ok = ok && std::equal(batch[i].Sketches.begin(), batch[i].Sketches.end(), sd.sketches.begin() + i * 64);
+        for (size_t j = 0; j < n; j += 3) {
+            auto p = batch[i].pair(batch[j]);
+            ok = ok && (int64_t)sd.same[i * n + j] == p.same && sd.distance[i * n + j] == p.distance;
+        }
+    }
+    EXPECT(ok);
+    EXPECT(sd.same[0 * n + 1] > 0 && sd.same[0 * n + 4] == 0);     // same family shares hashes, another family does not
+}
+
+int main(int argc, char **argv) {
     check(pg_init(0));
     TestFastaParser();
     TestMash();
     TestSmithWaterman();
     TestSantaLucia();
+    TestPcr();
+    TestSketchPersistenceAndMulti(argc > 1 ? argv[1] : nullptr);
     std::printf(failures ? "FAILED (%d)\n" : "ok: reference tests pass through the C++ host mirror\n", failures);
     return failures ? 1 : 0;
 }

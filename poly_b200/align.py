@@ -128,8 +128,8 @@ def SmithWatermanScores(queries: Sequence[BytesLike], template: BytesLike, scori
     return [int(x) for x in score], errs
 
 
-def SmithWaterman(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> int:
-    """Score of align.SmithWaterman(stringA, stringB, scoring) (align.go:171-203).
+def SmithWatermanScore(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> int:
+    """Score of align.SmithWaterman(stringA, stringB, scoring) (align.go:171-203), score kernel only.
     Raises AlphabetError where the reference returns (0, "", "", err)."""
     scores, errs = SmithWatermanScores([stringA], stringB, scoring, query_is_a=True)
     if errs[0] is not None:
@@ -142,7 +142,7 @@ def NeedlemanWunschScores(queries: Sequence[BytesLike], template: BytesLike, sco
     return SmithWatermanScores(queries, template, scoring, query_is_a, global_alignment=True)
 
 
-def NeedlemanWunsch(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> int:
+def NeedlemanWunschScore(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> int:
     """Score of align.NeedlemanWunsch(stringA, stringB, scoring); the aligned strings are not built."""
     scores, errs = NeedlemanWunschScores([stringA], stringB, scoring)
     if errs[0] is not None:
@@ -188,8 +188,8 @@ def SmithWatermanAligns(queries: Sequence[BytesLike], template: BytesLike, scori
 
 def SmithWatermanAlign(stringA: BytesLike, stringB: BytesLike, scoring: Scoring) -> Tuple[int, str, str]:
     """align.SmithWaterman(stringA, stringB, scoring) -> (score, alignA, alignB); raises
-    AlphabetError where the reference returns (0, "", "", err).  Needs len(stringA) <= 64 or
-    len(stringB) <= 64 (the shorter string rides in registers)."""
+    AlphabetError where the reference returns (0, "", "", err).  A string of <= 64 symbols rides in
+    registers; when both are longer the whole matrix is kept in HBM, as the reference keeps it on the heap."""
     a, b = _as_bytes(stringA), _as_bytes(stringB)
     if len(a) <= 64:
         score, sa, sb, err = SmithWatermanAligns([a], b, scoring, query_is_a=True)[0]
@@ -211,3 +211,21 @@ def NeedlemanWunschAlign(stringA: BytesLike, stringB: BytesLike, scoring: Scorin
     if err is not None:
         raise err
     return score, sa, sb
+
+
+def SmithWaterman(stringA: BytesLike, stringB: BytesLike, scoring: Scoring):
+    """align.SmithWaterman (align.go:171-232) with the reference's own return shape:
+    (score, alignA, alignB, err) -- err is None or the AlphabetError, and (0, "", "", err) on error."""
+    try:
+        return SmithWatermanAlign(stringA, stringB, scoring) + (None,)
+    except AlphabetError as e:
+        return 0, "", "", e
+
+
+def NeedlemanWunsch(stringA: BytesLike, stringB: BytesLike, scoring: Scoring):
+    """align.NeedlemanWunsch (align.go:100-166) with the reference's own return shape:
+    (score, alignA, alignB, err)."""
+    try:
+        return NeedlemanWunschAlign(stringA, stringB, scoring) + (None,)
+    except AlphabetError as e:
+        return 0, "", "", e

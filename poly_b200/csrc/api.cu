@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <cctype>
 #include <sched.h>
 #include <sys/syscall.h>
@@ -51,6 +52,89 @@ struct Scratch {
     }
 };
 
+// grow-only pinned host staging (pageable caller buffers go through these; under the context's mutex)
+struct PinnedScratch {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return PG_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            set_error("cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return PG_ERR_NOMEM;
+        }
+        cap = bytes;
+        return PG_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Fork-join helper threads for host-side copies between pageable caller memory and the pinned
+// staging buffers: one memcpy thread moves ~10 GB/s, PCIe 5 x16 moves 55.
+class CopyPool {
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int parts_ = 0, next_ = 0, pending_ = 0;
+    bool stop_ = false;
+
+    void drain_parts(std::unique_lock<std::mutex> &lk) {
+        while (fn_ && next_ < parts_) {
+            const int i = next_++;
+            const std::function<void(int)> *f = fn_;
+            lk.unlock();
+            (*f)(i);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+
+public:
+    int threads() const { return (int)workers_.size() + 1; }
+    void start(int helpers, int device) {
+        if (!workers_.empty() || helpers <= 0) return;
+        for (int t = 0; t < helpers; ++t)
+            workers_.emplace_back([this, device] {
+                pg_numa_bind_thread(device, nullptr);  // copies run next to the GPU's PCIe root
+                std::unique_lock<std::mutex> lk(mu_);
+                for (;;) {
+                    cv_work_.wait(lk, [&] { return stop_ || (fn_ && next_ < parts_); });
+                    if (stop_) return;
+                    drain_parts(lk);
+                }
+            });
+    }
+    // f(0) .. f(parts-1), each exactly once, on the helpers and the calling thread; returns when all are done
+    void run(int parts, const std::function<void(int)> &f) {
+        if (parts <= 0) return;
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = &f; parts_ = parts; next_ = 0; pending_ = parts;
+        cv_work_.notify_all();
+        drain_parts(lk);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    void stop() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (std::thread &t : workers_) t.join();
+        workers_.clear();
+        stop_ = false;
+    }
+};
+
 // One context per CUDA device of the process.  The library serves any number of devices from one
 // process (pg_*_multi shard a batch over them; pg_thread_device binds a thread to one) as well as
 // the one-process-per-GPU layout (pg_init(device) picks the process default).
@@ -62,6 +146,8 @@ struct DevCtx {
     std::atomic<bool> ready{false};
     cudaStream_t streams[N_SLOTS] = {nullptr, nullptr, nullptr};
     Scratch in[N_SLOTS], out[N_SLOTS], aux[N_SLOTS], st[N_SLOTS];
+    PinnedScratch pin_in[N_SLOTS], pin_out[N_SLOTS];
+    CopyPool pool;
     std::mutex mu;   // serialises the host-pointer entry points on this device
     std::mutex fmu;  // guards func_smem
     std::unordered_map<const void *, size_t> func_smem;  // largest dynamic smem configured per kernel
@@ -236,8 +322,10 @@ int pg_shutdown(void) {
         cudaDeviceSynchronize();
         for (int i = 0; i < N_SLOTS; ++i) {
             c.in[i].release(); c.out[i].release(); c.aux[i].release(); c.st[i].release();
+            c.pin_in[i].release(); c.pin_out[i].release();
             if (c.streams[i]) { cudaStreamDestroy(c.streams[i]); c.streams[i] = nullptr; }
         }
+        c.pool.stop();
         {
             std::lock_guard<std::mutex> lk3(c.fmu);
             c.func_smem.clear();
@@ -453,6 +541,20 @@ int pg_mash_sketch_uniform_scatter_dev(const uint8_t *d_bases, uint64_t n_local,
 
 // Pipelined host path shared by the uniform and ragged entry points: chunks of reads
 // cycle through 3 stream/buffer slots (H2D, kernel, D2H overlap across slots).
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int host_copy_helpers() {
+    if (const char *e = getenv("PG_HOST_COPY_THREADS")) return std::max(0, atoi(e) - 1);
+    cpu_set_t cur;
+    int cores = (int)std::thread::hardware_concurrency();
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) cores = std::min(cores, CPU_COUNT(&cur));
+    return std::max(0, std::min(8, cores / 2) - 1);
+}
+
 static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t ulen, uint64_t n_reads,
                        int32_t k, int32_t s, uint32_t flags, uint32_t *out, uint64_t row_stride,
                        uint32_t *count, int32_t *status) {
@@ -461,105 +563,169 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
     if ((rc = check_ks(k, s)) != PG_OK) return rc;
     if (n_reads == 0) return PG_OK;
     if (!bases || !out) { set_error("null buffer"); return PG_ERR_ARG; }
-    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    DevCtx *cx = t_ctx;
+    std::lock_guard<std::mutex> lk(cx->mu);
+    // Pinned caller buffers (pg_host_alloc, cudaHostRegister) are DMA'd directly.  Pageable ones (a Go
+    // []byte / []uint32) would be bounced by the driver at ~14 GB/s: they go through pinned staging
+    // buffers instead, filled / emptied by a few host threads while the other slots' DMA runs; the
+    // device then always produces compact rows and the zero tail of PG_SKETCH_PAD_ZERO rows is
+    // written by the host threads, not shipped over PCIe.
+    const bool stage_in = is_pageable(bases), stage_out = is_pageable(out);
+    if (stage_in || stage_out) cx->pool.start(host_copy_helpers(), cx->device);
+    const int nthr = cx->pool.threads();
     const bool want_status = status != nullptr || s <= 1;
-    const uint64_t target_bytes = 192ull << 20;  // input bytes per chunk
+    const uint64_t target_bytes = (stage_in || stage_out) ? (32ull << 20) : (192ull << 20);  // input bytes per chunk
+    const uint64_t target_out_bytes = 128ull << 20;                                          // staged output bytes per chunk
     bool any_panic = false;
-    std::vector<int32_t> st_host;
     uint64_t r0 = 0;
     int slot = 0;
-    struct Pending { uint64_t r0, nr; bool used; } pend[3] = {{0, 0, false}, {0, 0, false}, {0, 0, false}};
-    std::vector<int32_t> st_slot[3];
+    struct Pending { uint64_t r0, nr, dstride; bool used; } pend[N_SLOTS] = {};
+    std::vector<int32_t> st_slot[N_SLOTS];
+    auto par_rows = [&](uint64_t nrows, const std::function<void(uint64_t, uint64_t)> &f) {
+        const int parts = (int)std::min<uint64_t>((uint64_t)nthr, std::max<uint64_t>(1, nrows));
+        cx->pool.run(parts, [&](int i) { f(nrows * (uint64_t)i / parts, nrows * (uint64_t)(i + 1) / parts); });
+    };
     auto drain = [&](int sl) -> int {
         if (!pend[sl].used) return PG_OK;
-        PG_CUDA(cudaStreamSynchronize(t_ctx->streams[sl]));
+        PG_CUDA(cudaStreamSynchronize(cx->streams[sl]));
+        const Pending &pd = pend[sl];
+        if (stage_out && pd.dstride) {  // staged rows -> caller rows (+ zero tail up to the caller's stride)
+            const uint32_t *src = (const uint32_t *)cx->pin_out[sl].p;
+            par_rows(pd.nr, [&](uint64_t a, uint64_t b) {
+                if (pd.dstride == row_stride) {
+                    memcpy(out + (pd.r0 + a) * row_stride, src + a * pd.dstride, (b - a) * pd.dstride * 4);
+                    return;
+                }
+                for (uint64_t i = a; i < b; ++i) {
+                    uint32_t *dst = out + (pd.r0 + i) * row_stride;
+                    memcpy(dst, src + i * pd.dstride, pd.dstride * 4);
+                    memset(dst + pd.dstride, 0, (row_stride - pd.dstride) * 4);
+                }
+            });
+        } else if (row_stride > pd.dstride) {  // direct DMA wrote dstride words per row: zero the rest of each row
+            par_rows(pd.nr, [&](uint64_t a, uint64_t b) {
+                for (uint64_t i = a; i < b; ++i) memset(out + (pd.r0 + i) * row_stride + pd.dstride, 0, (row_stride - pd.dstride) * 4);
+            });
+        }
         if (want_status) {
-            for (uint64_t i = 0; i < pend[sl].nr; ++i) {
+            for (uint64_t i = 0; i < pd.nr; ++i) {
                 if (st_slot[sl][i] != PG_ITEM_OK) any_panic = true;
-                if (status) status[pend[sl].r0 + i] = st_slot[sl][i];
+                if (status) status[pd.r0 + i] = st_slot[sl][i];
             }
         }
         pend[sl].used = false;
         return PG_OK;
     };
-    while (r0 < n_reads) {
-        // chunk [r0, r1)
-        uint64_t r1, beg, end, maxlen, minlen;
-        if (offsets) {
-            beg = offsets[r0];
-            r1 = r0;
-            maxlen = 0;
-            minlen = ~0ull;
-            while (r1 < n_reads && (r1 == r0 || offsets[r1 + 1] - beg <= target_bytes)) {
-                if (offsets[r1 + 1] < offsets[r1]) { set_error("offsets not monotone at %llu", (unsigned long long)r1); return PG_ERR_ARG; }
-                const uint64_t len = offsets[r1 + 1] - offsets[r1];
-                maxlen = std::max(maxlen, len);
-                minlen = std::min(minlen, len);
-                ++r1;
-            }
-            end = offsets[r1];
-        } else {
-            uint64_t per = std::max<uint64_t>(1, target_bytes / std::max<uint32_t>(ulen, 1));
-            per = (per + 31) & ~31ull;  // keep chunk starts on K1 tile boundaries
-            r1 = std::min(n_reads, r0 + per);
-            beg = r0 * (uint64_t)ulen;
-            end = r1 * (uint64_t)ulen;
-            maxlen = minlen = ulen;
-        }
-        const uint64_t nr = r1 - r0;
-        const bool uniform = maxlen == minlen && maxlen <= 0xffffffffull;
-        const uint64_t cnt_max = std::min<uint64_t>(kmers_of(maxlen, k), (uint64_t)s);
-        const uint64_t dev_stride = (flags & PG_SKETCH_PAD_ZERO) ? (uint64_t)s : cnt_max;
-        if (row_stride < dev_stride) { set_error("row_stride %llu < %llu", (unsigned long long)row_stride, (unsigned long long)dev_stride); return PG_ERR_ARG; }
-
-        if ((rc = drain(slot)) != PG_OK) return rc;
-        cudaStream_t stx = t_ctx->streams[slot];
-        const uint64_t in_bytes = end - beg;
-        if ((rc = t_ctx->in[slot].reserve(in_bytes + 64)) != PG_OK) return rc;
-        if ((rc = t_ctx->out[slot].reserve(std::max<uint64_t>(nr * dev_stride * 4, 16))) != PG_OK) return rc;
-        uint8_t *d_in = (uint8_t *)t_ctx->in[slot].p;
-        uint32_t *d_out = (uint32_t *)t_ctx->out[slot].p;
-        int32_t *d_status = nullptr;
-        uint32_t *d_count = nullptr;
-        uint64_t *d_off = nullptr;
-        if (want_status) {
-            if ((rc = t_ctx->st[slot].reserve(nr * 4)) != PG_OK) return rc;
-            d_status = (int32_t *)t_ctx->st[slot].p;
-            PG_CUDA(cudaMemsetAsync(d_status, 0, nr * 4, stx));
-            st_slot[slot].assign(nr, 0);
-        }
-        if (in_bytes) PG_CUDA(cudaMemcpyAsync(d_in, bases + beg, in_bytes, cudaMemcpyHostToDevice, stx));
-        if (uniform) {
-            rc = launch_sketch_uniform(d_in, nr, (uint32_t)maxlen, k, s, flags, d_out, dev_stride, d_status, stx);
-        } else {
-            if ((rc = t_ctx->aux[slot].reserve((nr + 1) * 8 + nr * 4)) != PG_OK) return rc;
-            d_off = (uint64_t *)t_ctx->aux[slot].p;
-            d_count = (uint32_t *)(d_off + nr + 1);
-            PG_CUDA(cudaMemcpyAsync(d_off, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, stx));
-            // kernels index bases with absolute offsets: shift the base pointer
-            rc = launch_sketch_ragged(d_in - beg, d_off, nr, maxlen, k, s, flags, d_out, dev_stride, d_count, d_status, stx);
-        }
-        if (rc != PG_OK) return rc;
-        if (dev_stride) {
-            if (row_stride == dev_stride)
-                PG_CUDA(cudaMemcpyAsync(out + r0 * row_stride, d_out, nr * dev_stride * 4, cudaMemcpyDeviceToHost, stx));
-            else
-                PG_CUDA(cudaMemcpy2DAsync(out + r0 * row_stride, row_stride * 4, d_out, dev_stride * 4, dev_stride * 4, nr, cudaMemcpyDeviceToHost, stx));
-        }
-        if (count) {
-            if (uniform) {
-                for (uint64_t i = 0; i < nr; ++i) count[r0 + i] = (uint32_t)cnt_max;
+    auto body = [&]() -> int {
+        while (r0 < n_reads) {
+            // chunk [r0, r1)
+            uint64_t r1, beg, end, maxlen, minlen;
+            if (offsets) {
+                beg = offsets[r0];
+                r1 = r0;
+                maxlen = 0;
+                minlen = ~0ull;
+                while (r1 < n_reads && (r1 == r0 || offsets[r1 + 1] - beg <= target_bytes)) {
+                    if (offsets[r1 + 1] < offsets[r1]) { set_error("offsets not monotone at %llu", (unsigned long long)r1); return PG_ERR_ARG; }
+                    const uint64_t len = offsets[r1 + 1] - offsets[r1];
+                    maxlen = std::max(maxlen, len);
+                    minlen = std::min(minlen, len);
+                    ++r1;
+                    if (stage_out && (r1 - r0) * std::min<uint64_t>(kmers_of(maxlen, k), (uint64_t)s) * 4 >= target_out_bytes) break;
+                }
+                end = offsets[r1];
             } else {
-                PG_CUDA(cudaMemcpyAsync(count + r0, d_count, nr * 4, cudaMemcpyDeviceToHost, stx));
+                uint64_t per = std::max<uint64_t>(1, target_bytes / std::max<uint32_t>(ulen, 1));
+                const uint64_t row_bytes = std::min<uint64_t>(kmers_of(ulen, k), (uint64_t)s) * 4;
+                if (stage_out && row_bytes) per = std::min(per, std::max<uint64_t>(32, target_out_bytes / row_bytes));
+                per = (per + 31) & ~31ull;  // keep chunk starts on K1 tile boundaries
+                r1 = std::min(n_reads, r0 + per);
+                beg = r0 * (uint64_t)ulen;
+                end = r1 * (uint64_t)ulen;
+                maxlen = minlen = ulen;
             }
+            const uint64_t nr = r1 - r0;
+            const bool uniform = maxlen == minlen && maxlen <= 0xffffffffull;
+            const uint64_t cnt_max = std::min<uint64_t>(kmers_of(maxlen, k), (uint64_t)s);
+            const uint64_t need_stride = (flags & PG_SKETCH_PAD_ZERO) ? (uint64_t)s : cnt_max;
+            if (row_stride < need_stride) { set_error("row_stride %llu < %llu", (unsigned long long)row_stride, (unsigned long long)need_stride); return PG_ERR_ARG; }
+            // staged output: compact device rows, the host threads pad; direct output: the device pads
+            const uint32_t dev_flags = stage_out ? (flags & ~PG_SKETCH_PAD_ZERO) : flags;
+            const uint64_t dev_stride = stage_out ? cnt_max : need_stride;
+
+            int rc2;
+            if ((rc2 = drain(slot)) != PG_OK) return rc2;
+            cudaStream_t stx = cx->streams[slot];
+            const uint64_t in_bytes = end - beg;
+            if ((rc2 = cx->in[slot].reserve(in_bytes + 64)) != PG_OK) return rc2;
+            if ((rc2 = cx->out[slot].reserve(std::max<uint64_t>(nr * dev_stride * 4, 16))) != PG_OK) return rc2;
+            uint8_t *d_in = (uint8_t *)cx->in[slot].p;
+            uint32_t *d_out = (uint32_t *)cx->out[slot].p;
+            int32_t *d_status = nullptr;
+            uint32_t *d_count = nullptr;
+            uint64_t *d_off = nullptr;
+            if (want_status) {
+                if ((rc2 = cx->st[slot].reserve(nr * 4)) != PG_OK) return rc2;
+                d_status = (int32_t *)cx->st[slot].p;
+                PG_CUDA(cudaMemsetAsync(d_status, 0, nr * 4, stx));
+                st_slot[slot].assign(nr, 0);
+            }
+            const uint8_t *h_src = bases + beg;
+            if (stage_in && in_bytes) {
+                if ((rc2 = cx->pin_in[slot].reserve(in_bytes)) != PG_OK) return rc2;
+                uint8_t *pin = (uint8_t *)cx->pin_in[slot].p;
+                par_rows((in_bytes + (1u << 20) - 1) >> 20, [&](uint64_t a, uint64_t b) {  // 1 MiB granules
+                    const uint64_t lo = a << 20, hi = std::min<uint64_t>(in_bytes, b << 20);
+                    if (hi > lo) memcpy(pin + lo, h_src + lo, hi - lo);
+                });
+                h_src = pin;
+            }
+            if (in_bytes) PG_CUDA(cudaMemcpyAsync(d_in, h_src, in_bytes, cudaMemcpyHostToDevice, stx));
+            if (uniform) {
+                rc2 = launch_sketch_uniform(d_in, nr, (uint32_t)maxlen, k, s, dev_flags, d_out, dev_stride, d_status, stx);
+            } else {
+                if ((rc2 = cx->aux[slot].reserve((nr + 1) * 8 + nr * 4)) != PG_OK) return rc2;
+                d_off = (uint64_t *)cx->aux[slot].p;
+                d_count = (uint32_t *)(d_off + nr + 1);
+                PG_CUDA(cudaMemcpyAsync(d_off, offsets + r0, (nr + 1) * 8, cudaMemcpyHostToDevice, stx));
+                // kernels index bases with absolute offsets: shift the base pointer
+                rc2 = launch_sketch_ragged(d_in - beg, d_off, nr, maxlen, k, s, dev_flags, d_out, dev_stride, d_count, d_status, stx);
+            }
+            if (rc2 != PG_OK) return rc2;
+            if (dev_stride) {
+                if (stage_out) {
+                    if ((rc2 = cx->pin_out[slot].reserve(nr * dev_stride * 4)) != PG_OK) return rc2;
+                    PG_CUDA(cudaMemcpyAsync(cx->pin_out[slot].p, d_out, nr * dev_stride * 4, cudaMemcpyDeviceToHost, stx));
+                } else if (row_stride == dev_stride) {
+                    PG_CUDA(cudaMemcpyAsync(out + r0 * row_stride, d_out, nr * dev_stride * 4, cudaMemcpyDeviceToHost, stx));
+                } else {
+                    PG_CUDA(cudaMemcpy2DAsync(out + r0 * row_stride, row_stride * 4, d_out, dev_stride * 4, dev_stride * 4, nr, cudaMemcpyDeviceToHost, stx));
+                }
+            }
+            if (count) {
+                if (uniform) {
+                    for (uint64_t i = 0; i < nr; ++i) count[r0 + i] = (uint32_t)cnt_max;
+                } else {
+                    PG_CUDA(cudaMemcpyAsync(count + r0, d_count, nr * 4, cudaMemcpyDeviceToHost, stx));
+                }
+            }
+            if (want_status) PG_CUDA(cudaMemcpyAsync(st_slot[slot].data(), d_status, nr * 4, cudaMemcpyDeviceToHost, stx));
+            pend[slot] = {r0, nr, dev_stride, true};
+            slot = (slot + 1) % N_SLOTS;
+            r0 = r1;
         }
-        if (want_status) PG_CUDA(cudaMemcpyAsync(st_slot[slot].data(), d_status, nr * 4, cudaMemcpyDeviceToHost, stx));
-        pend[slot] = {r0, nr, true};
-        slot = (slot + 1) % 3;
-        r0 = r1;
+        for (int i = 0; i < N_SLOTS; ++i) {
+            const int rc2 = drain((slot + i) % N_SLOTS);  // oldest first
+            if (rc2 != PG_OK) return rc2;
+        }
+        return PG_OK;
+    };
+    rc = body();
+    if (rc != PG_OK) {  // nothing may still be copying into the caller's (or this frame's) buffers when we return
+        for (int i = 0; i < N_SLOTS; ++i) cudaStreamSynchronize(cx->streams[i]);
+        cudaGetLastError();
+        return rc;
     }
-    for (int i = 0; i < 3; ++i)
-        if ((rc = drain(i)) != PG_OK) return rc;
     if (any_panic) {
         set_error("at least one read hits an input on which mash.Sketch panics (sketchSize <= 1)");
         return PG_ERR_PANIC;

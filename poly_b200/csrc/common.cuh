@@ -114,6 +114,12 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
                     int64_t *d_score, int32_t *d_err, int64_t *d_errpos, uint8_t *d_align_a,
                     uint8_t *d_align_b, uint64_t out_stride, uint32_t *d_len, int32_t *d_status,
                     cudaStream_t st, int global = 0);
+// sw_align_long.cu (both strings longer than 64 symbols: full matrix in HBM)
+int launch_sw_align_long(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uint64_t max_qlen, const uint8_t *d_t,
+                         uint64_t tlen, int query_is_a, const int16_t *lut_a, const int16_t *lut_b, const int64_t *table,
+                         int n_a, int n_b, int64_t gap, const int64_t *d_score, const int32_t *d_err, uint8_t *d_align_a,
+                         uint8_t *d_align_b, uint64_t out_stride, uint32_t *d_len, int32_t *d_status, cudaStream_t st,
+                         int global);
 // tm.cu
 int launch_tm(const uint8_t *d_bases, const uint64_t *d_off, uint64_t n, double cp, double na,
               double mg, double *d_tm, double *d_dh, double *d_ds, int32_t *d_status,

@@ -254,9 +254,12 @@ int launch_sw_align(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
                     uint8_t *d_align_b, uint64_t out_stride, uint32_t *d_len, int32_t *d_status,
                     cudaStream_t st, int global) {
     if (nq == 0) return PG_OK;
-    if (max_qlen > 64) {
-        set_error("aligned strings are implemented for queries of <= 64 symbols (got %llu)", (unsigned long long)max_qlen);
-        return PG_ERR_UNSUPPORTED;
+    if (max_qlen > 64) {  // both strings may be long: whole matrix in HBM, literal traceback (sw_align_long.cu)
+        int rc = launch_sw_score(d_q, d_qoff, nq, max_qlen, d_t, tlen, query_is_a, lut_a, lut_b, table, n_a, n_b, gap,
+                                 d_score, d_err, d_errpos, st, global);
+        if (rc != PG_OK) return rc;
+        return launch_sw_align_long(d_q, d_qoff, nq, max_qlen, d_t, tlen, query_is_a, lut_a, lut_b, table, n_a, n_b, gap, d_score,
+                                    d_err, d_align_a, d_align_b, out_stride, d_len, d_status, st, global);
     }
     int64_t amax = 0;
     for (int i = 0; i < n_a * n_b; ++i) amax = std::max<int64_t>(amax, table[i] < 0 ? -table[i] : table[i]);

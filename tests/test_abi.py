@@ -55,7 +55,7 @@ def test_no_cpu_fallback_fails_loudly():
     with pytest.raises(_lib.PolyError):
         primers.MeltingTemp("GTAAAACGACGGCCAGT")
     with pytest.raises(_lib.PolyError):
-        align.SmithWaterman("GATTACA", "GCATGCU", align.NewScoring(None, -1))
+        align.SmithWatermanScore("GATTACA", "GCATGCU", align.NewScoring(None, -1))
     with pytest.raises(_lib.PolyError):
         mash.sketch_uniform(np.zeros(150 * 32, np.uint8), 32, 150, 21, 1000)
 

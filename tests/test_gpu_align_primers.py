@@ -23,24 +23,24 @@ SC = _make_scoring()
 
 def test_reference_TestSmithWaterman(gpu):
     """search/align/align_test.go:139-292 (scores)."""
-    assert align.SmithWaterman("TGTTACGG", "GGTTGACTA", SC) == 13
-    assert align.SmithWaterman("ACACACTA", "AGCACACA", SC) == 17
-    assert align.SmithWaterman("", "GAT", SC) == 0
-    assert align.SmithWaterman("", "", SC) == 0
-    assert align.SmithWaterman("G", "A", SC) == 0
-    assert align.SmithWaterman("G", "G", SC) == 3
-    assert align.SmithWaterman("G", "GATTACA", SC) == 3
+    assert align.SmithWatermanScore("TGTTACGG", "GGTTGACTA", SC) == 13
+    assert align.SmithWatermanScore("ACACACTA", "AGCACACA", SC) == 17
+    assert align.SmithWatermanScore("", "GAT", SC) == 0
+    assert align.SmithWatermanScore("", "", SC) == 0
+    assert align.SmithWatermanScore("G", "A", SC) == 0
+    assert align.SmithWatermanScore("G", "G", SC) == 3
+    assert align.SmithWatermanScore("G", "GATTACA", SC) == 3
 
 
 def test_reference_examples(gpu):
     """search/align/example_test.go:49-111."""
     a5 = align.NewAlphabet(["A", "C", "G", "T", "U"])
     sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, 2 * np.eye(5, dtype=np.int64) - 1), -1)
-    assert align.SmithWaterman("GATTACA", "GCATGCU", sc) == 2
+    assert align.SmithWatermanScore("GATTACA", "GCATGCU", sc) == 2
     an = align.NewAlphabet(["A", "C", "G", "T", "-"])
     sc = align.NewScoring(align.NewSubstitutionMatrix(an, an, align.NUC_4), -1)
-    assert align.SmithWaterman("GATTACA", "GCATGCT", sc) == 15  # literal index mapping, not 17
-    assert align.SmithWaterman("GATTACA", "GCATGCU", align.NewScoring(None, -1)) == 2  # matrix.Default
+    assert align.SmithWatermanScore("GATTACA", "GCATGCT", sc) == 15  # literal index mapping, not 17
+    assert align.SmithWatermanScore("GATTACA", "GCATGCU", align.NewScoring(None, -1)) == 2  # matrix.Default
 
 
 def test_sw_errors_match_reference_order(gpu, oracle):
@@ -55,7 +55,7 @@ def test_sw_errors_match_reference_order(gpu, oracle):
                 bad = (a if w[3] == 1 else b)[w[4]]
                 assert scores[0] == 0 and str(errs[0]) == f"Symbol {bad} not in alphabet"
     with pytest.raises(align.AlphabetError, match="Symbol X not in alphabet"):
-        align.SmithWaterman("ACGT", "ACGX", SC)
+        align.SmithWatermanScore("ACGT", "ACGX", SC)
 
 
 @pytest.mark.parametrize("maxq,tlen", [(25, 10000), (32, 777), (33, 500), (64, 9000), (65, 300), (200, 1000)])
@@ -159,9 +159,9 @@ def test_reference_TestNeedlemanWunsch(gpu):
     sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, 2 * np.eye(5, dtype=np.int64) - 1), -1)
     for a, b, want in [("GATTACA", "GCATGCU", 0), ("GATTACA", "GATTACA", 7), ("GATTACA", "GAT", -1), ("", "GAT", -3), ("", "", 0),
                        ("G", "A", -1), ("G", "G", 1), ("G", "GATTACA", -5), ("GAT", "", -3)]:
-        assert align.NeedlemanWunsch(a, b, sc) == want, (a, b)
+        assert align.NeedlemanWunschScore(a, b, sc) == want, (a, b)
     with pytest.raises(align.AlphabetError, match="Symbol X not in alphabet"):
-        align.NeedlemanWunsch("GATX", "GAT", sc)
+        align.NeedlemanWunschScore("GATX", "GAT", sc)
 
 
 @pytest.mark.parametrize("maxq,tlen", [(25, 3000), (40, 9000), (64, 500), (150, 400)])
@@ -311,3 +311,40 @@ def test_nw_align_batch_vs_oracle(gpu, oracle, maxq, tlen, gap):
             a, b = (qs[i], t) if query_is_a else (t, qs[i])
             w = oracle.nw_align(a, b, TEST_LUT, TEST_LUT, TEST_MAT, gap)
             assert res[i][3] is None and (res[i][0], res[i][1].encode(), res[i][2].encode()) == (w[0], w[1], w[2]), (i, query_is_a)
+
+
+def test_reference_return_shape_and_long_pairs(gpu, oracle):
+    """align.SmithWaterman / NeedlemanWunsch return (score, alignA, alignB, err) like the reference
+    (align.go:100,171); pairs with BOTH strings longer than 64 symbols keep the whole matrix in HBM
+    (sw_align_long.cu) and must give the oracle's strings, including the first-maximum rule and the
+    diagonal > up > left preference."""
+    assert align.SmithWaterman("TGTTACGG", "GGTTGACTA", SC) == (13, "GTT-AC", "GTTGAC", None)
+    sc5 = align.NewScoring(None, -1)
+    assert align.NeedlemanWunsch("GATTACA", "GATTACA", sc5) == (7, "GATTACA", "GATTACA", None)
+    score, a, b, err = align.SmithWaterman("ACGT", "ACGX", SC)
+    assert (score, a, b) == (0, "", "") and str(err) == "Symbol X not in alphabet"
+    rng = np.random.default_rng(64)
+    ALPHA = align.NewAlphabet(["-", "A", "C", "G", "T"])
+    MAT = TEST_MAT
+    lut = ALPHA.byte_lut()
+    mat = np.array(MAT, dtype=np.int64)
+    for la, lb in [(65, 65), (70, 300), (300, 70), (257, 1000), (1000, 999), (129, 65)]:
+        base = rng.choice(list(b"ACGT"), size=max(la, lb) + 50).astype(np.uint8)
+        a = bytes(base[:la])
+        mut = base[10: 10 + lb].copy()
+        flip = rng.random(lb) < 0.08
+        mut[flip] = rng.choice(list(b"ACGT"), size=int(flip.sum()))
+        b = bytes(np.delete(mut, rng.integers(0, lb, 3)))            # a few deletions -> gaps in the alignment
+        for gap in (-2, -5):
+            scg = align.NewScoring(align.NewSubstitutionMatrix(ALPHA, ALPHA, MAT), gap)
+            w = oracle.sw_align(a, b, lut, lut, mat, gap)
+            assert align.SmithWaterman(a, b, scg) == (w[0], w[1].decode(), w[2].decode(), None), (la, lb, gap)
+            w = oracle.nw_align(a, b, lut, lut, mat, gap)
+            assert align.NeedlemanWunsch(a, b, scg) == (w[0], w[1].decode(), w[2].decode(), None), (la, lb, gap)
+    # ties everywhere: homopolymers (first maximum in row-major order, diagonal preference)
+    a, b = b"A" * 100, b"A" * 90
+    w = oracle.sw_align(a, b, lut, lut, mat, -2)
+    assert align.SmithWaterman(a, b, SC) == (w[0], w[1].decode(), w[2].decode(), None)
+    # an error in a long pair: same (0, "", "", err) as the reference
+    score, sa, sb, err = align.SmithWaterman(b"ACGT" * 30 + b"N", b"ACGT" * 40, SC)
+    assert (score, sa, sb) == (0, "", "") and str(err) == "Symbol N not in alphabet"
