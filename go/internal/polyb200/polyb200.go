@@ -367,3 +367,30 @@ func FindSites(seqs []byte, seqOff []uint64, patterns []byte, patOff []uint64) (
 		return sites, nil
 	}
 }
+
+// FastqIngestRecords wraps pg_fastq_ingest_records: dense sequences + offsets, and per record the
+// spans {identifier line begin, length, quality line begin, length} into text.
+func FastqIngestRecords(text []byte) (bases []byte, offsets []uint64, spans []uint64, errCode int32, errLine uint64, err error) {
+	newlines := 0
+	for _, c := range text {
+		if c == '\n' {
+			newlines++
+		}
+	}
+	capRec := newlines/4 + 1
+	bases = make([]byte, len(text)+1)
+	offsets = make([]uint64, capRec+1)
+	spans = make([]uint64, 4*(capRec+1))
+	var n, total C.uint64_t
+	var code C.int32_t
+	var line C.uint64_t
+	var tp *C.uint8_t
+	if len(text) > 0 {
+		tp = (*C.uint8_t)(unsafe.Pointer(&text[0]))
+	}
+	err = locked(func() C.int {
+		return C.pg_fastq_ingest_records(tp, C.uint64_t(len(text)), (*C.uint8_t)(unsafe.Pointer(&bases[0])), C.uint64_t(len(bases)),
+			(*C.uint64_t)(unsafe.Pointer(&offsets[0])), (*C.uint64_t)(unsafe.Pointer(&spans[0])), C.uint64_t(capRec), &n, &total, &code, &line)
+	})
+	return bases[:total], offsets[:n+1], spans[:4*n], int32(code), uint64(line), err
+}

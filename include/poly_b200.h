@@ -310,6 +310,18 @@ int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
                         uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream);
 
+/* The same plus what fastq.Fastq holds besides the sequence (io/fastq/fastq.go:46-51): for record i
+ * spans[4i .. 4i+3] = {begin, length of the identifier line (with its '@', without the newline),
+ * begin, length of the quality line} as offsets into `text`.  The caller cuts Identifier
+ * (strings.Split(line, " ")[0][1:], fastq.go:158), Optionals (the "key=value" tokens, fastq.go:159-165)
+ * and Quality (fastq.go:199) out of the text it already holds: no second copy of the text is made. */
+int pg_fastq_ingest_records(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
+                            uint64_t *offsets, uint64_t *spans, uint64_t records_cap, uint64_t *n_records,
+                            uint64_t *total_bases, int32_t *err_code, uint64_t *err_line);
+int pg_fastq_ingest_records_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                                uint64_t *d_offsets, uint64_t *d_spans, uint64_t records_cap, uint64_t *n_records,
+                                uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream);
+
 /* ---- FASTA ingest -- fasta.Parse = NewParser(r, maxLineSize).ParseAll(),
  * io/fasta/fasta.go:72-77,96-118,149-243 -----------------------------------------
  * Parses a whole FASTA text buffer on the GPU into dense sequences + offsets and (optionally:

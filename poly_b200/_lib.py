@@ -76,6 +76,8 @@ _SIGS = {
     "pg_find_sites_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, _u8p, _u64p, C.c_uint32, C.c_uint32, _u32p, _u64p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pg_fastq_ingest": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "pg_fastq_ingest_dev": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p]),
+    "pg_fastq_ingest_records": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, _u64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
+    "pg_fastq_ingest_records_dev": (C.c_int, [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p, _u64p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p]),
     "pg_fasta_ingest": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_uint32, _u8p, C.c_uint64, _u64p, _u8p, C.c_uint64, _u64p, C.c_uint64,
                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "pg_fasta_ingest_dev": (C.c_int, [_u8p, C.c_uint64, C.c_uint32, C.c_uint32, _u8p, C.c_uint64, _u64p, _u8p, C.c_uint64, _u64p, C.c_uint64,

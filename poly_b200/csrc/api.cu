@@ -1401,35 +1401,60 @@ int pg_find_sites_batch(const uint8_t *seqs, const uint64_t *seq_offsets, uint64
     return PG_OK;
 }
 
-int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
-                        uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
-                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream) {
+static int fastq_ingest_dev_impl(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                                 uint64_t *d_offsets, uint64_t *d_spans, uint64_t records_cap, uint64_t *n_records,
+                                 uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream) {
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
     if (!n_records || !total_bases || !err_code || !err_line || !d_offsets) { set_error("null buffer"); return PG_ERR_ARG; }
     return launch_fastq_ingest(d_text, nbytes, d_bases, bases_cap, d_offsets, records_cap, n_records, total_bases, err_code,
-                               err_line, (cudaStream_t)stream);
+                               err_line, (cudaStream_t)stream, d_spans);
 }
 
-int pg_fastq_ingest(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
-                    uint64_t *offsets, uint64_t records_cap, uint64_t *n_records,
-                    uint64_t *total_bases, int32_t *err_code, uint64_t *err_line) {
+static int fastq_ingest_host_impl(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
+                                  uint64_t *offsets, uint64_t *spans, uint64_t records_cap, uint64_t *n_records,
+                                  uint64_t *total_bases, int32_t *err_code, uint64_t *err_line) {
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
     if (!n_records || !total_bases || !err_code || !err_line || !offsets) { set_error("null buffer"); return PG_ERR_ARG; }
     std::lock_guard<std::mutex> lk(t_ctx->mu);
     cudaStream_t st = t_ctx->streams[0];
-    Tmp d_text(st), d_bases(st), d_off(st);
+    Tmp d_text(st), d_bases(st), d_off(st), d_spans(st);
     if ((rc = d_text.alloc(nbytes + 16)) || (rc = d_bases.alloc(bases_cap + 16)) || (rc = d_off.alloc((records_cap + 1) * 8)))
         return rc;
+    if (spans && (rc = d_spans.alloc((records_cap + 1) * 32))) return rc;
     if (nbytes) PG_CUDA(cudaMemcpyAsync(d_text.p, text, nbytes, cudaMemcpyHostToDevice, st));
     rc = launch_fastq_ingest(d_text.as<uint8_t>(), nbytes, d_bases.as<uint8_t>(), bases_cap, d_off.as<uint64_t>(), records_cap,
-                             n_records, total_bases, err_code, err_line, st);
+                             n_records, total_bases, err_code, err_line, st, spans ? d_spans.as<uint64_t>() : nullptr);
     if (rc != PG_OK) return rc;
     if (*total_bases) PG_CUDA(cudaMemcpyAsync(bases, d_bases.p, *total_bases, cudaMemcpyDeviceToHost, st));
     PG_CUDA(cudaMemcpyAsync(offsets, d_off.p, (*n_records + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (spans && *n_records) PG_CUDA(cudaMemcpyAsync(spans, d_spans.p, *n_records * 32, cudaMemcpyDeviceToHost, st));
     PG_CUDA(cudaStreamSynchronize(st));
     return PG_OK;
+}
+
+int pg_fastq_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                        uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream) {
+    return fastq_ingest_dev_impl(d_text, nbytes, d_bases, bases_cap, d_offsets, nullptr, records_cap, n_records, total_bases, err_code, err_line, stream);
+}
+int pg_fastq_ingest_records_dev(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
+                                uint64_t *d_offsets, uint64_t *d_spans, uint64_t records_cap, uint64_t *n_records,
+                                uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, void *stream) {
+    if (!d_spans) { set_error("null spans"); return PG_ERR_ARG; }
+    return fastq_ingest_dev_impl(d_text, nbytes, d_bases, bases_cap, d_offsets, d_spans, records_cap, n_records, total_bases, err_code, err_line, stream);
+}
+int pg_fastq_ingest(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
+                    uint64_t *offsets, uint64_t records_cap, uint64_t *n_records,
+                    uint64_t *total_bases, int32_t *err_code, uint64_t *err_line) {
+    return fastq_ingest_host_impl(text, nbytes, bases, bases_cap, offsets, nullptr, records_cap, n_records, total_bases, err_code, err_line);
+}
+int pg_fastq_ingest_records(const uint8_t *text, uint64_t nbytes, uint8_t *bases, uint64_t bases_cap,
+                            uint64_t *offsets, uint64_t *spans, uint64_t records_cap, uint64_t *n_records,
+                            uint64_t *total_bases, int32_t *err_code, uint64_t *err_line) {
+    if (!spans) { set_error("null spans"); return PG_ERR_ARG; }
+    return fastq_ingest_host_impl(text, nbytes, bases, bases_cap, offsets, spans, records_cap, n_records, total_bases, err_code, err_line);
 }
 
 int pg_fasta_ingest_dev(const uint8_t *d_text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags,

@@ -136,7 +136,8 @@ int launch_find_sites(const uint8_t *d_seqs, const uint64_t *d_seq_off, uint64_t
 // fastq_ingest.cu
 int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
-                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st);
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st,
+                        uint64_t *d_spans = nullptr);
 // fasta_ingest.cu
 int launch_fasta_ingest(const uint8_t *d_text, uint64_t nbytes, uint32_t max_line_size, uint32_t flags,
                         uint8_t *d_bases, uint64_t bases_cap, uint64_t *d_offsets, uint8_t *d_names,

@@ -35,13 +35,14 @@ enum : int32_t {
 __global__ void __launch_bounds__(256)
 record_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__restrict__ nl, uint64_t n_lines,
               uint64_t n_cand, uint32_t *__restrict__ seq_len, uint64_t *__restrict__ seq_start,
-              int32_t *__restrict__ rec_err, uint32_t *__restrict__ rec_err_line, unsigned long long *__restrict__ first_bad) {
+              int32_t *__restrict__ rec_err, uint32_t *__restrict__ rec_err_line, unsigned long long *__restrict__ first_bad,
+              uint64_t *__restrict__ spans) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_cand) return;
     auto line_begin = [&](uint64_t li) -> uint64_t { return li == 0 ? 0 : nl[li - 1] + 1; };
     int32_t err = FQ_OK;
     uint32_t err_line = 0;
-    uint64_t s_beg = 0, s_len = 0;
+    uint64_t s_beg = 0, s_len = 0, id_beg = 0, id_len = 0, q_beg = 0, q_len = 0;
     bool no_at = false;
     for (int l = 0; l < 4 && err == FQ_OK; ++l) {
         const uint64_t li = 4 * r + l;
@@ -55,6 +56,8 @@ record_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__re
         if (l == 0) {
             if (e == b) { err = FQ_ERR_PANIC; err_line = 1; break; }  // string(line)[0] on ""
             no_at = __ldg(text + b) != '@';
+            id_beg = b;
+            id_len = e - b;
             // strings.Split(line, " ")[1:]: every datum (also an empty one) must hold '=' (optionalSplits[1])
             uint32_t token = 0;
             bool has_eq = false;
@@ -74,6 +77,8 @@ record_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__re
             s_len = e - b;
         } else if (l == 3) {
             if (e == b) { err = FQ_ERR_EMPTY_QUAL; err_line = 4; break; }
+            q_beg = b;
+            q_len = e - b;
         }
     }
     if (err == FQ_OK && no_at) { err = FQ_ERR_NO_AT; err_line = 4; }
@@ -81,6 +86,10 @@ record_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__re
     seq_start[r] = s_beg;
     rec_err[r] = err;
     rec_err_line[r] = err_line;
+    if (spans) {  // identifier line (with its '@', without the newline) and quality line of the record, as text spans
+        spans[4 * r + 0] = id_beg; spans[4 * r + 1] = id_len;
+        spans[4 * r + 2] = q_beg;  spans[4 * r + 3] = q_len;
+    }
     if (err != FQ_OK) atomicMin(first_bad, (unsigned long long)r);
 }
 
@@ -105,7 +114,7 @@ copy_sequences_kernel(const uint8_t *__restrict__ text, const uint64_t *__restri
 // (*n_records / *total_bases then hold the required sizes).
 int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases, uint64_t bases_cap,
                         uint64_t *d_offsets, uint64_t records_cap, uint64_t *n_records,
-                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st) {
+                        uint64_t *total_bases, int32_t *err_code, uint64_t *err_line, cudaStream_t st, uint64_t *d_spans) {
     *n_records = 0; *total_bases = 0; *err_code = FQ_OK; *err_line = 0;
     if (nbytes == 0) {
         if (records_cap + 1 >= 1 && d_offsets) PG_CUDA(cudaMemsetAsync(d_offsets, 0, 8, st));
@@ -123,7 +132,7 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
     const uint64_t n_cand = n_lines / 4 + ((n_lines % 4 != 0 || trailing) ? 1 : 0);
     int rc = PG_OK;
     uint32_t *d_len = nullptr, *d_eline = nullptr;
-    uint64_t *d_sstart = nullptr, *d_off_tmp = nullptr;
+    uint64_t *d_sstart = nullptr, *d_off_tmp = nullptr, *d_span_tmp = nullptr;
     int32_t *d_err = nullptr;
     unsigned long long *d_first = nullptr;
     if (n_cand) {
@@ -133,8 +142,9 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
         PG_CUDA(tmp.alloc(&d_err, n_cand));
         PG_CUDA(tmp.alloc(&d_first, 1));
         PG_CUDA(cudaMemsetAsync(d_first, 0xff, 8, st));
+        if (d_spans) PG_CUDA(tmp.alloc(&d_span_tmp, 4 * n_cand));
         record_kernel<<<(unsigned)((n_cand + 255) / 256), 256, 0, st>>>(d_text, nbytes, d_nl, n_lines, n_cand, d_len, d_sstart,
-                                                                       d_err, d_eline, d_first);
+                                                                       d_err, d_eline, d_first, d_span_tmp);
         note_launch("record_kernel");
         unsigned long long first_bad = ~0ull;
         PG_CUDA(cudaMemcpyAsync(&first_bad, d_first, 8, cudaMemcpyDeviceToHost, st));
@@ -167,6 +177,7 @@ int launch_fastq_ingest(const uint8_t *d_text, uint64_t nbytes, uint8_t *d_bases
                 rc = PG_ERR_ARG;
             } else {
                 PG_CUDA(cudaMemcpyAsync(d_offsets, d_off_tmp, (n_ok + 1) * 8, cudaMemcpyDeviceToDevice, st));
+                if (d_spans && n_ok) PG_CUDA(cudaMemcpyAsync(d_spans, d_span_tmp, n_ok * 32, cudaMemcpyDeviceToDevice, st));
                 if (n_ok) {
                     const unsigned blocks = (unsigned)std::min<uint64_t>((n_ok + 7) / 8, (uint64_t)sm_count() * 16);
                     copy_sequences_kernel<<<blocks, 256, 0, st>>>(d_text, d_sstart, d_off_tmp, n_ok, d_bases);

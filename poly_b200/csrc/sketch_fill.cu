@@ -40,10 +40,10 @@ __host__ __device__ inline uint32_t k1_in_bytes(uint32_t R, uint32_t L) {
 
 // lut_stride == 4 arrives as a kernel argument so that the table address byte*4 + base
 // stays an IMAD (FMA pipe) instead of being strength-reduced to LEA (ALU pipe).
-template <int K, int R>
+template <int K, int R, int ROTF = 0>
 __global__ void __launch_bounds__(R)
 sketch_fill_uniform_kernel(const uint8_t *__restrict__ bases, const SketchDst dst,
-                           uint32_t L, uint32_t nk, uint32_t lut_stride) {
+                           uint32_t L, uint32_t nk, uint32_t lut_stride, uint32_t rotmul) {
     constexpr int NB = K / 4;    // 4-byte body blocks per k-mer
     constexpr int TAIL = K % 4;  // tail bytes per k-mer
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
@@ -154,6 +154,8 @@ sketch_fill_ragged_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     constexpr int TAIL = K % 4;
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
     constexpr bool LUT = TAIL == 1;
+    constexpr int ROTF = 0;
+    const uint32_t rotmul = 0;
     static_assert(NB >= 1, "fast path needs k >= 4");
 
     extern __shared__ __align__(128) uint8_t smem[];
@@ -287,12 +289,12 @@ sketch_fill_generic_kernel(const uint8_t *__restrict__ bases, const uint64_t *__
 }
 
 // ---- launchers -------------------------------------------------------------------
-template <int K, int R>
+template <int K, int R, int ROTF = 0>
 static int launch_k1(const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
                      const SketchDst &dst, cudaStream_t st) {
     const size_t smem = (size_t)(R / 32) * (k1_in_bytes(32, L) + (size_t)32 * nk * 4);
-    { const int rc_ = func_smem((const void *)sketch_fill_uniform_kernel<K, R>, smem); if (rc_ != PG_OK) return rc_; }
-    sketch_fill_uniform_kernel<K, R><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, dst, L, nk, 4u);
+    { const int rc_ = func_smem((const void *)sketch_fill_uniform_kernel<K, R, ROTF>, smem); if (rc_ != PG_OK) return rc_; }
+    sketch_fill_uniform_kernel<K, R, ROTF><<<(unsigned)n_tiles, R, smem, st>>>(d_bases, dst, L, nk, 4u, 8192u);
     PG_LAUNCH_CHECK("sketch_fill_uniform_kernel");
     return PG_OK;
 }
@@ -301,6 +303,16 @@ template <int R>
 static int dispatch_k1(int k, const uint8_t *d_bases, uint64_t n_tiles, uint32_t L, uint32_t nk,
                        const SketchDst &dst, cudaStream_t st, bool *handled) {
     *handled = true;
+    // A/B knob: PG_K1_ROTFMA=n moves the rotate of the first n body rounds to the FMA pipe (k = 21 only)
+    static const int rotf = [] { const char *e = getenv("PG_K1_ROTFMA"); return e ? atoi(e) : 0; }();
+    if (k == 21 && R == 32 && rotf > 0) {
+        switch (rotf) {
+            case 1: return launch_k1<21, 32, 1>(d_bases, n_tiles, L, nk, dst, st);
+            case 2: return launch_k1<21, 32, 2>(d_bases, n_tiles, L, nk, dst, st);
+            case 3: return launch_k1<21, 32, 3>(d_bases, n_tiles, L, nk, dst, st);
+            default: return launch_k1<21, 32, 5>(d_bases, n_tiles, L, nk, dst, st);
+        }
+    }
     switch (k) {
 #define PG_K1_CASE(KK) \
     case KK: return launch_k1<KK, R>(d_bases, n_tiles, L, nk, dst, st);

@@ -417,6 +417,8 @@ sketch_select_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
     constexpr bool LUT = TAIL == 1;
     constexpr uint32_t k = K;
+    constexpr int ROTF = 0;
+    const uint32_t rotmul = 0;
     static_assert(NB >= 1 && K <= 32, "walk path: 4 <= k <= 32");
     static_assert(SELW_SEG % 4 == 0, "a segment is a whole number of word steps");
 
@@ -742,6 +744,8 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
     constexpr bool LUT = TAIL == 1;
     constexpr uint32_t k = K;
+    constexpr int ROTF = 0;
+    const uint32_t rotmul = 0;
     static_assert(NB >= 1 && K <= 32, "walk path: 4 <= k <= 32");
 
     extern __shared__ __align__(128) uint8_t smem[];  // 2 stage buffers | strip [SELT_SEG][32]

@@ -2,12 +2,16 @@
 
 Mirrors the record structure and the failure behaviour of io/fastq Parser.ParseNext / ParseN
 (/root/reference/io/fastq/fastq.go:88-99,117-214): strict 4-line records, the valid prefix is
-returned together with the first error.  Only the sequences are materialised.  SURVEY.md 8f.2.
+returned together with the first error.  `ingest` materialises only the sequences (what the sketch
+path needs); `Parse` returns the reference's records (Identifier, Optionals, Sequence, Quality) -- the
+sequences from the dense GPU output, the other three cut out of the caller's text with the line spans
+the kernel reports.  SURVEY.md 8f.2.
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -37,3 +41,36 @@ def ingest(text: bytes) -> Tuple[np.ndarray, np.ndarray, Optional[FastqError]]:
                                           C.byref(n), C.byref(tot), C.byref(ec), C.byref(el)))
     err = FastqError(ec.value, el.value) if ec.value else None
     return bases[: tot.value], offsets[: n.value + 1], err
+
+
+@dataclass
+class Fastq:
+    """fastq.Fastq (io/fastq/fastq.go:46-51)."""
+    Identifier: str = ""
+    Optionals: Dict[str, str] = field(default_factory=dict)
+    Sequence: str = ""
+    Quality: str = ""
+
+
+def Parse(text: bytes) -> Tuple[List[Fastq], Optional[FastqError]]:
+    """fastq.Parse (fastq.go:54-59): every record up to the first one the reference rejects, and that error."""
+    buf = np.frombuffer(text, dtype=np.uint8)
+    cap_rec = text.count(b"\n") // 4 + 1
+    bases = np.zeros(max(len(text), 1), dtype=np.uint8)
+    offsets = np.zeros(cap_rec + 1, dtype=np.uint64)
+    spans = np.zeros((cap_rec + 1, 4), dtype=np.uint64)
+    n, tot, ec, el = C.c_uint64(0), C.c_uint64(0), C.c_int32(0), C.c_uint64(0)
+    _lib.check(_lib.lib().pg_fastq_ingest_records(buf.ctypes.data if len(text) else None, len(text), bases.ctypes.data, len(bases), offsets.ctypes.data,
+                                                  spans.ctypes.data, cap_rec, C.byref(n), C.byref(tot), C.byref(ec), C.byref(el)))
+    err = FastqError(ec.value, el.value) if ec.value else None
+    out: List[Fastq] = []
+    seqs = bases.tobytes()
+    for i in range(n.value):
+        ib, il, qb, ql = (int(x) for x in spans[i])
+        tokens = text[ib: ib + il].decode("latin-1").split(" ")            # fastq.go:157
+        opts = {}
+        for datum in tokens[1:]:                                            # fastq.go:160-165 (every datum holds '=': checked on the GPU)
+            kv = datum.split("=")
+            opts[kv[0]] = kv[1]
+        out.append(Fastq(tokens[0][1:], opts, seqs[int(offsets[i]): int(offsets[i + 1])].decode("latin-1"), text[qb: qb + ql].decode("latin-1")))
+    return out, err

@@ -48,3 +48,23 @@ def py_parse(text: bytes):
             return seqs, 4, line
         seqs.append(rec[1])
     return seqs, 0, 0
+
+
+def py_parse_records(text: bytes):
+    """fastq.ParseAll with the record fields (io/fastq/fastq.go:46-51,117-214), pure Python:
+    ([(identifier, optionals, sequence, quality)], err_code, err_line)."""
+    seqs, ec, el = py_parse(text)
+    recs, pos = [], 0
+    for _ in range(len(seqs)):
+        lines = []
+        for _l in range(4):
+            q = text.index(b"\n", pos)
+            lines.append(text[pos:q].decode("latin-1"))
+            pos = q + 1
+        splits = lines[0].split(" ")                       # fastq.go:157
+        opts = {}
+        for datum in splits[1:]:
+            kv = datum.split("=")
+            opts[kv[0]] = kv[1]                            # fastq.go:161-164 (a later duplicate key wins, as in a Go map)
+        recs.append((splits[0][1:], opts, lines[1], lines[3]))
+    return recs, ec, el
