@@ -192,6 +192,22 @@ int pg_mash_distance_block_dev(const uint32_t *d_sketches, uint64_t n, int32_t s
                                uint64_t row_begin, uint64_t row_end, uint32_t *d_same,
                                double *d_distance, void *stream);
 
+/* The same row block as (i, j, same) triples of the pairs that share at least one hash: every ordered
+ * pair (i, j), row_begin <= i < row_end, j != i (with PG_PAIRS_UPPER: j > i only), whose matching count is
+ * non-zero, in no particular order.  Pairs that are not listed have same == 0 (Similarity 0, Distance 1,
+ * mash.go:134,139); the diagonal is never listed.  For n sketches this returns O(related pairs) instead of
+ * the n x rows matrix (cfg3: ~5e6 triples = 60 MB instead of 40 GB).  *n_pairs receives the number of
+ * qualifying pairs; PG_ERR_ARG (with the first pairs_cap stored) if it exceeds pairs_cap.  The _dev variant
+ * takes a DEVICE counter d_n_pairs (which may exceed pairs_cap) and never blocks on the result. */
+#define PG_PAIRS_UPPER 1u
+int pg_mash_distance_sparse(const uint32_t *sketches, uint64_t n, int32_t s, uint64_t row_begin,
+                            uint64_t row_end, uint32_t flags, uint32_t *pair_i, uint32_t *pair_j,
+                            uint32_t *pair_same, uint64_t pairs_cap, uint64_t *n_pairs);
+int pg_mash_distance_sparse_dev(const uint32_t *d_sketches, uint64_t n, int32_t s, uint64_t row_begin,
+                                uint64_t row_end, uint32_t flags, uint32_t *d_pair_i, uint32_t *d_pair_j,
+                                uint32_t *d_pair_same, uint64_t pairs_cap, uint64_t *d_n_pairs,
+                                void *stream);
+
 /* ---- align.SmithWaterman score -- search/align/align.go:171-203 -------------------
  * One template against n queries.  query_is_a != 0: stringA = query (outer loop),
  * stringB = template; else swapped.  lut_a/lut_b: byte -> index into the first /

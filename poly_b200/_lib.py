@@ -63,6 +63,8 @@ _SIGS = {
     "pg_mash_similarity_pairs_dev": (C.c_int, [_u32p, _u64p, C.c_uint64, _u32p, _u32p, C.c_uint64, _i64p, _f64p, _f64p, _i32p, C.c_void_p]),
     "pg_mash_distance_block": (C.c_int, [_u32p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _u32p, _f64p]),
     "pg_mash_distance_block_dev": (C.c_int, [_u32p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _u32p, _f64p, C.c_void_p]),
+    "pg_mash_distance_sparse": (C.c_int, [_u32p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "pg_mash_distance_sparse_dev": (C.c_int, [_u32p, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, _u32p, _u32p, _u32p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pg_sw_score_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, _u8p, C.c_uint64, C.c_int32, _i16p, _i16p, _i64p, C.c_int32, C.c_int32, C.c_int64, _i64p, _i32p, _i64p]),
     "pg_sw_score_batch_dev": (C.c_int, [_u8p, _u64p, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, C.c_int32, _i16p, _i16p, _i64p, C.c_int32, C.c_int32, C.c_int64, _i64p, _i32p, _i64p, C.c_void_p]),
     "pg_sw_align_batch": (C.c_int, [_u8p, _u64p, C.c_uint64, _u8p, C.c_uint64, C.c_int32, _i16p, _i16p, _i64p, C.c_int32, C.c_int32, C.c_int64, _i64p, _i32p, _i64p, _u8p, _u8p, C.c_uint64, _u32p, _i32p]),

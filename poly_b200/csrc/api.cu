@@ -1103,6 +1103,52 @@ int pg_mash_distance_block(const uint32_t *sketches, uint64_t n, int32_t s, uint
     return rc;
 }
 
+int pg_mash_distance_sparse_dev(const uint32_t *d_sketches, uint64_t n, int32_t s, uint64_t row_begin, uint64_t row_end, uint32_t flags,
+                                uint32_t *d_pair_i, uint32_t *d_pair_j, uint32_t *d_pair_same, uint64_t pairs_cap, uint64_t *d_n_pairs,
+                                void *stream) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (row_end > n || row_begin > row_end) { set_error("bad row range"); return PG_ERR_ARG; }
+    if (!d_n_pairs || (pairs_cap && (!d_pair_i || !d_pair_j || !d_pair_same))) { set_error("null buffer"); return PG_ERR_ARG; }
+    return launch_distance_sparse(d_sketches, n, s, row_begin, row_end, flags, d_pair_i, d_pair_j, d_pair_same, pairs_cap,
+                                  (unsigned long long *)d_n_pairs, (cudaStream_t)stream);
+}
+
+int pg_mash_distance_sparse(const uint32_t *sketches, uint64_t n, int32_t s, uint64_t row_begin, uint64_t row_end, uint32_t flags,
+                            uint32_t *pair_i, uint32_t *pair_j, uint32_t *pair_same, uint64_t pairs_cap, uint64_t *n_pairs) {
+    int rc = ensure_device();
+    if (rc != PG_OK) return rc;
+    if (!n_pairs) { set_error("null buffer"); return PG_ERR_ARG; }
+    *n_pairs = 0;
+    if (row_end > n || row_begin > row_end) { set_error("bad row range"); return PG_ERR_ARG; }
+    if (row_end == row_begin || n == 0) return PG_OK;
+    if (s <= 0) { set_error("distance over sketches of size %d: the reference panics", s); return PG_ERR_PANIC; }
+    if (pairs_cap && (!pair_i || !pair_j || !pair_same)) { set_error("null buffer"); return PG_ERR_ARG; }
+    std::lock_guard<std::mutex> lk(t_ctx->mu);
+    cudaStream_t st = t_ctx->streams[0];
+    Tmp d_sk(st), d_i(st), d_j(st), d_c(st), d_n(st);
+    if ((rc = d_sk.alloc(n * (uint64_t)s * 4)) || (rc = d_i.alloc(pairs_cap * 4)) || (rc = d_j.alloc(pairs_cap * 4)) ||
+        (rc = d_c.alloc(pairs_cap * 4)) || (rc = d_n.alloc(8)))
+        return rc;
+    PG_CUDA(cudaMemcpyAsync(d_sk.p, sketches, n * (uint64_t)s * 4, cudaMemcpyHostToDevice, st));
+    rc = launch_distance_sparse(d_sk.as<uint32_t>(), n, s, row_begin, row_end, flags, d_i.as<uint32_t>(), d_j.as<uint32_t>(), d_c.as<uint32_t>(),
+                                pairs_cap, d_n.as<unsigned long long>(), st);
+    if (rc != PG_OK) return rc;
+    unsigned long long found = 0;
+    PG_CUDA(cudaMemcpyAsync(&found, d_n.p, 8, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    *n_pairs = found;
+    const uint64_t kept = std::min<uint64_t>(found, pairs_cap);
+    if (kept) {
+        PG_CUDA(cudaMemcpyAsync(pair_i, d_i.p, kept * 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(pair_j, d_j.p, kept * 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaMemcpyAsync(pair_same, d_c.p, kept * 4, cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+    }
+    if (found > pairs_cap) { set_error("pairs_cap %llu < %llu pairs", (unsigned long long)pairs_cap, found); return PG_ERR_ARG; }
+    return PG_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // Smith-Waterman score
 // ---------------------------------------------------------------------------------

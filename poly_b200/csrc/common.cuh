@@ -80,6 +80,9 @@ int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_
                             cudaStream_t st);
 int launch_distance_block(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin,
                           uint64_t row_end, uint32_t *d_same, double *d_dist, cudaStream_t st);
+int launch_distance_sparse(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin, uint64_t row_end, uint32_t flags,
+                           uint32_t *d_i, uint32_t *d_j, uint32_t *d_same, uint64_t cap, unsigned long long *d_n_pairs,
+                           cudaStream_t st);
 // distance_join.cu (ascending sketches only): bucketed (value, id) index, built once per sketch
 // set and reused for every row block
 struct JoinIndex {

@@ -190,7 +190,74 @@ __global__ void sorted_flag_kernel(const uint32_t *__restrict__ sk, uint64_t n, 
     }
 }
 
+// dense row-block tile -> (i, j, same) triples of the non-zero off-diagonal entries
+__global__ void __launch_bounds__(256)
+compact_pairs_kernel(const uint32_t *__restrict__ tile, uint64_t rows, uint64_t n, uint64_t row0, uint32_t upper,
+                     uint32_t *__restrict__ oi, uint32_t *__restrict__ oj, uint32_t *__restrict__ osame, uint64_t cap,
+                     unsigned long long *__restrict__ counter) {
+    const uint64_t total = rows * n;
+    const uint32_t lane = threadIdx.x & 31u;
+    // the loop bound is warp-uniform (the ballots below need every lane): a warp covers 128 consecutive words
+    for (uint64_t w0 = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * 4; w0 < total; w0 += (uint64_t)gridDim.x * blockDim.x * 4) {
+        const uint64_t e0 = w0 + lane * 4;
+        uint32_t v[4] = {0, 0, 0, 0};
+        if (e0 + 3 < total && (n & 3) == 0) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(tile + e0);  // rows are 16-byte aligned when n % 4 == 0
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+            for (int t = 0; t < 4; ++t) if (e0 + t < total) v[t] = tile[e0 + t];
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const uint64_t e = e0 + t;
+            const uint64_t i = row0 + (e < total ? e / n : 0), j = e < total ? e % n : 0;
+            const bool keep = e < total && v[t] != 0 && j != i && (!upper || j > i);
+            const uint32_t b = __ballot_sync(0xffffffffu, keep);
+            if (!b) continue;
+            unsigned long long base = 0;
+            if (lane == (uint32_t)(__ffs(b) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(b));
+            base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+            const unsigned long long slot = base + __popc(b & ((1u << lane) - 1u));
+            if (keep && slot < cap) { oi[slot] = (uint32_t)i; oj[slot] = (uint32_t)j; osame[slot] = v[t]; }
+        }
+    }
+}
+
 }  // namespace
+
+// Non-zero off-diagonal matching counts of rows [row_begin, row_end) as (i, j, same) triples: dense tiles of
+// the row block (same kernels as the dense entry point) compacted on the device, so only the informative
+// pairs ever leave the GPU.  *d_n_pairs counts every qualifying pair, also beyond pairs_cap.
+int launch_distance_sparse(const uint32_t *d_sk, uint64_t n, int s, uint64_t row_begin, uint64_t row_end, uint32_t flags,
+                           uint32_t *d_i, uint32_t *d_j, uint32_t *d_same, uint64_t cap, unsigned long long *d_n_pairs,
+                           cudaStream_t st) {
+    PG_CUDA(cudaMemsetAsync(d_n_pairs, 0, 8, st));
+    if (row_end <= row_begin || n == 0) return PG_OK;
+    if (n > 0xffffffffull) { set_error("too many sketches for 32-bit pair indices"); return PG_ERR_ARG; }
+    DistancePlan plan;
+    int rc = distance_plan_create(d_sk, n, s, st, &plan);
+    // tiles of <= 8 GiB: every pass over the index costs one read of all its entries
+    const uint64_t rows_per = std::max<uint64_t>(8, std::min<uint64_t>(row_end - row_begin, ((2ull << 30) / n) & ~7ull));
+    uint32_t *d_tile = nullptr;
+    if (rc == PG_OK) {
+        cudaError_t e = cudaMallocAsync(&d_tile, rows_per * n * 4, st);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMallocAsync(%llu) for the pair tile failed", (unsigned long long)(rows_per * n * 4)); rc = PG_ERR_NOMEM; }
+    }
+    for (uint64_t rb = row_begin; rb < row_end && rc == PG_OK; rb += rows_per) {
+        const uint64_t re = std::min(row_end, rb + rows_per);
+        rc = distance_plan_rows(plan, rb, re, d_tile, nullptr, st);
+        if (rc != PG_OK) break;
+        const uint64_t quads = ((re - rb) * n + 3) / 4;
+        compact_pairs_kernel<<<(unsigned)std::min<uint64_t>((quads + 255) / 256, (uint64_t)sm_count() * 16), 256, 0, st>>>(
+            d_tile, re - rb, n, rb, flags & PG_PAIRS_UPPER, d_i, d_j, d_same, cap, d_n_pairs);
+        note_launch("compact_pairs_kernel");
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "compact_pairs_kernel", __FILE__, __LINE__);
+    }
+    if (d_tile) cudaFreeAsync(d_tile, st);
+    distance_plan_destroy(plan, st);
+    return rc;
+}
 
 int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_t n_sk,
                             const uint32_t *d_a, const uint32_t *d_b, uint64_t n_pairs,

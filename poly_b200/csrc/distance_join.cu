@@ -97,7 +97,36 @@ __global__ void scatter_kernel(const uint32_t *__restrict__ sk, uint64_t total, 
     }
 }
 
-// One CTA per value bucket: sort the bucket's (value, id) keys, then every value run of g >= 2 distinct
+// One CTA per value bucket, once per index: sort the bucket's (value << 32 | id) keys in shared memory and
+// write them back, so that every later row-block pass only loads them.
+__global__ void __launch_bounds__(JOIN_THREADS)
+bucket_sort_kernel(uint64_t *__restrict__ entries, const uint64_t *__restrict__ start, uint32_t nbuckets) {
+    extern __shared__ __align__(16) uint64_t key[];  // [JOIN_CAP]
+    for (uint32_t b = blockIdx.x; b < nbuckets; b += gridDim.x) {
+        const uint64_t lo = start[b];
+        const uint32_t m = (uint32_t)(start[b + 1] - lo);
+        if (m < 2) continue;
+        uint32_t P = 1;
+        while (P < m) P <<= 1;
+        for (uint32_t i = threadIdx.x; i < P; i += JOIN_THREADS) key[i] = i < m ? entries[lo + i] : ~0ull;
+        __syncthreads();
+        for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
+            for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = threadIdx.x; t < (P >> 1); t += JOIN_THREADS) {
+                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
+                    const bool up = (i & k2) == 0;
+                    const uint64_t a = key[i], c = key[ixj];
+                    if ((a > c) == up) { key[i] = c; key[ixj] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) entries[lo + i] = key[i];
+        __syncthreads();
+    }
+}
+
+// One CTA per value bucket: load the bucket's sorted (value, id) keys, then every value run of g >= 2 distinct
 // ids contributes min(c_a, c_b) to same[a][b] for its ordered pairs a != b (the diagonal is s for every
 // ascending sketch and is written by diag_kernel).  Emission is warp-cooperative: for one row a the lanes
 // run ALONG the run, i.e. along row a of the matrix, so the reductions of one instruction fall into
@@ -115,21 +144,8 @@ bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restr
         const uint64_t lo = start[b];
         const uint32_t m = (uint32_t)(start[b + 1] - lo);
         if (m == 0) continue;
-        uint32_t P = 1;
-        while (P < m) P <<= 1;
-        for (uint32_t i = threadIdx.x; i < P; i += JOIN_THREADS) key[i] = i < m ? entries[lo + i] : ~0ull;
+        for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) key[i] = entries[lo + i];  // sorted by bucket_sort_kernel
         __syncthreads();
-        for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
-            for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
-                for (uint32_t t = threadIdx.x; t < (P >> 1); t += JOIN_THREADS) {
-                    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), ixj = i | j;
-                    const bool up = (i & k2) == 0;
-                    const uint64_t a = key[i], c = key[ixj];
-                    if ((a > c) == up) { key[i] = c; key[ixj] = a; }
-                }
-                __syncthreads();
-            }
-        }
         // run bounds and (value, id) multiplicities: the thread at the first position of a value run walks it
         for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) {
             const uint32_t v = (uint32_t)(key[i] >> 32);
@@ -221,6 +237,9 @@ int join_build(const uint32_t *d_sk, uint64_t n, int s, cudaStream_t st, JoinInd
             PG_CUDA(cudaMallocAsync(&d_entries, total * 8, st));
             scatter_kernel<<<sms * 16, 256, 0, st>>>(d_sk, total, (uint32_t)s, d_scalars, (uint32_t)nb, d_start, d_cursor, d_entries);
             note_launch("scatter_kernel");
+            { const int rc_ = func_smem((const void *)bucket_sort_kernel, JOIN_CAP * 8); if (rc_ != PG_OK) return rc_; }
+            bucket_sort_kernel<<<(unsigned)std::min<uint64_t>(nb, (uint64_t)sms * 24), JOIN_THREADS, JOIN_CAP * 8, st>>>(d_entries, d_start, (uint32_t)nb);
+            note_launch("bucket_sort_kernel");
             ix->entries = d_entries; ix->start = d_start; ix->nb = nb; ix->ok = true;
         } else {
             cudaFreeAsync(d_start, st);

@@ -11,6 +11,7 @@ path here beyond marshalling.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -181,6 +182,29 @@ def distance_block(sketches: np.ndarray, row_begin: int = 0, row_end: Optional[i
         raise GoPanic("index out of range [-1]")
     _lib.check(rc)
     return same, dist
+
+
+def distance_sparse(sketches: np.ndarray, row_begin: int = 0, row_end: Optional[int] = None, upper: bool = True):
+    """The pairs of a row block that share at least one hash, as (i, j, same) arrays sorted by (i, j);
+    every pair that is not listed has same == 0 (Distance 1).  upper: only j > i."""
+    sketches = np.ascontiguousarray(sketches, dtype=np.uint32)
+    n, s = sketches.shape
+    row_end = n if row_end is None else row_end
+    cap = max(1024, 4 * (row_end - row_begin))
+    while True:
+        pi, pj, ps = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        cnt = C.c_uint64(0)
+        rc = _lib.lib().pg_mash_distance_sparse(sketches.ctypes.data, n, s, row_begin, row_end, 1 if upper else 0, pi.ctypes.data, pj.ctypes.data,
+                                                ps.ctypes.data, cap, C.byref(cnt))
+        if rc == _lib.PG_ERR_ARG and cnt.value > cap:
+            cap = int(cnt.value)
+            continue
+        if rc == _lib.PG_ERR_PANIC:
+            raise GoPanic("index out of range [-1]")
+        _lib.check(rc)
+        k = int(cnt.value)
+        order = np.lexsort((pj[:k], pi[:k]))
+        return pi[:k][order], pj[:k][order], ps[:k][order]
 
 
 def DistanceMatrix(mashes: Sequence[Mash]) -> np.ndarray:

@@ -471,3 +471,23 @@ def test_select_rows_wider_than_s_are_zero_filled(gpu, oracle):
     got = d_out.cpu().numpy().view(np.uint32)
     rc, want = oracle.sketch_batch(reads, synth.uniform_offsets(n, L), k, s, variant=1)
     assert rc == 0 and np.array_equal(got[:, :s], want) and not got[:, s:].any()
+
+
+def test_distance_sparse_equals_dense(gpu, oracle):
+    """pg_mash_distance_sparse: exactly the non-zero off-diagonal entries of the dense row block, for ascending
+    sketches (inverted-index join) and for unsorted zero-padded ones (pairwise kernel), full and upper."""
+    n, L, k, s = 96, 3000, 21, 128
+    reads = synth.family_reads(n, L, family=6)
+    sk = mash.sketch_uniform(reads, n, L, k, s)
+    sk[7] = sk[6]                                      # identical sketches
+    fill, _, _ = mash.sketch_arrays(synth.independent_reads(33, 150), synth.uniform_offsets(33, 150), 21, 200, pad_zero=True)
+    fill[3] = fill[2]
+    for sketches in (sk, fill):
+        dense, _ = mash.distance_block(sketches, want_distance=False)
+        for (rb, re) in [(0, len(sketches)), (5, 41)]:
+            for upper in (True, False):
+                pi, pj, ps = mash.distance_sparse(sketches, rb, re, upper=upper)
+                want = [(i, j, int(dense[i, j])) for i in range(rb, re) for j in range(len(sketches))
+                        if dense[i, j] and i != j and (j > i or not upper)]
+                assert list(zip(pi.tolist(), pj.tolist(), ps.tolist())) == want
+    assert len(mash.distance_sparse(sk)[0]) > 100
