@@ -434,6 +434,16 @@ def secondary_leg(cx, clocks_mhz):
     k3["frac_of_hbm_peak"] = k3["algorithmic_GBps"] / cx.peak
     k3.pop("_result", None)
     out.append(k3)
+    torch.cuda.empty_cache()
+    k3s = cx.all_pairs_sparse(d_sk, n, s)
+    k3s.update({"name": "cfg3 all-pairs, sparse upper-triangle output (K3)", "config": "configs[2]: the same all-pairs pass, returning only the pairs that share a hash",
+                "pairs_unordered": pairs_unordered, "algorithmic_bytes": n * s * 4 + 4 * pairs_unordered,
+                "parity_vs_oracle": rc == 0 and cx.all_pairs_check(k3s, want_same, rows_chk, 400),
+                "parity_sample": f"rows 0..{rows_chk - 1} x columns 0..399, entries with j > i",
+                "cpu_baseline": k3["cpu_baseline"]})
+    k3s["unordered_pairs_per_s"] = pairs_unordered / k3s["ms"] * 1e3
+    k3s.pop("_sparse", None)
+    out.append(k3s)
     del d_reads, d_sk
     torch.cuda.empty_cache()
     # ---- cfg5: SW (K4) + Tm (K5) ----
@@ -626,9 +636,42 @@ def make_all_pairs(cx):
                 "output_bytes": rows * n * 4, "_result": d_same}
 
     def check(k3, want_same, rows, cols, col0=0):
+        if "_sparse" in k3:  # triples -> the dense sample (upper triangle only: j > i)
+            di, dj, dc, cnt, r0 = k3["_sparse"]
+            i, j, c = (t[:cnt].cpu().numpy().astype(np.int64) for t in (di, dj, dc))
+            sel = (i < r0 + rows) & (j >= col0) & (j < col0 + cols)
+            got = np.zeros((rows, cols), dtype=np.uint32)
+            got[i[sel] - r0, j[sel] - col0] = c[sel].astype(np.uint32)
+            want = want_same.copy()
+            for a in range(rows):  # entries the sparse upper form does not carry: j <= i
+                want[a, : max(0, r0 + a + 1 - col0)] = 0
+            return bool(np.array_equal(got, want))
         got = k3["_result"][:rows, col0: col0 + cols].cpu().numpy().view(np.uint32)
         return bool(np.array_equal(got, want_same))
 
+    def all_pairs_sparse(d_sk, n, s, r0=0, r1=None, timer=None, cap=32_000_000):
+        r1 = n if r1 is None else r1
+        d_i, d_j, d_c = (torch.empty(cap, dtype=torch.int32, device=cx.dev) for _ in range(3))
+        d_n = torch.zeros(1, dtype=torch.int64, device=cx.dev)
+        sk = d_sk if d_sk.is_contiguous() else d_sk.contiguous()
+
+        def run():
+            cx.check(L.pg_mash_distance_sparse_dev(sk.data_ptr(), n, s, r0, r1, 1, d_i.data_ptr(), d_j.data_ptr(), d_c.data_ptr(), cap, d_n.data_ptr(), cx.stream))
+
+        l0 = L.pg_launch_count()
+        run()
+        launches = L.pg_launch_count() - l0
+        if timer is None:
+            ms, _ = ev_time(run, iters=1)
+        else:
+            _, ms = timer(run)
+        cnt = int(d_n.item())
+        return {"ms": ms, "rows": r1 - r0, "cols": n, "value": (r1 - r0) * n / ms / 1e6, "unit": "Gpairs/s (ordered pairs of the row block covered)",
+                "kernel": "bucket_join_kernel + compact_pairs_kernel", "gpu_launches_per_pass": launches,
+                "output": "sparse (i, j, same) triples of the pairs with j > i that share a hash", "pairs_listed": cnt, "output_bytes": cnt * 12,
+                "fits_capacity": cnt <= cap, "_sparse": (d_i, d_j, d_c, min(cnt, cap), r0)}
+
+    cx.all_pairs_sparse = all_pairs_sparse
     return all_pairs, check
 
 

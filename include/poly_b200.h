@@ -14,10 +14,18 @@
  *     thread-local message;
  *   - the caller owns every buffer; the library never retains a caller pointer
  *     after return (cgo pointer rule) and never frees caller memory;
- *   - functions without the _dev suffix take HOST pointers and perform the
- *     host<->device copies themselves; *_dev functions take DEVICE pointers on the
- *     current device plus a CUDA stream (cudaStream_t cast to void*, NULL = the
- *     legacy default stream) and are asynchronous with respect to the host;
+ *   - functions without the _dev suffix take HOST pointers (pageable or pinned) and
+ *     perform the host<->device copies themselves; *_dev functions take DEVICE
+ *     pointers on the calling thread's device (pg_thread_device / pg_init) plus a
+ *     CUDA stream (cudaStream_t cast to void*, NULL = the legacy default stream) and
+ *     only enqueue work: the sketch, Smith-Waterman / Needleman-Wunsch score, Tm and
+ *     synth *_dev entry points never wait for the device.  Exceptions, which
+ *     synchronise the given stream before returning because a host decision depends
+ *     on a device result: pg_mash_distance_block_dev / pg_mash_distance_sparse_dev
+ *     (sortedness and bucket sizes choose the algorithm), pg_fastq_ingest_dev /
+ *     pg_fasta_ingest_dev (they return counts and the error position by value), and
+ *     pg_mash_sketch_batch_dev for ragged batches the threshold path does not take
+ *     (s < 2, or more than 4 Mi row x item slots) when they hold few long sequences;
  *   - there is NO CPU fallback: without a usable sm_100 device every compute entry
  *     point fails with PG_ERR_NO_DEVICE.
  */

@@ -733,8 +733,18 @@ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
 
 #define PG_EMIT_STRIP(R_, H_) \
     if ((H_) <= tm1) { my_strip[c * 32u] = (H_); ++c; }
+// RARE variant (expected admissions per warp step << 1, e.g. genomes: T/2^32 ~ s/n ~ 3e-4): one test of the
+// minimum of the step's four hashes and a branch that is almost never taken, instead of four predicated
+// compare/store/add triples.  Only valid for unchecked steps (all four hashes of the step exist).
+#define PG_EMIT_STRIP_RARE(R_, H_)                                                       \
+    if ((R_) == 3) {                                                                     \
+        if (min(min(h[0], h[1]), min(h[2], h[3])) <= tm1) {                              \
+            _Pragma("unroll") for (int rr = 0; rr < 4; ++rr)                             \
+                if (h[rr] <= tm1) { my_strip[c * 32u] = h[rr]; ++c; }                    \
+        }                                                                                \
+    }
 
-template <int K>
+template <int K, bool RARE>
 __global__ void __launch_bounds__(32)
 sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets, uint32_t uniform_len,
                           uint64_t row0, uint64_t n_rows, uint32_t items_per_row, uint32_t s, uint32_t mu, uint32_t cap,
@@ -850,8 +860,13 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
             }
             uint32_t i = 0;
             if (nk == SELT_SEG) {
+                if (RARE) {
 #pragma unroll
-                for (int q = 0; q < SELT_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, PG_EMIT_STRIP)
+                    for (int q = 0; q < SELT_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, PG_EMIT_STRIP_RARE)
+                } else {
+#pragma unroll
+                    for (int q = 0; q < SELT_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, PG_EMIT_STRIP)
+                }
             } else {
 #pragma unroll 1
                 for (int q0 = 0; q0 < SELT_SEG / 4; q0 += NB) {
@@ -889,6 +904,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     }
 }
 #undef PG_EMIT_STRIP
+#undef PG_EMIT_STRIP_RARE
 
 // Stage B: exact bottom-s of the admitted candidates of one row (cnt <= cap by construction; rows whose
 // count is < s or > cap go onto the retry list).
@@ -1069,7 +1085,9 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + (size_t)s + 2 * SEL_NBK + 64 + 1 + 16;
     const size_t smem_b = words_b * 4;
     if (smem_b > 220 * 1024) return PG_OK;
-    { const int rc_ = func_smem((const void *)sketch_thresh_walk_kernel<K>, smem_a); if (rc_ != PG_OK) return rc_; }
+    // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
+    const bool rare = (uint64_t)mu * 512 < nmax;
+    { const int rc_ = func_smem(rare ? (const void *)sketch_thresh_walk_kernel<K, true> : (const void *)sketch_thresh_walk_kernel<K, false>, smem_a); if (rc_ != PG_OK) return rc_; }
     { const int rc_ = func_smem((const void *)sketch_thresh_select_kernel, smem_b); if (rc_ != PG_OK) return rc_; }
     int per_sm = 1;
     PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_thresh_select_kernel, SELT_SEL_THREADS, smem_b));
@@ -1088,8 +1106,12 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     for (uint64_t r0 = 0; r0 < n_reads; r0 += group) {
         const uint64_t rows = std::min(group, n_reads - r0);
         PG_CUDA(cudaMemsetAsync(d_cnt, 0, rows * 4, st));
-        sketch_thresh_walk_kernel<K><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)ipr,
-                                                                                 (uint32_t)s, mu, cap, d_cand, d_cnt, 4u);
+        if (rare)
+            sketch_thresh_walk_kernel<K, true><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)ipr,
+                                                                                           (uint32_t)s, mu, cap, d_cand, d_cnt, 4u);
+        else
+            sketch_thresh_walk_kernel<K, false><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)ipr,
+                                                                                            (uint32_t)s, mu, cap, d_cand, d_cnt, 4u);
         PG_LAUNCH_CHECK("sketch_thresh_walk_kernel");
         const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
         sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)K,
