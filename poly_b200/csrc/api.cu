@@ -99,6 +99,10 @@ class CopyPool {
     }
 
 public:
+    CopyPool() = default;
+    CopyPool(const CopyPool &) = delete;
+    CopyPool &operator=(const CopyPool &) = delete;
+    ~CopyPool() { stop(); }  // contexts are statics: joinable threads at exit would call std::terminate
     int threads() const { return (int)workers_.size() + 1; }
     void start(int helpers, int device) {
         if (!workers_.empty() || helpers <= 0) return;
