@@ -13,6 +13,7 @@
 // the outer loop; the reported error (first failing cell in row-major order,
 // align.go:188-191) does, and is resolved per orientation at the end.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <type_traits>
@@ -179,6 +180,116 @@ sw_score_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__
     if (errpos) errpos[qi] = ep;
 }
 
+// Two queries per thread, packed as 2 x int16 in one register (DPX __viaddmax_s16x2): the same four
+// ALU-pipe instructions per DP step now advance TWO cells, doubling the issue-bound cell rate of the
+// 32-bit kernel.  Used for Smith-Waterman (local) scores with gap <= 0 when every DP value provably fits
+// 15 bits (host check) and the query profile fits shared memory.  Thread t owns queries 2t and 2t+1 of its
+// block; the profile word prof[sym][row][thread] holds S(qA_row, sym) in the low and S(qB_row, sym) in the
+// high half.  Rows at or beyond a query's length score -16384, which the zero floor of align.go:192-195
+// turns into 0: such cells never exceed a real cell and never feed one (a cell only depends on smaller rows).
+constexpr int SW16_NEG = -16384;
+
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+
+template <int ROWS>
+__global__ void __launch_bounds__(SW_THREADS)
+sw_score_x2_kernel(SwParams p, const int16_t *__restrict__ lut_q, const int16_t *__restrict__ lut_t,
+                   const int *__restrict__ tab, int gap, int64_t *__restrict__ score,
+                   int32_t *__restrict__ err, int64_t *__restrict__ errpos) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    // layout: [s_tidx: SW_TCHUNK bytes][s_lut_t: 256 int16][s_tab: n_q*n_t int][prof: n_t*ROWS*threads u32]
+    uint8_t *s_tidx = sm;
+    int16_t *s_lut_t = reinterpret_cast<int16_t *>(sm + SW_TCHUNK);
+    int *s_tab = reinterpret_cast<int *>(sm + SW_TCHUNK + 512);
+    uint32_t *s_prof = reinterpret_cast<uint32_t *>(s_tab + p.n_q * p.n_t);
+    __shared__ unsigned long long s_first_bad_t;
+
+    const uint32_t tid = threadIdx.x;
+    for (int i = tid; i < p.n_q * p.n_t; i += SW_THREADS) s_tab[i] = tab[i];
+    for (int i = tid; i < 256; i += SW_THREADS) s_lut_t[i] = lut_t[i];
+    if (tid == 0) s_first_bad_t = ~0ull;
+    __syncthreads();
+
+    const uint64_t q0 = ((uint64_t)blockIdx.x * SW_THREADS + tid) * 2;
+    uint64_t qbeg[2] = {0, 0};
+    uint32_t qlen[2] = {0, 0};
+    int64_t first_bad_q[2] = {-1, -1};
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (q0 + h < p.nq) {
+            qbeg[h] = p.qoff[q0 + h];
+            qlen[h] = (uint32_t)(p.qoff[q0 + h + 1] - qbeg[h]);
+        }
+    // expand the packed profile: row i of query h scores through table row lut_q[q_h[i]] (row 0 for a bad symbol,
+    // reported at the end), -16384 beyond the query
+    for (int i = 0; i < ROWS; ++i) {
+        int row[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            row[h] = -1;
+            if (i < (int)qlen[h]) {
+                const int ix = lut_q[__ldg(p.q + qbeg[h] + i)];
+                if (ix < 0) { if (first_bad_q[h] < 0) first_bad_q[h] = i; row[h] = 0; }
+                else row[h] = ix * p.n_t;
+            }
+        }
+        for (int t = 0; t < p.n_t; ++t)
+            s_prof[(t * ROWS + i) * SW_THREADS + tid] = pack16(row[0] < 0 ? SW16_NEG : s_tab[row[0] + t], row[1] < 0 ? SW16_NEG : s_tab[row[1] + t]);
+    }
+    uint32_t col[ROWS];
+#pragma unroll
+    for (int i = 0; i < ROWS; ++i) col[i] = 0u;
+    uint32_t best = 0u;
+    const uint32_t gap2 = pack16(gap, gap);
+
+    for (uint64_t t0 = 0; t0 < p.tlen; t0 += SW_TCHUNK) {
+        const uint32_t tc = (uint32_t)min((uint64_t)SW_TCHUNK, p.tlen - t0);
+        __syncthreads();
+        for (uint32_t j = tid; j < tc; j += SW_THREADS) {
+            const int ix = s_lut_t[__ldg(p.t + t0 + j)];
+            if (ix < 0) atomicMin(&s_first_bad_t, (unsigned long long)(t0 + j));
+            s_tidx[j] = ix < 0 ? 0 : (uint8_t)ix;
+        }
+        __syncthreads();
+        if (qlen[0] | qlen[1]) {
+            for (uint32_t j = 0; j < tc; ++j) {
+                const uint32_t *pcol = s_prof + (size_t)s_tidx[j] * ROWS * SW_THREADS + tid;
+                uint32_t diag = 0u, up = 0u;
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i) {
+                    const uint32_t old = col[i];                             // H[i][j-1] of both queries
+                    uint32_t v = __viaddmax_s16x2(diag, pcol[i * SW_THREADS], 0u);  // align.go:192,195
+                    v = __viaddmax_s16x2(old, gap2, v);
+                    v = __viaddmax_s16x2(up, gap2, v);
+                    best = __vmaxs2(best, v);                                // align.go:197-201
+                    diag = old;
+                    up = v;
+                    col[i] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int64_t bad_t = s_first_bad_t == ~0ull ? -1 : (int64_t)s_first_bad_t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (q0 + h >= p.nq) continue;
+        int32_t ec = 0;
+        int64_t ep = -1;
+        if (qlen[h] > 0 && p.tlen > 0) {
+            const int64_t bad_a = p.query_is_a ? first_bad_q[h] : bad_t;
+            const int64_t bad_b = p.query_is_a ? bad_t : first_bad_q[h];
+            if (bad_a == 0) { ec = 1; ep = 0; }
+            else if (bad_b >= 0) { ec = 2; ep = bad_b; }
+            else if (bad_a > 0) { ec = 1; ep = bad_a; }
+        }
+        const int b16 = (int)(int16_t)(h ? (best >> 16) : (best & 0xffffu));
+        score[q0 + h] = ec ? 0 : (int64_t)b16;
+        if (err) err[q0 + h] = ec;
+        if (errpos) errpos[q0 + h] = ep;
+    }
+}
+
 // Long queries: same recurrence, DP column in global scratch laid out [cell][query]
 // so that a warp's accesses coalesce.
 template <typename T>
@@ -240,7 +351,7 @@ sw_score_long_kernel(SwParams p, uint64_t q_first, const int16_t *__restrict__ l
 template <typename T>
 int run_sw(const SwParams &p, uint64_t max_qlen, const int16_t *h_lut_q, const int16_t *h_lut_t,
            const std::vector<int64_t> &tab_qt, int64_t gap, int64_t *d_score, int32_t *d_err,
-           int64_t *d_errpos, cudaStream_t st) {
+           int64_t *d_errpos, cudaStream_t st, bool x2_ok = false) {
     // small parameter block: LUTs + table (query symbol major)
     const size_t ntab = (size_t)p.n_q * p.n_t;
     std::vector<uint8_t> blob(512 * 2 + ntab * sizeof(T));
@@ -284,6 +395,26 @@ int run_sw(const SwParams &p, uint64_t max_qlen, const int16_t *h_lut_q, const i
         launched = true;
         return true;
     };
+    // packed 2 x int16 kernel: local alignment, gap <= 0, every DP value < 2^14 (checked by the caller: x2_ok)
+    auto try_x2 = [&](auto rows_tag) -> bool {
+        constexpr int ROWS = decltype(rows_tag)::value;
+        if (launched || max_qlen > (uint64_t)ROWS) return false;
+        const size_t smem = SW_TCHUNK + 512 + ntab * sizeof(int) + (size_t)p.n_t * ROWS * SW_THREADS * sizeof(uint32_t);
+        if (smem > 100 * 1024) return false;
+        cudaFuncSetAttribute(sw_score_x2_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sw_score_x2_kernel<ROWS><<<(unsigned)((p.nq + 2 * SW_THREADS - 1) / (2 * SW_THREADS)), SW_THREADS, smem, st>>>(
+            p, d_lut_q, d_lut_t, reinterpret_cast<const int *>(d_tab), (int)gap, d_score, d_err, d_errpos);
+        note_launch("sw_score_x2_kernel");
+        launched = true;
+        return true;
+    };
+    if (sizeof(T) == 4 && x2_ok) {
+        try_x2(std::integral_constant<int, 8>{});
+        try_x2(std::integral_constant<int, 16>{});
+        try_x2(std::integral_constant<int, 24>{});
+        try_x2(std::integral_constant<int, 28>{});
+        try_x2(std::integral_constant<int, 32>{});
+    }
     if (sizeof(T) == 4) {
         try_rows(std::integral_constant<int, 8>{});
         try_rows(std::integral_constant<int, 16>{});
@@ -353,8 +484,12 @@ int launch_sw_score(const uint8_t *d_q, const uint64_t *d_qoff, uint64_t nq, uin
     const long double bound = global ? (long double)std::max(amax, agap) * (long double)(max_qlen + tlen + 2)
                                      : (long double)amax * (long double)std::min<uint64_t>(max_qlen, tlen) +
                                            (long double)std::max(amax, agap);
-    if (bound < 2.0e9L)
-        return run_sw<int>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st);
+    if (bound < 2.0e9L) {
+        // two queries per register (2 x int16) when a local alignment's values stay below 2^14 and gap <= 0
+        static const bool no_x2 = [] { const char *e = getenv("PG_SW_NO_X2"); return e && atoi(e) != 0; }();  // A/B knob
+        const bool x2_ok = !global && gap <= 0 && bound < 16000.0L && agap < 16000 && nq >= 2 && !no_x2;
+        return run_sw<int>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st, x2_ok);
+    }
     return run_sw<long long>(p, max_qlen, lut_q, lut_t, tab_qt, gap, d_score, d_err, d_errpos, st);
 }
 

@@ -348,3 +348,35 @@ def test_reference_return_shape_and_long_pairs(gpu, oracle):
     # an error in a long pair: same (0, "", "", err) as the reference
     score, sa, sb, err = align.SmithWaterman(b"ACGT" * 30 + b"N", b"ACGT" * 40, SC)
     assert (score, sa, sb) == (0, "", "") and str(err) == "Symbol N not in alphabet"
+
+
+def test_sw_packed_int16_kernel(gpu, oracle):
+    """sw_score_x2_kernel (two queries per register, DPX s16x2): odd batch sizes, empty queries, queries whose
+    partner is longer / shorter / invalid, tables with larger magnitudes, gap 0, both orientations; and the
+    bound that sends larger scores back to the 32-bit kernel."""
+    rng = np.random.default_rng(16)
+    a5 = align.NewAlphabet(["-", "A", "C", "G", "T"])
+    lut5 = a5.byte_lut()
+    for nq, maxq, tlen, gap, scale in [(3, 25, 2000, -2, 1), (301, 32, 9000, -7, 60), (77, 28, 500, 0, 1), (2, 8, 100, -1, 100), (129, 16, 8200, -3, 9)]:
+        mat = (np.array(TEST_MAT, dtype=np.int64) * scale)
+        mat[2, 3] = mat[3, 2] = scale * 2                     # not just a match / mismatch table
+        sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, mat.tolist()), gap)
+        qs = [bytes(rng.choice(list(b"ACGT-"), size=int(rng.integers(0, maxq + 1))).astype(np.uint8)) for _ in range(nq)]
+        qs[0] = bytes(rng.choice(list(b"ACGT"), size=maxq).astype(np.uint8))
+        if nq > 2:
+            qs[1] = b""
+            qs[2] = qs[2][:3] + b"N" + qs[2][3:maxq - 1]      # invalid symbol: (0, err) for this query only
+        t = bytes(rng.choice(list(b"ACGT"), size=tlen).astype(np.uint8))
+        for query_is_a in (True, False):
+            scores, errs = align.SmithWatermanScores(qs, t, sc, query_is_a=query_is_a)
+            for i in range(nq):
+                x, y = (qs[i], t) if query_is_a else (t, qs[i])
+                w = oracle.sw_score(x, y, lut5, lut5, mat, gap)
+                assert scores[i] == w[0] and (errs[i] is None) == (w[3] == 0), (nq, i, query_is_a)
+    # 25 x 700 = 17500 > 2^14: the packed kernel must not be chosen (values would wrap)
+    mat = np.array(TEST_MAT, dtype=np.int64) * 700
+    sc = align.NewScoring(align.NewSubstitutionMatrix(a5, a5, mat.tolist()), -2)
+    q = [bytes(rng.choice(list(b"ACGT"), size=25).astype(np.uint8)) for _ in range(10)]
+    t = q[3] + bytes(rng.choice(list(b"ACGT"), size=300).astype(np.uint8))
+    scores, _ = align.SmithWatermanScores(q, t, sc)
+    assert scores[3] == 25 * 3 * 700 and all(scores[i] == oracle.sw_score(q[i], t, lut5, lut5, mat, -2)[0] for i in range(10))
