@@ -465,11 +465,14 @@ def secondary_leg(cx, clocks_mhz):
     offs_h = np.arange(mc + 1, dtype=np.uint64) * PL
     t0 = time.perf_counter(); rc, want_sc = oracle_ffi.sw_score_batch(pr_host[: mc * PL], offs_h, tpl_host, lut, lut, mat, -2, cores); dtc = time.perf_counter() - t0
     cells = m * PL * TL
-    alu_ceiling = 148 * 64 * clk / 4  # ALU pipe: 64 lanes/clk/SM, 4 ALU-pipe instructions (3 DPX add-max + 1 max) per cell
+    k4_name = (L.pg_last_kernel() or b"").decode()
+    per_cell = 2 if "x2" in k4_name else 4  # 3 DPX add-max + 1 max per DP step; the packed int16 kernel advances two cells per step
+    alu_ceiling = 148 * 64 * clk / per_cell  # ALU pipe: 64 lanes/clk/SM
     out.append({"name": "cfg5 Smith-Waterman score (K4)", "config": "configs[4]: 1M x 25 bp primers vs a 10 kb template, +3/-3, gap -2",
-                "kernel": (L.pg_last_kernel() or b"").decode(), "ms": ms, "value": cells / ms / 1e9, "unit": "TCUPS",
+                "kernel": k4_name, "ms": ms, "value": cells / ms / 1e9, "unit": "TCUPS",
                 "bound": "integer ALU / DPX issue", "alu_issue_ceiling_tcups": alu_ceiling / 1e12,
-                "alu_issue_ceiling_derivation": f"148 SMs x 64 ALU lanes x {clk / 1e6:.0f} MHz / 4 ALU-pipe instructions per cell",
+                "alu_issue_ceiling_derivation": f"148 SMs x 64 ALU lanes x {clk / 1e6:.0f} MHz / {per_cell} ALU-pipe instructions per cell"
+                                                + (" (4 per DP step of the 2 x int16 packed kernel, two cells per step)" if per_cell == 2 else ""),
                 "frac_of_alu_issue_ceiling": (cells / ms * 1e3) / alu_ceiling,
                 "parity_vs_oracle": rc == 0 and bool(np.array_equal(score[:mc].cpu().numpy(), want_sc)) and int(ec.abs().max().item()) == 0,
                 "parity_sample": f"first {mc} primers",
