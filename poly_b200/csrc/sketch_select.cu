@@ -833,9 +833,18 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
         if (!tail_by_tma(c0, ch)) __syncwarp();  // plain-store part of this stage
 
         uint32_t c = 0;  // hashes this lane admitted in this chunk
-        const uint32_t seg = lane * SELT_SEG;
+        // A full chunk gives every lane SELT_SEG positions.  A shorter (last) chunk is spread over all lanes
+        // instead of leaving the upper lanes idle while the lower ones walk full segments: an odd number
+        // of word steps per lane keeps the lanes' staged words in different banks.
+        uint32_t seg_len = SELT_SEG;
+        if (ch != SELT_CHUNK) {
+            uint32_t steps = (ch + 127u) >> 7;  // ceil(ch / 32 lanes / 4 positions per step)
+            steps |= 1u;
+            seg_len = 4u * steps;               // <= SELT_SEG because ch < SELT_CHUNK
+        }
+        const uint32_t seg = lane * seg_len;
         if (seg < ch) {
-            const uint32_t nk = min((uint32_t)SELT_SEG, ch - seg);
+            const uint32_t nk = min(seg_len, ch - seg);
             const uint32_t b0 = head + seg;
             const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage) + (b0 >> 2);
             const uint8_t *sb = stage + b0 + 4 * NB;
@@ -858,23 +867,26 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
                 raw_a = raw_b;
                 raw_b = *swp++;
             }
+            // whole groups of NB word steps without bounds tests, then < NB checked steps: the loop body is
+            // NB steps of code (it stays in the instruction cache) instead of a fully unrolled segment
             uint32_t i = 0;
-            if (nk == SELT_SEG) {
-                if (RARE) {
+            const uint32_t n_main = (nk / (4 * NB)) * (4 * NB);
+            if (RARE) {
+#pragma unroll 1
+                while (i < n_main) {
 #pragma unroll
-                    for (int q = 0; q < SELT_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, PG_EMIT_STRIP_RARE)
-                } else {
-#pragma unroll
-                    for (int q = 0; q < SELT_SEG / 4; ++q) PG_KMER_STEP(q % NB, false, PG_EMIT_STRIP)
+                    for (int u = 0; u < NB; ++u) PG_KMER_STEP(u, false, PG_EMIT_STRIP_RARE)
                 }
             } else {
 #pragma unroll 1
-                for (int q0 = 0; q0 < SELT_SEG / 4; q0 += NB) {
+                while (i < n_main) {
 #pragma unroll
-                    for (int u = 0; u < NB; ++u) {
-                        if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_STRIP)
-                    }
+                    for (int u = 0; u < NB; ++u) PG_KMER_STEP(u, false, PG_EMIT_STRIP)
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_STRIP)
             }
         }
         // flush: compact the strip columns into the row's candidate list (order is irrelevant: a multiset)
@@ -917,10 +929,10 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
     extern __shared__ __align__(16) uint32_t smem_w[];
     SelSmem m;
     m.cand = smem_w;                                 // [max(cap, P)]
-    m.keep = m.cand + ((max(cap, P) + 3u) & ~3u);    // scratch of the final stage: s + ties + one cursor per bucket
+    m.keep = m.cand + ((max(cap, P) + 3u) & ~3u);    // [max(cap, s + SEL_NBK + 64)]: candidates grouped by bucket / scratch of the generic path
     m.kv = nullptr;
     m.bytes = nullptr;
-    m.hist = m.keep + s + SEL_NBK + 64;
+    m.hist = m.keep + max(((cap + 3u) & ~3u), s + SEL_NBK + 64);
     m.misc = m.hist + SEL_NBK + 1;
     m.tmpcap = (uint32_t)(m.hist - m.keep);
     const uint32_t tid = threadIdx.x;
@@ -937,19 +949,73 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
             continue;
         }
         const uint32_t *src = gcand + lrow * (uint64_t)cap;
-        for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) m.cand[i] = __ldg(src + i);
-        __syncthreads();
         uint32_t *dst = out + row * row_stride;
-        // candidates are < T: spread them over the 2048 value buckets of the final stage
+        // candidates are < T: spread them over the 2048 value buckets (about one candidate per bucket)
         const uint32_t tm1 = selt_threshold_m1(n, mu);
         const uint32_t bits = 32u - __clz(tm1 | 1u);
         const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
-        if (!final_bucket_sort<SELT_SEL_THREADS>(m, cnt, s, dst, bshift)) {
-            if (cnt > s) prune_to_s<SELT_SEL_THREADS>(m, cnt, s);
-            for (uint32_t i = s + tid; i < P; i += SELT_SEL_THREADS) m.cand[i] = 0xffffffffu;
+        // ---- tight counting sort by bucket, exact rank inside the (tiny) buckets --------------------
+        // cur[b]: bucket count -> exclusive start -> (after the scatter) end of bucket b = start of b + 1
+        uint32_t *cur = m.hist;   // [SEL_NBK]
+        uint32_t *tmp = m.keep;   // [cnt] candidates grouped by bucket (the launcher sizes keep[] for cap words)
+        for (uint32_t i = tid; i < SEL_NBK; i += SELT_SEL_THREADS) cur[i] = 0;
+        if (tid == 0) m.misc[0] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
+            const uint32_t e = __ldg(src + i);
+            m.cand[i] = e;
+            atomicAdd(&cur[e >> bshift], 1u);
+        }
+        __syncthreads();
+        {   // exclusive scan over the buckets: 8 per thread, warp scan, warp totals
+            constexpr int PER = SEL_NBK / SELT_SEL_THREADS;
+            uint32_t cb[PER], sum = 0, mx = 0;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { cb[j] = cur[tid * PER + j]; sum += cb[j]; mx = max(mx, cb[j]); }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)(tid & 31u) >= d) incl += y;
+            }
+            __shared__ uint32_t s_wtot[SELT_SEL_THREADS / 32];
+            if ((tid & 31u) == 31u) s_wtot[tid >> 5] = incl;
+            mx = __reduce_max_sync(0xffffffffu, mx);
+            if ((tid & 31u) == 0 && mx > 48u) atomicMax(&m.misc[0], mx);  // a crowded bucket: quadratic ranking would hurt
             __syncthreads();
-            bitonic_sort<SELT_SEL_THREADS>(m.cand, P);
-            for (uint32_t i = tid; i < s; i += SELT_SEL_THREADS) dst[i] = m.cand[i];
+            uint32_t run = incl - sum;
+            for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_wtot[w];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { cur[tid * PER + j] = run; run += cb[j]; }
+        }
+        __syncthreads();
+        const bool crowded = m.misc[0] != 0;
+        if (!crowded) {
+            for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
+                const uint32_t e = m.cand[i];
+                tmp[atomicAdd(&cur[e >> bshift], 1u)] = e;
+            }
+            __syncthreads();
+            for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
+                const uint32_t e = tmp[p], b = e >> bshift;
+                const uint32_t lo = b ? cur[b - 1] : 0u;
+                if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
+                const uint32_t hi = cur[b];
+                uint32_t r = lo;
+                for (uint32_t q = lo; q < hi; ++q) {
+                    const uint32_t x = tmp[q];
+                    r += (x < e) || (x == e && q < p);  // ties keep distinct slots through the index
+                }
+                if (r < s) dst[r] = e;
+            }
+        } else {  // degenerate value distribution: the generic exact path (radix select, bitonic sort)
+            if (!final_bucket_sort<SELT_SEL_THREADS>(m, cnt, s, dst, bshift)) {
+                if (cnt > s) prune_to_s<SELT_SEL_THREADS>(m, cnt, s);
+                for (uint32_t i = s + tid; i < P; i += SELT_SEL_THREADS) m.cand[i] = 0xffffffffu;
+                __syncthreads();
+                bitonic_sort<SELT_SEL_THREADS>(m.cand, P);
+                for (uint32_t i = tid; i < s; i += SELT_SEL_THREADS) dst[i] = m.cand[i];
+            }
         }
         if (extra.n > 0) {  // fused all-gather: replicate the finished row into every rank's buffer
             __syncthreads();
@@ -1082,7 +1148,8 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     uint32_t cap = mu + 8u * (uint32_t)ceil(sqrt((double)mu)) + 96u;
     cap = (cap + 3u) & ~3u;
     const size_t smem_a = 2 * (size_t)SELT_STAGE_BYTES + (size_t)SELT_SEG * 32 * 4;
-    const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + (size_t)s + 2 * SEL_NBK + 64 + 1 + 16;
+    const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64) +
+                           SEL_NBK + 1 + 16;
     const size_t smem_b = words_b * 4;
     if (smem_b > 220 * 1024) return PG_OK;
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
