@@ -110,6 +110,8 @@ bucket_sort_kernel(uint64_t *__restrict__ entries, const uint64_t *__restrict__ 
         while (P < m) P <<= 1;
         for (uint32_t i = threadIdx.x; i < P; i += JOIN_THREADS) key[i] = i < m ? entries[lo + i] : ~0ull;
         __syncthreads();
+        // Pair t of a stage with distance j touches elements inside the 64-element block [64 * (t / 32), +64)
+        // whenever j <= 32, and a warp owns 32 consecutive pairs t: those stages only need a warp barrier.
         for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
             for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
                 for (uint32_t t = threadIdx.x; t < (P >> 1); t += JOIN_THREADS) {
@@ -118,8 +120,10 @@ bucket_sort_kernel(uint64_t *__restrict__ entries, const uint64_t *__restrict__ 
                     const uint64_t a = key[i], c = key[ixj];
                     if ((a > c) == up) { key[i] = c; key[ixj] = a; }
                 }
-                __syncthreads();
+                if (j > 32) __syncthreads();  // this stage wrote outside the warp's own 64-element block
+                else __syncwarp();            // stages with distance <= 32 read and write inside it
             }
+            __syncthreads();  // the next k2 starts with a distance that may cross warps
         }
         for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) entries[lo + i] = key[i];
         __syncthreads();
@@ -139,31 +143,90 @@ bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restr
     uint16_t *rs = reinterpret_cast<uint16_t *>(key + JOIN_CAP);     // [JOIN_CAP] first position of my value run
     uint16_t *re = rs + JOIN_CAP;                                    // [JOIN_CAP] one past its last position
     uint16_t *mult = re + JOIN_CAP;                                  // [JOIN_CAP] multiplicity at a (value, id) head, 0 elsewhere
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_scan[2 * (JOIN_THREADS / 32)];
+    __shared__ uint32_t s_next;
+    const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t b = blockIdx.x; b < nbuckets; b += gridDim.x) {
         const uint64_t lo = start[b];
         const uint32_t m = (uint32_t)(start[b + 1] - lo);
         if (m == 0) continue;
         for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) key[i] = entries[lo + i];  // sorted by bucket_sort_kernel
         __syncthreads();
-        // run bounds and (value, id) multiplicities: the thread at the first position of a value run walks it
-        for (uint32_t i = threadIdx.x; i < m; i += JOIN_THREADS) {
-            const uint32_t v = (uint32_t)(key[i] >> 32);
-            if (i > 0 && (uint32_t)(key[i - 1] >> 32) == v) continue;
-            uint32_t e = i + 1;
-            while (e < m && (uint32_t)(key[e] >> 32) == v) ++e;
-            uint32_t head = i;
-            for (uint32_t j = i; j < e; ++j) {
-                rs[j] = (uint16_t)i;
-                re[j] = (uint16_t)e;
-                if (j > i && key[j] == key[j - 1]) { mult[j] = 0; ++mult[head]; }
-                else { head = j; mult[j] = 1; }
+        // run bounds by two scans over the head flags of the value runs (a run of g ids used to be walked by
+        // ONE thread: g serial steps with 31 idle lanes), multiplicities by a short forward look (duplicates
+        // of one (value, id) are rare)
+        {
+            constexpr int PER = JOIN_CAP / JOIN_THREADS;  // 16 consecutive positions per thread
+            const uint32_t p0 = threadIdx.x * PER;
+            const uint32_t lane_ = threadIdx.x & 31u, warp_ = threadIdx.x >> 5;
+            // forward: rs[i] = last run head at or before i
+            uint32_t last = 0;
+            bool any = false;
+            for (int t = 0; t < PER; ++t) {
+                const uint32_t i = p0 + t;
+                if (i < m && (i == 0 || (uint32_t)(key[i - 1] >> 32) != (uint32_t)(key[i] >> 32))) { last = i; any = true; }
             }
+            uint32_t carry = any ? last + 1 : 0;  // 0 = no head in my span (positions are >= 0: shift by one)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, carry, d);
+                if ((int)lane_ >= d) carry = max(carry, y);
+            }
+            if (lane_ == 31) s_scan[warp_] = carry;
+            uint32_t before = __shfl_up_sync(0xffffffffu, carry, 1);
+            if (lane_ == 0) before = 0;
+            __syncthreads();
+            for (uint32_t w = 0; w < warp_; ++w) before = max(before, s_scan[w]);
+            uint32_t run_head = before ? before - 1 : 0;
+            for (int t = 0; t < PER; ++t) {
+                const uint32_t i = p0 + t;
+                if (i >= m) break;
+                if (i == 0 || (uint32_t)(key[i - 1] >> 32) != (uint32_t)(key[i] >> 32)) run_head = i;
+                rs[i] = (uint16_t)run_head;
+                uint32_t c = 0;
+                if (i == 0 || key[i - 1] != key[i]) {  // head of a (value, id) group
+                    c = 1;
+                    while (i + c < m && key[i + c] == key[i]) ++c;
+                }
+                mult[i] = (uint16_t)c;
+            }
+            __syncthreads();
+            // backward: re[i] = first run head after i (m if none)
+            uint32_t nxt = m;
+            for (int t = PER - 1; t >= 0; --t) {
+                const uint32_t i = p0 + t;
+                if (i < m && rs[i] == i) nxt = i;  // smallest head in my span
+            }
+            uint32_t c2 = nxt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_down_sync(0xffffffffu, c2, d);
+                if ((int)lane_ + d < 32) c2 = min(c2, y);
+            }
+            if (lane_ == 0) s_scan[8 + warp_] = c2;
+            uint32_t after = __shfl_down_sync(0xffffffffu, c2, 1);
+            if (lane_ == 31) after = m;
+            __syncthreads();
+            for (uint32_t w = warp_ + 1; w < JOIN_THREADS / 32; ++w) after = min(after, s_scan[8 + w]);
+            uint32_t next_head = after;
+            for (int t = PER - 1; t >= 0; --t) {
+                const uint32_t i = p0 + t;
+                if (i >= m) continue;
+                re[i] = (uint16_t)next_head;
+                if (rs[i] == i) next_head = i;
+            }
+            if (threadIdx.x == 0) s_next = 0;
         }
         __syncthreads();
-        // emission: 32 positions per warp step; those that head a (value, id) group of the row block inside a
+        // emission: chunks of 32 positions handed out dynamically (runs cluster: a static split leaves most warps
+        // waiting at the barrier); the positions of a chunk that head a (value, id) group of the row block inside a
         // run with other members are served one after the other by the whole warp
-        for (uint32_t a0 = warp * 32u; a0 < m; a0 += (JOIN_THREADS / 32) * 32u) {
+        for (;;) {
+            uint32_t chunk = 0;
+            if (lane == 0) chunk = atomicAdd(&s_next, 1u);
+            chunk = __shfl_sync(0xffffffffu, chunk, 0);
+            const uint32_t a0 = chunk * 32u;
+            if (a0 >= m) break;
             const uint32_t a = a0 + lane;
             bool mine = false;
             if (a < m && mult[a] != 0) {
