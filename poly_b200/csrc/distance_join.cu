@@ -218,31 +218,41 @@ bucket_join_kernel(const uint64_t *__restrict__ entries, const uint64_t *__restr
             if (threadIdx.x == 0) s_next = 0;
         }
         __syncthreads();
-        // emission: chunks of 32 positions handed out dynamically (runs cluster: a static split leaves most warps
-        // waiting at the barrier); the positions of a chunk that head a (value, id) group of the row block inside a
-        // run with other members are served one after the other by the whole warp
+        // emission, one value run at a time: chunks of 32 positions are handed out dynamically (runs cluster: a
+        // static split leaves most warps waiting at the barrier); the warp that owns a run's first position serves
+        // the whole run.  The b side of a 32-wide tile sits in registers (lane = one member), the a side is
+        // broadcast member by member with shuffles, so one (a, tile) step is a handful of instructions and its
+        // reductions go to neighbouring words of row a.
         for (;;) {
             uint32_t chunk = 0;
             if (lane == 0) chunk = atomicAdd(&s_next, 1u);
             chunk = __shfl_sync(0xffffffffu, chunk, 0);
-            const uint32_t a0 = chunk * 32u;
-            if (a0 >= m) break;
-            const uint32_t a = a0 + lane;
-            bool mine = false;
-            if (a < m && mult[a] != 0) {
-                const uint32_t ida = (uint32_t)key[a];
-                mine = ida >= row_begin && ida < row_end && (uint32_t)(re[a] - rs[a]) > mult[a];  // anybody else in the run?
-            }
-            uint32_t todo = __ballot_sync(0xffffffffu, mine);
-            while (todo) {
-                const uint32_t src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const uint32_t pa = a0 + src;
-                const uint32_t ca = mult[pa], r0 = rs[pa], r1 = re[pa];
-                uint32_t *row = same + ((uint32_t)key[pa] - row_begin) * n;
-                for (uint32_t j = r0 + lane; j < r1; j += 32) {
-                    const uint32_t cb = mult[j];
-                    if (cb != 0 && (j < pa || j >= pa + ca)) atomicAdd(row + (uint32_t)key[j], min(ca, cb));
+            const uint32_t c0 = chunk * 32u;
+            if (c0 >= m) break;
+            const uint32_t pos = c0 + lane;
+            uint32_t heads = __ballot_sync(0xffffffffu, pos < m && rs[pos] == pos && (uint32_t)re[pos] - pos > mult[pos]);  // runs with >= 2 members
+            while (heads) {
+                const uint32_t h = c0 + (__ffs(heads) - 1);
+                heads &= heads - 1;
+                const uint32_t r0 = h, r1 = re[h];
+                for (uint32_t b0 = r0; b0 < r1; b0 += 32) {       // tile of b members in registers
+                    const uint32_t jb = b0 + lane;
+                    const uint32_t cb = jb < r1 ? mult[jb] : 0u;
+                    const uint32_t idb = jb < r1 ? (uint32_t)key[jb] : 0u;
+                    for (uint32_t a0 = r0; a0 < r1; a0 += 32) {   // tile of a members, broadcast one by one
+                        const uint32_t ja = a0 + lane;
+                        const uint32_t ca_l = ja < r1 ? mult[ja] : 0u;
+                        const uint32_t ida_l = ja < r1 ? (uint32_t)key[ja] : 0u;
+                        uint32_t amask = __ballot_sync(0xffffffffu, ca_l != 0 && ida_l >= row_begin && ida_l < row_end);
+                        while (amask) {
+                            const uint32_t src = __ffs(amask) - 1;
+                            amask &= amask - 1;
+                            const uint32_t ca = __shfl_sync(0xffffffffu, ca_l, src);
+                            const uint32_t ida = __shfl_sync(0xffffffffu, ida_l, src);
+                            if (cb != 0 && idb != ida)  // a (value, id) group never pairs with itself
+                                atomicAdd(same + (ida - row_begin) * n + idb, min(ca, cb));
+                        }
+                    }
                 }
             }
         }

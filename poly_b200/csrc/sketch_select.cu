@@ -718,12 +718,21 @@ select_merge_kernel(const uint32_t *__restrict__ part, const uint32_t *__restric
 //   B. sketch_thresh_select_kernel: one CTA per row loads the ~mu candidates and runs the exact
 //      bucket sort-select (ties counted) -> ascending bottom-s, stored to every destination.
 // Extra HBM traffic: mu words per row written and read once (cfg3: 2 x 1 GB next to 1.8 GB algorithmic).
-constexpr int SELT_SEG = 68;
-constexpr int SELT_CHUNK = 32 * SELT_SEG;  // 2176 k-mer positions per warp chunk
+// Positions per lane per chunk: 4 x an ODD number of word steps (lanes read their staged words an odd number
+// of words apart: bank-conflict free) that is a multiple of NB = K / 4 where NB is odd, so that a full
+// segment is whole groups of the NB-step loop body and never enters the bounds-checked tail; for even NB one
+// checked step remains.
+template <int K>
+struct SeltGeom {
+    static constexpr int NB = K / 4;
+    static constexpr int STEPS = NB == 2 ? 17 : NB == 3 ? 21 : NB == 4 ? 17 : NB == 5 ? 15 : NB == 6 ? 19 : NB == 7 ? 21 : 17;
+    static constexpr int SEG = 4 * STEPS;      // 60 .. 84 k-mer positions
+    static constexpr int CHUNK = 32 * SEG;     // per warp chunk
+    static constexpr int STAGE = (15 + CHUNK + 32 + 48 + 15 + 255) / 256 * 256;  // head + chunk + k + over-read pad; also the dense flush buffer
+    static_assert(STEPS % 2 == 1 && (NB % 2 == 0 || STEPS % NB == 0), "segment geometry");
+};
 constexpr int SELT_ITEM_CHUNKS = 8;
-constexpr int SELT_STAGE_BYTES = (15 + SELT_CHUNK + 32 + 48 + 15) / 16 * 16;  // head + chunk + k + over-read pad
 constexpr int SELT_SEL_THREADS = 256;
-static_assert(SELT_SEG % 4 == 0 && (SELT_SEG / 4) % 2 == 1, "whole word steps, odd word distance between lanes");
 
 __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
     if ((uint64_t)mu >= n) return 0xffffffffu;  // every hash is a candidate
@@ -757,6 +766,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     constexpr int ROTF = 0;
     const uint32_t rotmul = 0;
     static_assert(NB >= 1 && K <= 32, "walk path: 4 <= k <= 32");
+    constexpr int SELT_SEG = SeltGeom<K>::SEG, SELT_CHUNK = SeltGeom<K>::CHUNK, SELT_STAGE_BYTES = SeltGeom<K>::STAGE;
 
     extern __shared__ __align__(128) uint8_t smem[];  // 2 stage buffers | strip [SELT_SEG][32]
     __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
@@ -902,14 +912,25 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
             if (lane == 0) base = atomicAdd(&gcnt[lrow], tot);
             base = __shfl_sync(0xffffffffu, base, 0);
             if ((uint64_t)base + tot <= cap) {  // otherwise the count alone tells stage B that the row overflowed
-                const uint32_t maxc = __reduce_max_sync(0xffffffffu, c);
-                const uint32_t below = (1u << lane) - 1u;
-                uint32_t off = base;
-                for (uint32_t j = 0; j < maxc; ++j) {
-                    const bool v = j < c;
-                    const uint32_t b = __ballot_sync(0xffffffffu, v);
-                    if (v) my_cand[off + __popc(b & below)] = my_strip[j * 32u];
-                    off += __popc(b);
+                if (tot <= SELT_STAGE_BYTES / 4) {
+                    // usual case: the chunk's stage buffer is dead by now -- gather the strip columns into it (lane l's
+                    // entries behind those of the lanes below it), then copy the dense list out with coalesced stores
+                    uint32_t *dense = reinterpret_cast<uint32_t *>(smem + buf * SELT_STAGE_BYTES);
+                    const uint32_t excl = incl - c;
+                    __syncwarp();  // every lane is done reading the staged bytes
+                    for (uint32_t j = 0; j < c; ++j) dense[excl + j] = my_strip[j * 32u];
+                    __syncwarp();
+                    for (uint32_t i = lane; i < tot; i += 32) my_cand[base + i] = dense[i];
+                } else {  // many admissions (T close to 2^32): compact strip row by strip row with ballots
+                    const uint32_t maxc = __reduce_max_sync(0xffffffffu, c);
+                    const uint32_t below = (1u << lane) - 1u;
+                    uint32_t off = base;
+                    for (uint32_t j = 0; j < maxc; ++j) {
+                        const bool v = j < c;
+                        const uint32_t b = __ballot_sync(0xffffffffu, v);
+                        if (v) my_cand[off + __popc(b & below)] = my_strip[j * 32u];
+                        off += __popc(b);
+                    }
                 }
             }
         }
@@ -955,23 +976,24 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         const uint32_t bits = 32u - __clz(tm1 | 1u);
         const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
         // ---- tight counting sort by bucket, exact rank inside the (tiny) buckets --------------------
-        // cur[b]: bucket count -> exclusive start -> (after the scatter) end of bucket b = start of b + 1
-        uint32_t *cur = m.hist;   // [SEL_NBK]
-        uint32_t *tmp = m.keep;   // [cnt] candidates grouped by bucket (the launcher sizes keep[] for cap words)
-        for (uint32_t i = tid; i < SEL_NBK; i += SELT_SEL_THREADS) cur[i] = 0;
-        if (tid == 0) m.misc[0] = 0;
+        // cur[b]: bucket count -> exclusive start -> (after the scatter) end of bucket b = start of b + 1.
+        // Everything is addressed as smem_w[offset + i]: through the pointers of `m` the compiler cannot prove the
+        // shared address space and emits generic loads / atomics (three times the instructions).
+        const uint32_t o_cand = 0, o_tmp = (uint32_t)(m.keep - smem_w), o_cur = (uint32_t)(m.hist - smem_w), o_flag = (uint32_t)(m.misc - smem_w);
+        for (uint32_t i = tid; i < SEL_NBK; i += SELT_SEL_THREADS) smem_w[o_cur + i] = 0;
+        if (tid == 0) smem_w[o_flag] = 0;
         __syncthreads();
         for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
             const uint32_t e = __ldg(src + i);
-            m.cand[i] = e;
-            atomicAdd(&cur[e >> bshift], 1u);
+            smem_w[o_cand + i] = e;
+            atomicAdd(&smem_w[o_cur + (e >> bshift)], 1u);
         }
         __syncthreads();
         {   // exclusive scan over the buckets: 8 per thread, warp scan, warp totals
             constexpr int PER = SEL_NBK / SELT_SEL_THREADS;
             uint32_t cb[PER], sum = 0, mx = 0;
 #pragma unroll
-            for (int j = 0; j < PER; ++j) { cb[j] = cur[tid * PER + j]; sum += cb[j]; mx = max(mx, cb[j]); }
+            for (int j = 0; j < PER; ++j) { cb[j] = smem_w[o_cur + tid * PER + j]; sum += cb[j]; mx = max(mx, cb[j]); }
             uint32_t incl = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -981,29 +1003,29 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
             __shared__ uint32_t s_wtot[SELT_SEL_THREADS / 32];
             if ((tid & 31u) == 31u) s_wtot[tid >> 5] = incl;
             mx = __reduce_max_sync(0xffffffffu, mx);
-            if ((tid & 31u) == 0 && mx > 48u) atomicMax(&m.misc[0], mx);  // a crowded bucket: quadratic ranking would hurt
+            if ((tid & 31u) == 0 && mx > 48u) atomicMax(&smem_w[o_flag], mx);  // a crowded bucket: quadratic ranking would hurt
             __syncthreads();
             uint32_t run = incl - sum;
             for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_wtot[w];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) { cur[tid * PER + j] = run; run += cb[j]; }
+            for (int j = 0; j < PER; ++j) { smem_w[o_cur + tid * PER + j] = run; run += cb[j]; }
         }
         __syncthreads();
-        const bool crowded = m.misc[0] != 0;
+        const bool crowded = smem_w[o_flag] != 0;
         if (!crowded) {
             for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
-                const uint32_t e = m.cand[i];
-                tmp[atomicAdd(&cur[e >> bshift], 1u)] = e;
+                const uint32_t e = smem_w[o_cand + i];
+                smem_w[o_tmp + atomicAdd(&smem_w[o_cur + (e >> bshift)], 1u)] = e;
             }
             __syncthreads();
             for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
-                const uint32_t e = tmp[p], b = e >> bshift;
-                const uint32_t lo = b ? cur[b - 1] : 0u;
+                const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
+                const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
                 if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
-                const uint32_t hi = cur[b];
+                const uint32_t hi = smem_w[o_cur + b];
                 uint32_t r = lo;
                 for (uint32_t q = lo; q < hi; ++q) {
-                    const uint32_t x = tmp[q];
+                    const uint32_t x = smem_w[o_tmp + q];
                     r += (x < e) || (x == e && q < p);  // ties keep distinct slots through the index
                 }
                 if (r < s) dst[r] = e;
@@ -1139,7 +1161,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     const uint64_t len_max = d_offsets ? max_read_len : read_len;
     if (s < 2 || len_max <= (uint64_t)K || n_reads > 0xffffffffull) return PG_OK;  // s == 1 needs the positional panic rule
     const uint64_t nmax = len_max - K;
-    const uint64_t item_len = (uint64_t)SELT_ITEM_CHUNKS * SELT_CHUNK;
+    const uint64_t item_len = (uint64_t)SELT_ITEM_CHUNKS * SeltGeom<K>::CHUNK;
     const uint64_t ipr = (nmax + item_len - 1) / item_len;
     if (ipr > 0xffffffffull) return PG_OK;
     // ragged batches map items as row x ipr (rows shorter than the longest leave empty items): bounded waste only
@@ -1147,7 +1169,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     const uint32_t mu = (uint32_t)s + 8u * (uint32_t)ceil(sqrt((double)s)) + 64u;
     uint32_t cap = mu + 8u * (uint32_t)ceil(sqrt((double)mu)) + 96u;
     cap = (cap + 3u) & ~3u;
-    const size_t smem_a = 2 * (size_t)SELT_STAGE_BYTES + (size_t)SELT_SEG * 32 * 4;
+    const size_t smem_a = 2 * (size_t)SeltGeom<K>::STAGE + (size_t)SeltGeom<K>::SEG * 32 * 4;
     const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64) +
                            SEL_NBK + 1 + 16;
     const size_t smem_b = words_b * 4;

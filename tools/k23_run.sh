@@ -1,0 +1,8 @@
+set -x
+timeout 600 python -m pytest tests/test_gpu_mash.py -x -q --timeout 200 --timeout-method thread 2>&1 | tail -4
+timeout 300 python tools/bench_secondary.py --only-k2 2>&1 | cut -c1-200
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 8 --csv --log-file gpurun_out/r02_k2_launches.csv python tools/bench_secondary.py --only-k2 > /dev/null 2>&1
+grep -v "^==" gpurun_out/r02_k2_launches.csv | awk -F'","' '{print substr($5,1,50), $NF}' | head -9
+N=50000 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/r02_k3_launches_v4.csv python tools/prof_k3.py > gpurun_out/k3_under_ncu.log 2>&1
+grep -v "^==" gpurun_out/r02_k3_launches_v4.csv | awk -F'","' '{print substr($5,1,50), $NF}' | tail -9
+timeout 200 python tools/prof_k3.py
