@@ -983,10 +983,23 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         for (uint32_t i = tid; i < SEL_NBK; i += SELT_SEL_THREADS) smem_w[o_cur + i] = 0;
         if (tid == 0) smem_w[o_flag] = 0;
         __syncthreads();
-        for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
-            const uint32_t e = __ldg(src + i);
-            smem_w[o_cand + i] = e;
-            atomicAdd(&smem_w[o_cur + (e >> bshift)], 1u);
+        // loads in batches of 8 per thread: all of a batch are in flight together (one global round trip per
+        // batch instead of one per element -- the row is otherwise a chain of ten load latencies)
+        for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = base + u * SELT_SEL_THREADS + tid;
+                v[u] = i < cnt ? __ldg(src + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = base + u * SELT_SEL_THREADS + tid;
+                if (i < cnt) {
+                    smem_w[o_cand + i] = v[u];
+                    atomicAdd(&smem_w[o_cur + (v[u] >> bshift)], 1u);
+                }
+            }
         }
         __syncthreads();
         {   // exclusive scan over the buckets: 8 per thread, warp scan, warp totals
