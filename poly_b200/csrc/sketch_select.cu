@@ -50,6 +50,15 @@ struct SelSmem {
     uint32_t tmpcap;  // words available at keep[] for the final scatter (keep+kv+bytes are contiguous)
 };
 
+// atom.shared.add with the old value, as ONE instruction.  nvcc wraps atomicAdd(&shared[i], 1) whose result is
+// used into a leader-election loop over the distinct addresses of the warp (ncu: ~12 instructions x up to 32
+// rounds per call); the hardware resolves same-address lanes by itself.
+__device__ __forceinline__ uint32_t smem_fetch_inc(uint32_t *p) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_t p) {
     // little-endian 4-byte window at byte position p of the staged bytes
     const uint32_t a = bytes_w[p >> 2], b = bytes_w[(p >> 2) + 1];
@@ -197,7 +206,7 @@ __device__ bool final_bucket_sort(const SelSmem &m, uint32_t cnt, uint32_t s, ui
     __syncthreads();
     for (uint32_t i = tid; i < cnt; i += NT) {
         const uint32_t e = m.cand[i], b = e >> bshift;
-        if (b <= bt) tmp[bstart[b] + atomicAdd(&cursor[b], 1u)] = e;
+        if (b <= bt) tmp[bstart[b] + smem_fetch_inc(&cursor[b])] = e;
     }
     __syncthreads();
     // rank inside the bucket -> final position (ties keep distinct slots via the index tie-break)
@@ -740,8 +749,11 @@ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
     return t ? (uint32_t)(t - 1) : 0u;
 }
 
+// branch-free: the hash is always stored at the lane's next strip slot and the slot is only kept when the
+// hash is admitted (nvcc turned the `if` into a BSSY / BRA / BSYNC region per k-mer: 11 instructions and a
+// fetch redirect instead of 4 straight-line ones).  c <= number of k-mers walked so far < rows of the strip.
 #define PG_EMIT_STRIP(R_, H_) \
-    if ((H_) <= tm1) { my_strip[c * 32u] = (H_); ++c; }
+    { my_strip[c * 32u] = (H_); c += ((H_) <= tm1) ? 1u : 0u; }
 // RARE variant (expected admissions per warp step << 1, e.g. genomes: T/2^32 ~ s/n ~ 3e-4): one test of the
 // minimum of the step's four hashes and a branch that is almost never taken, instead of four predicated
 // compare/store/add triples.  Only valid for unchecked steps (all four hashes of the step exist).
@@ -1028,7 +1040,7 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         if (!crowded) {
             for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
                 const uint32_t e = smem_w[o_cand + i];
-                smem_w[o_tmp + atomicAdd(&smem_w[o_cur + (e >> bshift)], 1u)] = e;
+                smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (e >> bshift)])] = e;
             }
             __syncthreads();
             for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
