@@ -1038,11 +1038,13 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         __syncthreads();
         const bool crowded = smem_w[o_flag] != 0;
         if (!crowded) {
+#pragma unroll 4
             for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
                 const uint32_t e = smem_w[o_cand + i];
                 smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (e >> bshift)])] = e;
             }
             __syncthreads();
+#pragma unroll 2
             for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
                 const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
                 const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
