@@ -784,7 +784,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     __shared__ __align__(16) uint32_t s_lut[LUT ? 256 : 4];
     __shared__ __align__(8) uint64_t s_bar[3];
     const uint32_t lane = threadIdx.x;
-    const uint64_t item = blockIdx.x;
+    const uint32_t item = blockIdx.x;                   // 32-bit: a 64-bit divide costs ~120 instructions per CTA
     const uint64_t lrow = item / items_per_row;  // row within this launch group
     if (lrow >= n_rows) return;
     const uint64_t row = row0 + lrow;
@@ -798,7 +798,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     }
     const uint64_t n = len > k ? len - k : 0;
     if (n < s || n == 0) return;  // fill regime: other kernel
-    const uint64_t p0 = (item % items_per_row) * (uint64_t)(SELT_ITEM_CHUNKS * SELT_CHUNK);
+    const uint64_t p0 = (uint64_t)(item % items_per_row) * (uint64_t)(SELT_ITEM_CHUNKS * SELT_CHUNK);
     if (p0 >= n) return;
     const uint64_t p1 = min(n, p0 + (uint64_t)(SELT_ITEM_CHUNKS * SELT_CHUNK));
     const uint8_t *seq = bases + beg;
@@ -1044,18 +1044,39 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                 smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (e >> bshift)])] = e;
             }
             __syncthreads();
-#pragma unroll 2
-            for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
-                const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
+            // one thread per BUCKET: its (few) members are ordered in registers and leave as one contiguous
+            // piece of the output -- no per-element loop over the bucket (sum of k^2 compares with two
+            // predicates each), neighbouring threads write neighbouring pieces
+            const uint32_t n_used = (tm1 >> bshift) + 1u;
+            for (uint32_t b = tid; b < n_used; b += SELT_SEL_THREADS) {
                 const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
-                if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
                 const uint32_t hi = smem_w[o_cur + b];
-                uint32_t r = lo;
-                for (uint32_t q = lo; q < hi; ++q) {
-                    const uint32_t x = smem_w[o_tmp + q];
-                    r += (x < e) || (x == e && q < p);  // ties keep distinct slots through the index
+                if (lo >= s || hi == lo) continue;  // beyond the s-th smallest, or empty
+                const uint32_t kk = hi - lo;
+                if (kk == 1) {
+                    dst[lo] = smem_w[o_tmp + lo];
+                } else if (kk <= 4) {
+                    uint32_t v0 = smem_w[o_tmp + lo], v1 = smem_w[o_tmp + lo + 1];
+                    uint32_t v2 = kk > 2 ? smem_w[o_tmp + lo + 2] : 0xffffffffu, v3 = kk > 3 ? smem_w[o_tmp + lo + 3] : 0xffffffffu;
+#define PG_CE(A_, B_) { const uint32_t lo_ = min(A_, B_), hi_ = max(A_, B_); A_ = lo_; B_ = hi_; }
+                    PG_CE(v0, v1) PG_CE(v2, v3) PG_CE(v0, v2) PG_CE(v1, v3) PG_CE(v1, v2)
+#undef PG_CE
+                    dst[lo] = v0;
+                    if (lo + 1 < s) dst[lo + 1] = v1;
+                    if (kk > 2 && lo + 2 < s) dst[lo + 2] = v2;
+                    if (kk > 3 && lo + 3 < s) dst[lo + 3] = v3;
+                } else {  // up to 48 members (checked above): rank by counting, ties by index
+                    for (uint32_t p = lo; p < hi; ++p) {
+                        const uint32_t e = smem_w[o_tmp + p];
+                        uint32_t r = lo;
+#pragma unroll 1
+                        for (uint32_t q = lo; q < hi; ++q) {
+                            const uint32_t x = smem_w[o_tmp + q];
+                            r += (x < e) + ((x == e) & (q < p));
+                        }
+                        if (r < s) dst[r] = e;
+                    }
                 }
-                if (r < s) dst[r] = e;
             }
         } else {  // degenerate value distribution: the generic exact path (radix select, bitonic sort)
             if (!final_bucket_sort<SELT_SEL_THREADS>(m, cnt, s, dst, bshift)) {
