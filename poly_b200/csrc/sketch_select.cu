@@ -1044,39 +1044,19 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                 smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (e >> bshift)])] = e;
             }
             __syncthreads();
-            // one thread per BUCKET: its (few) members are ordered in registers and leave as one contiguous
-            // piece of the output -- no per-element loop over the bucket (sum of k^2 compares with two
-            // predicates each), neighbouring threads write neighbouring pieces
-            const uint32_t n_used = (tm1 >> bshift) + 1u;
-            for (uint32_t b = tid; b < n_used; b += SELT_SEL_THREADS) {
+#pragma unroll 2
+            for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
+                const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
                 const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
+                if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
                 const uint32_t hi = smem_w[o_cur + b];
-                if (lo >= s || hi == lo) continue;  // beyond the s-th smallest, or empty
-                const uint32_t kk = hi - lo;
-                if (kk == 1) {
-                    dst[lo] = smem_w[o_tmp + lo];
-                } else if (kk <= 4) {
-                    uint32_t v0 = smem_w[o_tmp + lo], v1 = smem_w[o_tmp + lo + 1];
-                    uint32_t v2 = kk > 2 ? smem_w[o_tmp + lo + 2] : 0xffffffffu, v3 = kk > 3 ? smem_w[o_tmp + lo + 3] : 0xffffffffu;
-#define PG_CE(A_, B_) { const uint32_t lo_ = min(A_, B_), hi_ = max(A_, B_); A_ = lo_; B_ = hi_; }
-                    PG_CE(v0, v1) PG_CE(v2, v3) PG_CE(v0, v2) PG_CE(v1, v3) PG_CE(v1, v2)
-#undef PG_CE
-                    dst[lo] = v0;
-                    if (lo + 1 < s) dst[lo + 1] = v1;
-                    if (kk > 2 && lo + 2 < s) dst[lo + 2] = v2;
-                    if (kk > 3 && lo + 3 < s) dst[lo + 3] = v3;
-                } else {  // up to 48 members (checked above): rank by counting, ties by index
-                    for (uint32_t p = lo; p < hi; ++p) {
-                        const uint32_t e = smem_w[o_tmp + p];
-                        uint32_t r = lo;
+                uint32_t r = lo;
 #pragma unroll 1
-                        for (uint32_t q = lo; q < hi; ++q) {
-                            const uint32_t x = smem_w[o_tmp + q];
-                            r += (x < e) + ((x == e) & (q < p));
-                        }
-                        if (r < s) dst[r] = e;
-                    }
+                for (uint32_t q = lo; q < hi; ++q) {
+                    const uint32_t x = smem_w[o_tmp + q];
+                    r += (x < e) + ((x == e) & (q < p));  // ties keep distinct slots through the index
                 }
+                if (r < s) dst[r] = e;
             }
         } else {  // degenerate value distribution: the generic exact path (radix select, bitonic sort)
             if (!final_bucket_sort<SELT_SEL_THREADS>(m, cnt, s, dst, bshift)) {
