@@ -247,7 +247,7 @@ int po_fastq_parse(const uint8_t *text, uint64_t n, uint64_t *seq_start, uint64_
             uint64_t q = pos;
             while (q < n && text[q] != '\n') q++;
             line++;                                     /* parser.line++ precedes the error check */
-            if (q >= n) { e = 1; break; }               /* ReadSlice: io.EOF -> handleErr */
+            if (q >= n) { e = (n - pos >= 2 * 32 * 1024) ? 6 : 1; break; } /* ReadSlice: the 64 KiB buffer fills before EOF is seen -> ErrBufferFull, else io.EOF */
             if (q + 1 - pos > 2 * 32 * 1024) { e = 6; break; }
             lb[l] = pos; le[l] = q; pos = q + 1;
             if (l == 0) {

@@ -46,8 +46,11 @@ record_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint64_t *__re
     bool no_at = false;
     for (int l = 0; l < 4 && err == FQ_OK; ++l) {
         const uint64_t li = 4 * r + l;
-        if (li >= n_lines) {  // no newline: ReadSlice returns io.EOF (with or without trailing bytes)
-            err = FQ_ERR_EOF;  // includes the empty tail: Peek succeeded earlier only if bytes remain
+        if (li >= n_lines) {  // no newline left: ReadSlice fills its buffer first -- 64 KiB without a delimiter is
+            // bufio.ErrBufferFull, less is io.EOF (with or without trailing bytes; the empty tail included:
+            // Peek succeeded earlier only if bytes remain)
+            const uint64_t tail = n - line_begin(li);
+            err = tail >= FQ_MAX_LINE ? FQ_ERR_LINE_TOO_LONG : FQ_ERR_EOF;
             err_line = l + 1;
             break;
         }

@@ -27,7 +27,7 @@ def py_parse(text: bytes):
             q = text.find(b"\n", pos)
             line += 1
             if q < 0:
-                return seqs, 1, line
+                return seqs, (6 if n - pos >= 65536 else 1), line   # bufio fills its 64 KiB buffer before it can see EOF
             if q + 1 - pos > 65536:
                 return seqs, 6, line
             ln = text[pos:q]
