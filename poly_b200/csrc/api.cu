@@ -208,10 +208,10 @@ static int ctx_create_locked(int device) {
         if (!c.streams[i]) PG_CUDA(cudaStreamCreateWithFlags(&c.streams[i], cudaStreamNonBlocking));
     {   // Stream-ordered temporaries (cudaMallocAsync) are freed at the end of every call and most calls
         // synchronise: with the default release threshold of 0 the pool would hand its memory back to the
-        // driver each time.  Keep up to 4 GiB cached so that small calls do not pay a driver allocation.
+        // driver each time.  Keep up to 12 GiB cached (the 8 GiB pair tiles of the sparse distance path included) so that small calls do not pay a driver allocation.
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = 4ull << 30, cur = 0;
+            uint64_t keep = 12ull << 30, cur = 0;
             if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < keep)
                 cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }

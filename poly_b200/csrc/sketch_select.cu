@@ -59,6 +59,11 @@ __device__ __forceinline__ uint32_t smem_fetch_inc(uint32_t *p) {
     return old;
 }
 
+__device__ __forceinline__ uint32_t smem_fetch_min(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_t p) {
     // little-endian 4-byte window at byte position p of the staged bytes
     const uint32_t a = bytes_w[p >> 2], b = bytes_w[(p >> 2) + 1];
@@ -742,6 +747,7 @@ struct SeltGeom {
 };
 constexpr int SELT_ITEM_CHUNKS = 8;
 constexpr int SELT_SEL_THREADS = 256;
+constexpr uint32_t SELT_TAB_SLACK = 256;  // slots behind the table for the probes of the largest values
 
 __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
     if ((uint64_t)mu >= n) return 0xffffffffu;  // every hash is a candidate
@@ -958,10 +964,10 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                             uint64_t row0, uint64_t n_rows, uint32_t k, uint32_t s, uint32_t P, uint32_t mu, uint32_t cap,
                             const uint32_t *__restrict__ gcand, const uint32_t *__restrict__ gcnt, uint32_t *__restrict__ out,
                             uint64_t row_stride, uint32_t *__restrict__ count, int32_t *__restrict__ status, const SketchDst extra,
-                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry) {
+                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry, uint32_t tab_slots) {
     extern __shared__ __align__(16) uint32_t smem_w[];
     SelSmem m;
-    m.cand = smem_w;                                 // [max(cap, P)]
+    m.cand = smem_w;                                 // [max(cap, P)]; the ordered-insertion table aliases cand + keep
     m.keep = m.cand + ((max(cap, P) + 3u) & ~3u);    // [max(cap, s + SEL_NBK + 64)]: candidates grouped by bucket / scratch of the generic path
     m.kv = nullptr;
     m.bytes = nullptr;
@@ -987,6 +993,71 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         const uint32_t tm1 = selt_threshold_m1(n, mu);
         const uint32_t bits = 32u - __clz(tm1 | 1u);
         const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
+        // ---- ordered insertion (the usual path) -------------------------------------------------------
+        // The candidates are ~uniform in [0, T): candidate e goes to slot e * M / T of a table of M ~ 1.5 cap slots
+        // and settles by linear probing where every probe is ONE shared atomicMin: the slot keeps the smaller
+        // value, the larger one moves on.  With a monotone home slot the table ends up ASCENDING with gaps
+        // (the parallel form of an insertion sort; duplicates keep their multiplicity), so the output is a
+        // compaction of the first s occupied slots: ~40 thread instructions per candidate instead of the
+        // ~150 of histogram / scan / scatter / rank.  Long probe chains (clustered values) or the table end
+        // raise a flag and the row takes the counting sort below, which re-reads the candidates.
+        bool done = false;
+        if (tm1 != 0xffffffffu && tab_slots != 0) {  // 0xffffffff is the EMPTY mark: unfiltered rows take the other path
+            const uint32_t o_tab = 0, n_tab = tab_slots + SELT_TAB_SLACK;
+            const uint32_t o_f = (uint32_t)(m.misc - smem_w);
+            for (uint32_t i = tid; i < n_tab; i += SELT_SEL_THREADS) smem_w[o_tab + i] = 0xffffffffu;
+            if (tid == 0) smem_w[o_f] = 0;
+            __syncthreads();
+            const uint64_t scale = (((uint64_t)tab_slots) << 32) / ((uint64_t)tm1 + 1);  // home = e * M / T
+            for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
+                uint32_t v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t i = base + u * SELT_SEL_THREADS + tid;
+                    v[u] = i < cnt ? __ldg(src + i) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    uint32_t e = v[u];
+                    if (e == 0xffffffffu) continue;  // past the end of the list
+                    uint32_t i = (uint32_t)(((uint64_t)e * scale) >> 32);
+                    uint32_t probes = 0;
+                    for (;;) {
+                        const uint32_t old = smem_fetch_min(&smem_w[o_tab + i], e);
+                        if (old == 0xffffffffu) break;
+                        e = max(old, e);
+                        ++i;
+                        if (++probes > 128u || i >= n_tab) { smem_w[o_f] = 1u; break; }
+                    }
+                }
+            }
+            __syncthreads();
+            if (smem_w[o_f] == 0) {
+                // compaction: every thread owns a run of consecutive slots; block scan of the occupied counts
+                const uint32_t per = (n_tab + SELT_SEL_THREADS - 1) / SELT_SEL_THREADS;
+                const uint32_t s0 = tid * per, s1 = min(s0 + per, n_tab);
+                uint32_t mine = 0;
+                for (uint32_t i = s0; i < s1; ++i) mine += smem_w[o_tab + i] != 0xffffffffu;
+                uint32_t incl = mine;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((int)(tid & 31u) >= d) incl += y;
+                }
+                __shared__ uint32_t s_wt2[SELT_SEL_THREADS / 32];
+                if ((tid & 31u) == 31u) s_wt2[tid >> 5] = incl;
+                __syncthreads();
+                uint32_t pos = incl - mine;
+                for (uint32_t w = 0; w < (tid >> 5); ++w) pos += s_wt2[w];
+                for (uint32_t i = s0; i < s1 && pos < s; ++i) {
+                    const uint32_t x = smem_w[o_tab + i];
+                    if (x != 0xffffffffu) dst[pos++] = x;
+                }
+                done = true;
+            }
+            __syncthreads();
+        }
+        if (!done) {
         // ---- tight counting sort by bucket, exact rank inside the (tiny) buckets --------------------
         // cur[b]: bucket count -> exclusive start -> (after the scatter) end of bucket b = start of b + 1.
         // Everything is addressed as smem_w[offset + i]: through the pointers of `m` the compiler cannot prove the
@@ -1067,6 +1138,7 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                 for (uint32_t i = tid; i < s; i += SELT_SEL_THREADS) dst[i] = m.cand[i];
             }
         }
+        }  // !done
         if (extra.n > 0) {  // fused all-gather: replicate the finished row into every rank's buffer
             __syncthreads();
 #pragma unroll
@@ -1201,6 +1273,11 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64) +
                            SEL_NBK + 1 + 16;
     const size_t smem_b = words_b * 4;
+    // ordered-insertion table: 1.5 cap slots (+ slack) laid over cand[] + keep[]; 0 = does not fit
+    const size_t words_ck = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64);
+    uint32_t tab_slots = (uint32_t)std::min<size_t>((size_t)cap * 3 / 2, words_ck > SELT_TAB_SLACK ? words_ck - SELT_TAB_SLACK : 0);
+    if (tab_slots < cap + cap / 8) tab_slots = 0;
+    if (getenv("PG_K2T_NO_INSERT")) tab_slots = 0;  // A/B knob
     if (smem_b > 220 * 1024) return PG_OK;
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
     const bool rare = (uint64_t)mu * 512 < nmax;
@@ -1233,7 +1310,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
         const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
         sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)K,
                                                                                          (uint32_t)s, P, mu, cap, d_cand, d_cnt, d_out, row_stride,
-                                                                                         d_count, d_status, ex, d_retry, d_nretry);
+                                                                                         d_count, d_status, ex, d_retry, d_nretry, tab_slots);
         PG_LAUNCH_CHECK("sketch_thresh_select_kernel");
     }
     // rows the estimate failed on (few distinct k-mers, heavy duplication): exact streaming kernel, device-side list
