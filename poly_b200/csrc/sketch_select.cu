@@ -993,7 +993,7 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         const uint32_t tm1 = selt_threshold_m1(n, mu);
         const uint32_t bits = 32u - __clz(tm1 | 1u);
         const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
-        // ---- ordered insertion (the usual path) -------------------------------------------------------
+        // ---- ordered insertion (experimental, PG_K2T_INSERT=1) ----------------------------------------
         // The candidates are ~uniform in [0, T): candidate e goes to slot e * M / T of a table of M ~ 1.5 cap slots
         // and settles by linear probing where every probe is ONE shared atomicMin: the slot keeps the smaller
         // value, the larger one moves on.  With a monotone home slot the table ends up ASCENDING with gaps
@@ -1277,7 +1277,8 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     const size_t words_ck = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64);
     uint32_t tab_slots = (uint32_t)std::min<size_t>((size_t)cap * 3 / 2, words_ck > SELT_TAB_SLACK ? words_ck - SELT_TAB_SLACK : 0);
     if (tab_slots < cap + cap / 8) tab_slots = 0;
-    if (getenv("PG_K2T_NO_INSERT")) tab_slots = 0;  // A/B knob
+    if (!getenv("PG_K2T_INSERT")) tab_slots = 0;  // measured slower than the counting sort (3.14 vs 1.55 ms at cfg3: a warp waits for its
+                                                  // longest probe chain); kept behind the knob for A/B runs, profiles/r02_k2_tuning.md
     if (smem_b > 220 * 1024) return PG_OK;
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
     const bool rare = (uint64_t)mu * 512 < nmax;
