@@ -69,6 +69,37 @@ static __device__ __align__(16) const KmixTable g_kmix_byte = make_kmix_table();
         raw_b = *swp++;                                                                        \
         i += 4;                                                                                \
     }
+// The same word step with a ROLLED ring: slot 0 is always the oldest pre-mix and the ring is shifted by one
+// after the step ((NB - 1) x 4 register moves), so a loop over steps needs ONE step of code instead of NB
+// (k = 31: 15 KB of SASS -> 2.5 KB).  For kernels whose unrolled body no longer fits the instruction caches.
+#define PG_KMER_STEP_ROLLED(CHECKED, EMIT)                                                     \
+    {                                                                                          \
+        uint32_t w[4];                                                                         \
+        w[0] = w_cur;                                                                          \
+        w[1] = __funnelshift_r(w_cur, w_nxt, 8);                                               \
+        w[2] = __funnelshift_r(w_cur, w_nxt, 16);                                              \
+        w[3] = __funnelshift_r(w_cur, w_nxt, 24);                                              \
+        uint32_t h[4];                                                                         \
+        _Pragma("unroll") for (int r = 0; r < 4; ++r) {                                        \
+            uint32_t x = mm3_round0(ring[r][0]);                                               \
+            _Pragma("unroll") for (int j = 1; j < NB; ++j) x = mm3_round(x, ring[r][j]);       \
+            if (LUT) x ^= lds_u32(sb[i + r] * lut_stride + lut_base);                          \
+            else if (TAIL) x ^= mm3_kmix(w[r] & TAILMASK);                                     \
+            x ^= (uint32_t)K;                                                                  \
+            h[r] = mm3_fmix(x);                                                                \
+            _Pragma("unroll") for (int j = 0; j + 1 < NB; ++j) ring[r][j] = ring[r][j + 1];    \
+            ring[r][NB - 1] = mm3_kmix(w[r]);                                                  \
+        }                                                                                      \
+        EMIT(0, h[0]);                                                                         \
+        if (!(CHECKED) || i + 1 < nk) EMIT(1, h[1]);                                           \
+        if (!(CHECKED) || i + 2 < nk) EMIT(2, h[2]);                                           \
+        if (!(CHECKED) || i + 3 < nk) EMIT(3, h[3]);                                           \
+        w_cur = w_nxt;                                                                         \
+        w_nxt = __funnelshift_r(raw_a, raw_b, sh);                                             \
+        raw_a = raw_b;                                                                         \
+        raw_b = *swp++;                                                                        \
+        i += 4;                                                                                \
+    }
 // positional store: hash of k-mer i + r -> my_out[i + r]
 #define PG_EMIT_POSITIONAL(R_, H_) my_out[i + (R_)] = (H_)
 #define PG_K1_STEP(U, CHECKED) PG_KMER_STEP(U, CHECKED, PG_EMIT_POSITIONAL)

@@ -746,6 +746,7 @@ struct SeltGeom {
     static_assert(STEPS % 2 == 1 && (NB % 2 == 0 || STEPS % NB == 0), "segment geometry");
 };
 constexpr int SELT_ITEM_CHUNKS = 8;
+#define SELT_ROLLED_DEFAULT(K_) (false)  // set per k after the A/B (profiles/r02_k2_tuning.md)
 constexpr int SELT_SEL_THREADS = 256;
 constexpr uint32_t SELT_TAB_SLACK = 256;  // slots behind the table for the probes of the largest values
 
@@ -771,7 +772,7 @@ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
         }                                                                                \
     }
 
-template <int K, bool RARE>
+template <int K, bool RARE, bool ROLLED>
 __global__ void __launch_bounds__(32)
 sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets, uint32_t uniform_len,
                           uint64_t row0, uint64_t n_rows, uint32_t items_per_row, uint32_t s, uint32_t mu, uint32_t cap,
@@ -898,23 +899,35 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
             // whole groups of NB word steps without bounds tests, then < NB checked steps: the loop body is
             // NB steps of code (it stays in the instruction cache) instead of a fully unrolled segment
             uint32_t i = 0;
-            const uint32_t n_main = (nk / (4 * NB)) * (4 * NB);
-            if (RARE) {
+            if (ROLLED) {  // one step of code, ring shifted by register moves: the body fits the L0 instruction cache
+                const uint32_t n_full = nk & ~3u;
+                if (RARE) {
 #pragma unroll 1
-                while (i < n_main) {
-#pragma unroll
-                    for (int u = 0; u < NB; ++u) PG_KMER_STEP(u, false, PG_EMIT_STRIP_RARE)
+                    while (i < n_full) PG_KMER_STEP_ROLLED(false, PG_EMIT_STRIP_RARE)
+                } else {
+#pragma unroll 1
+                    while (i < n_full) PG_KMER_STEP_ROLLED(false, PG_EMIT_STRIP)
                 }
+                if (i < nk) PG_KMER_STEP_ROLLED(true, PG_EMIT_STRIP)
             } else {
+                const uint32_t n_main = (nk / (4 * NB)) * (4 * NB);
+                if (RARE) {
 #pragma unroll 1
-                while (i < n_main) {
+                    while (i < n_main) {
 #pragma unroll
-                    for (int u = 0; u < NB; ++u) PG_KMER_STEP(u, false, PG_EMIT_STRIP)
+                        for (int u = 0; u < NB; ++u) PG_KMER_STEP(u, false, PG_EMIT_STRIP_RARE)
+                    }
+                } else {
+#pragma unroll 1
+                    while (i < n_main) {
+#pragma unroll
+                        for (int u = 0; u < NB; ++u) PG_KMER_STEP(u, false, PG_EMIT_STRIP)
+                    }
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < NB; ++u) {
-                if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_STRIP)
+                for (int u = 0; u < NB; ++u) {
+                    if (i < nk) PG_KMER_STEP(u, true, PG_EMIT_STRIP)
+                }
             }
         }
         // flush: compact the strip columns into the row's candidate list (order is irrelevant: a multiset)
@@ -1282,7 +1295,12 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     if (smem_b > 220 * 1024) return PG_OK;
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
     const bool rare = (uint64_t)mu * 512 < nmax;
-    { const int rc_ = func_smem(rare ? (const void *)sketch_thresh_walk_kernel<K, true> : (const void *)sketch_thresh_walk_kernel<K, false>, smem_a); if (rc_ != PG_OK) return rc_; }
+    // PG_K2T_ROLLED=1: one-step loop body with the ring shifted by register moves (A/B knob)
+    static const int rolled_env = [] { const char *e = getenv("PG_K2T_ROLLED"); return e ? atoi(e) : -1; }();
+    const bool rolled = rolled_env >= 0 ? rolled_env != 0 : SELT_ROLLED_DEFAULT(K);
+    const void *walk_fn = rare ? (rolled ? (const void *)sketch_thresh_walk_kernel<K, true, true> : (const void *)sketch_thresh_walk_kernel<K, true, false>)
+                               : (rolled ? (const void *)sketch_thresh_walk_kernel<K, false, true> : (const void *)sketch_thresh_walk_kernel<K, false, false>);
+    { const int rc_ = func_smem(walk_fn, smem_a); if (rc_ != PG_OK) return rc_; }
     { const int rc_ = func_smem((const void *)sketch_thresh_select_kernel, smem_b); if (rc_ != PG_OK) return rc_; }
     int per_sm = 1;
     PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_thresh_select_kernel, SELT_SEL_THREADS, smem_b));
@@ -1301,12 +1319,14 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     for (uint64_t r0 = 0; r0 < n_reads; r0 += group) {
         const uint64_t rows = std::min(group, n_reads - r0);
         PG_CUDA(cudaMemsetAsync(d_cnt, 0, rows * 4, st));
-        if (rare)
-            sketch_thresh_walk_kernel<K, true><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)ipr,
-                                                                                           (uint32_t)s, mu, cap, d_cand, d_cnt, 4u);
-        else
-            sketch_thresh_walk_kernel<K, false><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)ipr,
-                                                                                            (uint32_t)s, mu, cap, d_cand, d_cnt, 4u);
+#define PG_LAUNCH_WALK(RARE_, ROLLED_)                                                                                     \
+    sketch_thresh_walk_kernel<K, RARE_, ROLLED_><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, \
+                                                                                            (uint32_t)ipr, (uint32_t)s, mu, cap, d_cand, d_cnt, 4u)
+        if (rare && rolled) PG_LAUNCH_WALK(true, true);
+        else if (rare) PG_LAUNCH_WALK(true, false);
+        else if (rolled) PG_LAUNCH_WALK(false, true);
+        else PG_LAUNCH_WALK(false, false);
+#undef PG_LAUNCH_WALK
         PG_LAUNCH_CHECK("sketch_thresh_walk_kernel");
         const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
         sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)K,
