@@ -746,11 +746,12 @@ struct SeltGeom {
     static_assert(STEPS % 2 == 1 && (NB % 2 == 0 || STEPS % NB == 0), "segment geometry");
 };
 constexpr int SELT_ITEM_CHUNKS = 8;
-#define SELT_ROLLED_DEFAULT(K_) (false)  // set per k after the A/B (profiles/r02_k2_tuning.md)
+// one-step rolled body from NB = 6 (k >= 24) on: k = 31 walk 2.55 -> 2.04 ms; k = 21 (NB = 5) 1.38 -> 1.43 ms (profiles/r02_k2_tuning.md)
+#define SELT_ROLLED_DEFAULT(K_) ((K_) / 4 >= 6)
 constexpr int SELT_SEL_THREADS = 256;
 constexpr uint32_t SELT_TAB_SLACK = 256;  // slots behind the table for the probes of the largest values
 
-__device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
+__host__ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
     if ((uint64_t)mu >= n) return 0xffffffffu;  // every hash is a candidate
     const uint64_t t = ((uint64_t)mu << 32) / n;
     return t ? (uint32_t)(t - 1) : 0u;
@@ -776,7 +777,7 @@ template <int K, bool RARE, bool ROLLED>
 __global__ void __launch_bounds__(32)
 sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__restrict__ offsets, uint32_t uniform_len,
                           uint64_t row0, uint64_t n_rows, uint32_t items_per_row, uint32_t s, uint32_t mu, uint32_t cap,
-                          uint32_t *__restrict__ gcand, uint32_t *__restrict__ gcnt, uint32_t lut_stride) {
+                          uint32_t *__restrict__ gcand, uint32_t *__restrict__ gcnt, uint32_t lut_stride, uint32_t tm1_uniform) {
     constexpr int NB = K / 4;
     constexpr int TAIL = K % 4;
     constexpr uint32_t TAILMASK = TAIL == 1 ? 0xffu : TAIL == 2 ? 0xffffu : 0xffffffu;
@@ -809,7 +810,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     if (p0 >= n) return;
     const uint64_t p1 = min(n, p0 + (uint64_t)(SELT_ITEM_CHUNKS * SELT_CHUNK));
     const uint8_t *seq = bases + beg;
-    const uint32_t tm1 = selt_threshold_m1(n, mu);
+    const uint32_t tm1 = offsets ? selt_threshold_m1(n, mu) : tm1_uniform;  // fixed-length reads: computed once on the host
     uint32_t *my_cand = gcand + lrow * (uint64_t)cap;
     uint32_t *strip = reinterpret_cast<uint32_t *>(smem + 2 * SELT_STAGE_BYTES);
     uint32_t *my_strip = strip + lane;
@@ -977,7 +978,7 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                             uint64_t row0, uint64_t n_rows, uint32_t k, uint32_t s, uint32_t P, uint32_t mu, uint32_t cap,
                             const uint32_t *__restrict__ gcand, const uint32_t *__restrict__ gcnt, uint32_t *__restrict__ out,
                             uint64_t row_stride, uint32_t *__restrict__ count, int32_t *__restrict__ status, const SketchDst extra,
-                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry, uint32_t tab_slots) {
+                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry, uint32_t tab_slots, uint32_t tm1_uniform) {
     extern __shared__ __align__(16) uint32_t smem_w[];
     SelSmem m;
     m.cand = smem_w;                                 // [max(cap, P)]; the ordered-insertion table aliases cand + keep
@@ -1003,7 +1004,7 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         const uint32_t *src = gcand + lrow * (uint64_t)cap;
         uint32_t *dst = out + row * row_stride;
         // candidates are < T: spread them over the 2048 value buckets (about one candidate per bucket)
-        const uint32_t tm1 = selt_threshold_m1(n, mu);
+        const uint32_t tm1 = offsets ? selt_threshold_m1(n, mu) : tm1_uniform;
         const uint32_t bits = 32u - __clz(tm1 | 1u);
         const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
         // ---- ordered insertion (experimental, PG_K2T_INSERT=1) ----------------------------------------
@@ -1294,6 +1295,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
                                                   // longest probe chain); kept behind the knob for A/B runs, profiles/r02_k2_tuning.md
     if (smem_b > 220 * 1024) return PG_OK;
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
+    const uint32_t tm1_u = d_offsets ? 0u : selt_threshold_m1(nmax, mu);  // every row of a fixed-length batch has n == nmax
     const bool rare = (uint64_t)mu * 512 < nmax;
     // PG_K2T_ROLLED=1: one-step loop body with the ring shifted by register moves (A/B knob)
     static const int rolled_env = [] { const char *e = getenv("PG_K2T_ROLLED"); return e ? atoi(e) : -1; }();
@@ -1321,7 +1323,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
         PG_CUDA(cudaMemsetAsync(d_cnt, 0, rows * 4, st));
 #define PG_LAUNCH_WALK(RARE_, ROLLED_)                                                                                     \
     sketch_thresh_walk_kernel<K, RARE_, ROLLED_><<<(unsigned)(rows * ipr), 32, smem_a, st>>>(d_bases, d_offsets, read_len, r0, rows, \
-                                                                                            (uint32_t)ipr, (uint32_t)s, mu, cap, d_cand, d_cnt, 4u)
+                                                                                            (uint32_t)ipr, (uint32_t)s, mu, cap, d_cand, d_cnt, 4u, tm1_u)
         if (rare && rolled) PG_LAUNCH_WALK(true, true);
         else if (rare) PG_LAUNCH_WALK(true, false);
         else if (rolled) PG_LAUNCH_WALK(false, true);
@@ -1331,7 +1333,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
         const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
         sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)K,
                                                                                          (uint32_t)s, P, mu, cap, d_cand, d_cnt, d_out, row_stride,
-                                                                                         d_count, d_status, ex, d_retry, d_nretry, tab_slots);
+                                                                                         d_count, d_status, ex, d_retry, d_nretry, tab_slots, tm1_u);
         PG_LAUNCH_CHECK("sketch_thresh_select_kernel");
     }
     // rows the estimate failed on (few distinct k-mers, heavy duplication): exact streaming kernel, device-side list
