@@ -59,11 +59,6 @@ __device__ __forceinline__ uint32_t smem_fetch_inc(uint32_t *p) {
     return old;
 }
 
-__device__ __forceinline__ uint32_t smem_fetch_min(uint32_t *p, uint32_t v) {
-    uint32_t old;
-    asm volatile("atom.shared.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
-    return old;
-}
 __device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_t p) {
     // little-endian 4-byte window at byte position p of the staged bytes
     const uint32_t a = bytes_w[p >> 2], b = bytes_w[(p >> 2) + 1];
@@ -749,7 +744,6 @@ constexpr int SELT_ITEM_CHUNKS = 8;
 // one-step rolled body from NB = 6 (k >= 24) on: k = 31 walk 2.55 -> 2.04 ms; k = 21 (NB = 5) 1.38 -> 1.43 ms (profiles/r02_k2_tuning.md)
 #define SELT_ROLLED_DEFAULT(K_) ((K_) / 4 >= 6)
 constexpr int SELT_SEL_THREADS = 256;
-constexpr uint32_t SELT_TAB_SLACK = 256;  // slots behind the table for the probes of the largest values
 
 __host__ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint32_t mu) {
     if ((uint64_t)mu >= n) return 0xffffffffu;  // every hash is a candidate
@@ -971,23 +965,21 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
 #undef PG_EMIT_STRIP
 #undef PG_EMIT_STRIP_RARE
 
-// Stage B: exact bottom-s of the admitted candidates of one row (cnt <= cap by construction; rows whose
-// count is < s or > cap go onto the retry list).
+// Stage B: exact bottom-s of the admitted candidates of one row (cnt <= cap by construction).  A counting sort
+// over 2048 value buckets scaled to T (about one candidate per bucket) with an exact rank inside the bucket;
+// ties keep distinct slots through their index.  Rows whose count is < s or > cap, or whose values crowd into
+// one bucket (degenerate distribution: ranking would be quadratic), go onto the retry list for the exact
+// streaming kernel.  Shared memory is only the bucket-grouped copy (cap words) and the 2048 counters, so ~10
+// rows are in flight per SM; the candidates themselves are read from global memory twice (second time from L2).
 __global__ void __launch_bounds__(SELT_SEL_THREADS)
-sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint64_t *__restrict__ offsets, uint32_t uniform_len,
-                            uint64_t row0, uint64_t n_rows, uint32_t k, uint32_t s, uint32_t P, uint32_t mu, uint32_t cap,
-                            const uint32_t *__restrict__ gcand, const uint32_t *__restrict__ gcnt, uint32_t *__restrict__ out,
-                            uint64_t row_stride, uint32_t *__restrict__ count, int32_t *__restrict__ status, const SketchDst extra,
-                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry, uint32_t tab_slots, uint32_t tm1_uniform) {
-    extern __shared__ __align__(16) uint32_t smem_w[];
-    SelSmem m;
-    m.cand = smem_w;                                 // [max(cap, P)]; the ordered-insertion table aliases cand + keep
-    m.keep = m.cand + ((max(cap, P) + 3u) & ~3u);    // [max(cap, s + SEL_NBK + 64)]: candidates grouped by bucket / scratch of the generic path
-    m.kv = nullptr;
-    m.bytes = nullptr;
-    m.hist = m.keep + max(((cap + 3u) & ~3u), s + SEL_NBK + 64);
-    m.misc = m.hist + SEL_NBK + 1;
-    m.tmpcap = (uint32_t)(m.hist - m.keep);
+sketch_thresh_select_kernel(const uint64_t *__restrict__ offsets, uint32_t uniform_len, uint64_t row0, uint64_t n_rows, uint32_t k,
+                            uint32_t s, uint32_t mu, uint32_t cap, const uint32_t *__restrict__ gcand,
+                            const uint32_t *__restrict__ gcnt, uint32_t *__restrict__ out, uint64_t row_stride,
+                            uint32_t *__restrict__ count, int32_t *__restrict__ status, const SketchDst extra,
+                            uint32_t *__restrict__ retry_rows, uint32_t *__restrict__ n_retry, uint32_t tm1_uniform) {
+    extern __shared__ __align__(16) uint32_t smem_w[];  // tmp[cap] | cur[SEL_NBK] | flag
+    const uint32_t o_tmp = 0, o_cur = (cap + 3u) & ~3u, o_flag = o_cur + SEL_NBK;
+    __shared__ uint32_t s_wtot[SELT_SEL_THREADS / 32];
     const uint32_t tid = threadIdx.x;
     for (uint64_t lrow = blockIdx.x; lrow < n_rows; lrow += gridDim.x) {
         const uint64_t row = row0 + lrow;
@@ -1003,85 +995,13 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
         }
         const uint32_t *src = gcand + lrow * (uint64_t)cap;
         uint32_t *dst = out + row * row_stride;
-        // candidates are < T: spread them over the 2048 value buckets (about one candidate per bucket)
         const uint32_t tm1 = offsets ? selt_threshold_m1(n, mu) : tm1_uniform;
         const uint32_t bits = 32u - __clz(tm1 | 1u);
-        const uint32_t bshift = bits > 11u ? bits - 11u : 0u;
-        // ---- ordered insertion (experimental, PG_K2T_INSERT=1) ----------------------------------------
-        // The candidates are ~uniform in [0, T): candidate e goes to slot e * M / T of a table of M ~ 1.5 cap slots
-        // and settles by linear probing where every probe is ONE shared atomicMin: the slot keeps the smaller
-        // value, the larger one moves on.  With a monotone home slot the table ends up ASCENDING with gaps
-        // (the parallel form of an insertion sort; duplicates keep their multiplicity), so the output is a
-        // compaction of the first s occupied slots: ~40 thread instructions per candidate instead of the
-        // ~150 of histogram / scan / scatter / rank.  Long probe chains (clustered values) or the table end
-        // raise a flag and the row takes the counting sort below, which re-reads the candidates.
-        bool done = false;
-        if (tm1 != 0xffffffffu && tab_slots != 0) {  // 0xffffffff is the EMPTY mark: unfiltered rows take the other path
-            const uint32_t o_tab = 0, n_tab = tab_slots + SELT_TAB_SLACK;
-            const uint32_t o_f = (uint32_t)(m.misc - smem_w);
-            for (uint32_t i = tid; i < n_tab; i += SELT_SEL_THREADS) smem_w[o_tab + i] = 0xffffffffu;
-            if (tid == 0) smem_w[o_f] = 0;
-            __syncthreads();
-            const uint64_t scale = (((uint64_t)tab_slots) << 32) / ((uint64_t)tm1 + 1);  // home = e * M / T
-            for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
-                uint32_t v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const uint32_t i = base + u * SELT_SEL_THREADS + tid;
-                    v[u] = i < cnt ? __ldg(src + i) : 0xffffffffu;
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    uint32_t e = v[u];
-                    if (e == 0xffffffffu) continue;  // past the end of the list
-                    uint32_t i = (uint32_t)(((uint64_t)e * scale) >> 32);
-                    uint32_t probes = 0;
-                    for (;;) {
-                        const uint32_t old = smem_fetch_min(&smem_w[o_tab + i], e);
-                        if (old == 0xffffffffu) break;
-                        e = max(old, e);
-                        ++i;
-                        if (++probes > 128u || i >= n_tab) { smem_w[o_f] = 1u; break; }
-                    }
-                }
-            }
-            __syncthreads();
-            if (smem_w[o_f] == 0) {
-                // compaction: every thread owns a run of consecutive slots; block scan of the occupied counts
-                const uint32_t per = (n_tab + SELT_SEL_THREADS - 1) / SELT_SEL_THREADS;
-                const uint32_t s0 = tid * per, s1 = min(s0 + per, n_tab);
-                uint32_t mine = 0;
-                for (uint32_t i = s0; i < s1; ++i) mine += smem_w[o_tab + i] != 0xffffffffu;
-                uint32_t incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-                    if ((int)(tid & 31u) >= d) incl += y;
-                }
-                __shared__ uint32_t s_wt2[SELT_SEL_THREADS / 32];
-                if ((tid & 31u) == 31u) s_wt2[tid >> 5] = incl;
-                __syncthreads();
-                uint32_t pos = incl - mine;
-                for (uint32_t w = 0; w < (tid >> 5); ++w) pos += s_wt2[w];
-                for (uint32_t i = s0; i < s1 && pos < s; ++i) {
-                    const uint32_t x = smem_w[o_tab + i];
-                    if (x != 0xffffffffu) dst[pos++] = x;
-                }
-                done = true;
-            }
-            __syncthreads();
-        }
-        if (!done) {
-        // ---- tight counting sort by bucket, exact rank inside the (tiny) buckets --------------------
-        // cur[b]: bucket count -> exclusive start -> (after the scatter) end of bucket b = start of b + 1.
-        // Everything is addressed as smem_w[offset + i]: through the pointers of `m` the compiler cannot prove the
-        // shared address space and emits generic loads / atomics (three times the instructions).
-        const uint32_t o_cand = 0, o_tmp = (uint32_t)(m.keep - smem_w), o_cur = (uint32_t)(m.hist - smem_w), o_flag = (uint32_t)(m.misc - smem_w);
+        const uint32_t bshift = bits > 11u ? bits - 11u : 0u;  // candidates are <= tm1: at most 2048 buckets
         for (uint32_t i = tid; i < SEL_NBK; i += SELT_SEL_THREADS) smem_w[o_cur + i] = 0;
         if (tid == 0) smem_w[o_flag] = 0;
         __syncthreads();
-        // loads in batches of 8 per thread: all of a batch are in flight together (one global round trip per
-        // batch instead of one per element -- the row is otherwise a chain of ten load latencies)
+        // histogram; loads in batches of 8 per thread so that a batch is one global round trip
         for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
             uint32_t v[8];
 #pragma unroll
@@ -1090,13 +1010,8 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                 v[u] = i < cnt ? __ldg(src + i) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t i = base + u * SELT_SEL_THREADS + tid;
-                if (i < cnt) {
-                    smem_w[o_cand + i] = v[u];
-                    atomicAdd(&smem_w[o_cur + (v[u] >> bshift)], 1u);
-                }
-            }
+            for (int u = 0; u < 8; ++u)
+                if (base + u * SELT_SEL_THREADS + tid < cnt) atomicAdd(&smem_w[o_cur + (v[u] >> bshift)], 1u);
         }
         __syncthreads();
         {   // exclusive scan over the buckets: 8 per thread, warp scan, warp totals
@@ -1110,10 +1025,9 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
                 const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
                 if ((int)(tid & 31u) >= d) incl += y;
             }
-            __shared__ uint32_t s_wtot[SELT_SEL_THREADS / 32];
             if ((tid & 31u) == 31u) s_wtot[tid >> 5] = incl;
             mx = __reduce_max_sync(0xffffffffu, mx);
-            if ((tid & 31u) == 0 && mx > 48u) atomicMax(&smem_w[o_flag], mx);  // a crowded bucket: quadratic ranking would hurt
+            if ((tid & 31u) == 0 && mx > 48u) atomicMax(&smem_w[o_flag], mx);
             __syncthreads();
             uint32_t run = incl - sum;
             for (uint32_t w = 0; w < (tid >> 5); ++w) run += s_wtot[w];
@@ -1121,38 +1035,38 @@ sketch_thresh_select_kernel(const uint8_t *__restrict__ bases_unused, const uint
             for (int j = 0; j < PER; ++j) { smem_w[o_cur + tid * PER + j] = run; run += cb[j]; }
         }
         __syncthreads();
-        const bool crowded = smem_w[o_flag] != 0;
-        if (!crowded) {
-#pragma unroll 4
-            for (uint32_t i = tid; i < cnt; i += SELT_SEL_THREADS) {
-                const uint32_t e = smem_w[o_cand + i];
-                smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (e >> bshift)])] = e;
-            }
+        if (smem_w[o_flag] != 0) {  // crowded bucket: degenerate values, the exact streaming kernel takes the row
             __syncthreads();
-#pragma unroll 2
-            for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
-                const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
-                const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
-                if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
-                const uint32_t hi = smem_w[o_cur + b];
-                uint32_t r = lo;
-#pragma unroll 1
-                for (uint32_t q = lo; q < hi; ++q) {
-                    const uint32_t x = smem_w[o_tmp + q];
-                    r += (x < e) + ((x == e) & (q < p));  // ties keep distinct slots through the index
-                }
-                if (r < s) dst[r] = e;
-            }
-        } else {  // degenerate value distribution: the generic exact path (radix select, bitonic sort)
-            if (!final_bucket_sort<SELT_SEL_THREADS>(m, cnt, s, dst, bshift)) {
-                if (cnt > s) prune_to_s<SELT_SEL_THREADS>(m, cnt, s);
-                for (uint32_t i = s + tid; i < P; i += SELT_SEL_THREADS) m.cand[i] = 0xffffffffu;
-                __syncthreads();
-                bitonic_sort<SELT_SEL_THREADS>(m.cand, P);
-                for (uint32_t i = tid; i < s; i += SELT_SEL_THREADS) dst[i] = m.cand[i];
-            }
+            if (tid == 0) retry_rows[atomicAdd(n_retry, 1u)] = (uint32_t)row;
+            continue;
         }
-        }  // !done
+        // scatter into bucket order (second read of the candidates: L2); cur[b] ends as the END of bucket b
+        for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t i = base + u * SELT_SEL_THREADS + tid;
+                v[u] = i < cnt ? __ldg(src + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (base + u * SELT_SEL_THREADS + tid < cnt) smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (v[u] >> bshift)])] = v[u];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
+            const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
+            const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
+            if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
+            const uint32_t hi = smem_w[o_cur + b];
+            uint32_t r = lo;
+#pragma unroll 1
+            for (uint32_t q = lo; q < hi; ++q) {
+                const uint32_t x = smem_w[o_tmp + q];
+                r += (x < e) + ((x == e) & (q < p));  // ties keep distinct slots through the index
+            }
+            if (r < s) dst[r] = e;
+        }
         if (extra.n > 0) {  // fused all-gather: replicate the finished row into every rank's buffer
             __syncthreads();
 #pragma unroll
@@ -1284,15 +1198,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     uint32_t cap = mu + 8u * (uint32_t)ceil(sqrt((double)mu)) + 96u;
     cap = (cap + 3u) & ~3u;
     const size_t smem_a = 2 * (size_t)SeltGeom<K>::STAGE + (size_t)SeltGeom<K>::SEG * 32 * 4;
-    const size_t words_b = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64) +
-                           SEL_NBK + 1 + 16;
-    const size_t smem_b = words_b * 4;
-    // ordered-insertion table: 1.5 cap slots (+ slack) laid over cand[] + keep[]; 0 = does not fit
-    const size_t words_ck = (((size_t)std::max(cap, P) + 3) & ~(size_t)3) + std::max<size_t>(((size_t)cap + 3) & ~(size_t)3, (size_t)s + SEL_NBK + 64);
-    uint32_t tab_slots = (uint32_t)std::min<size_t>((size_t)cap * 3 / 2, words_ck > SELT_TAB_SLACK ? words_ck - SELT_TAB_SLACK : 0);
-    if (tab_slots < cap + cap / 8) tab_slots = 0;
-    if (!getenv("PG_K2T_INSERT")) tab_slots = 0;  // measured slower than the counting sort (3.14 vs 1.55 ms at cfg3: a warp waits for its
-                                                  // longest probe chain); kept behind the knob for A/B runs, profiles/r02_k2_tuning.md
+    const size_t smem_b = ((((size_t)cap + 3) & ~(size_t)3) + SEL_NBK + 16) * 4;  // tmp | cur | flag
     if (smem_b > 220 * 1024) return PG_OK;
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
     const uint32_t tm1_u = d_offsets ? 0u : selt_threshold_m1(nmax, mu);  // every row of a fixed-length batch has n == nmax
@@ -1331,9 +1237,9 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
 #undef PG_LAUNCH_WALK
         PG_LAUNCH_CHECK("sketch_thresh_walk_kernel");
         const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
-        sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_bases, d_offsets, read_len, r0, rows, (uint32_t)K,
-                                                                                         (uint32_t)s, P, mu, cap, d_cand, d_cnt, d_out, row_stride,
-                                                                                         d_count, d_status, ex, d_retry, d_nretry, tab_slots, tm1_u);
+        sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_offsets, read_len, r0, rows, (uint32_t)K, (uint32_t)s, mu, cap,
+                                                                                         d_cand, d_cnt, d_out, row_stride, d_count, d_status, ex,
+                                                                                         d_retry, d_nretry, tm1_u);
         PG_LAUNCH_CHECK("sketch_thresh_select_kernel");
     }
     // rows the estimate failed on (few distinct k-mers, heavy duplication): exact streaming kernel, device-side list
