@@ -408,7 +408,8 @@ def secondary_leg(cx, clocks_mhz):
     # >= 7 body rounds x 3 + pre-mix 3 + 3-byte tail 4 + length xor 1 + fmix 8 = 37 thread instructions per k-mer
     inst = 37
     ceiling = 148 * 4 * clk * 32 / inst  # SMs x sub-partitions x issue/clk x lanes / instructions per k-mer
-    out.append({"name": "cfg3 sketch (K2)", "config": "configs[2]: 100k x 10 kbp long reads, k=31, sketchSize=2000", "kernel": (L.pg_last_kernel() or b"").decode(),
+    out.append({"name": "cfg3 sketch (K2)", "config": "configs[2]: 100k x 10 kbp long reads, k=31, sketchSize=2000",
+                "kernel": "sketch_thresh_walk_kernel + sketch_thresh_select_kernel (+ sketch_select_walk_kernel over the retry list, empty here)",
                 "ms": ms, "value": n * RL / ms / 1e6, "unit": "Gbases/s", "gpu_launches_per_pass": launches,
                 "bound": "integer issue (not HBM: 1.8 B/base)", "int_issue_ceiling_gbases_per_s": ceiling / 1e9,
                 "int_issue_ceiling_derivation": f"148 SMs x 4 sub-partitions x {clk / 1e6:.0f} MHz x 32 lanes / {inst} instructions per 31-mer "
