@@ -100,6 +100,17 @@ static __device__ __align__(16) const KmixTable g_kmix_byte = make_kmix_table();
         raw_b = *swp++;                                                                        \
         i += 4;                                                                                \
     }
+// Rotate the ring by G slots (slot G becomes slot 0).  A loop body of G unrolled PG_KMER_STEP(0..G-1) followed by
+// this rotation is the middle ground between the fully unrolled NB-step body (no moves, NB steps of code) and the
+// rolled one ((NB - 1) x 4 moves per step): about (NB + 1) x 4 / G moves per step.
+#define PG_RING_ROTATE(G)                                                                      \
+    {                                                                                          \
+        _Pragma("unroll") for (int r = 0; r < 4; ++r) {                                        \
+            uint32_t t_[NB];                                                                   \
+            _Pragma("unroll") for (int q = 0; q < NB; ++q) t_[q] = ring[r][(q + (G)) % NB];    \
+            _Pragma("unroll") for (int q = 0; q < NB; ++q) ring[r][q] = t_[q];                 \
+        }                                                                                      \
+    }
 // positional store: hash of k-mer i + r -> my_out[i + r]
 #define PG_EMIT_POSITIONAL(R_, H_) my_out[i + (R_)] = (H_)
 #define PG_K1_STEP(U, CHECKED) PG_KMER_STEP(U, CHECKED, PG_EMIT_POSITIONAL)

@@ -59,6 +59,21 @@ __device__ __forceinline__ uint32_t smem_fetch_inc(uint32_t *p) {
     return old;
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {  // shared-space load from a 32-bit shared address
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void stg_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// acc += (x < e), n += (x == e): a compare and a predicated add each (nvcc's own code is add, select, move per counter)
+__device__ __forceinline__ void count_lt_eq(uint32_t x, uint32_t e, uint32_t &acc, uint32_t &n) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.lt.u32 p, %2, %3;\n\tsetp.eq.u32 q, %2, %3;\n\t@p add.u32 %0, %0, 1;\n\t@q add.u32 %1, %1, 1;\n\t}"
+        : "+r"(acc), "+r"(n)
+        : "r"(x), "r"(e));
+}
+
 __device__ __forceinline__ uint32_t smem_window(const uint32_t *bytes_w, uint32_t p) {
     // little-endian 4-byte window at byte position p of the staged bytes
     const uint32_t a = bytes_w[p >> 2], b = bytes_w[(p >> 2) + 1];
@@ -712,20 +727,21 @@ select_merge_kernel(const uint32_t *__restrict__ part, const uint32_t *__restric
 // ---- K2t: the select regime by a value threshold -------------------------------------------------
 // The bottom-s multiset of n hashes is contained in {h < T} as soon as that set has >= s members.  For
 // hash values that behave like uniform draws (murmur3 of distinct k-mers) T = mu/n * 2^32 with
-// mu = s + 8 sqrt(s) + 64 admits mu hashes on average and fewer than s only 8 standard deviations below
+// mu = s + 6 sqrt(s) + 48 admits mu hashes on average and fewer than s only 6 standard deviations below
 // the mean -- and whether it did is CHECKED, never assumed: a row whose admitted count is < s (few
 // distinct k-mers) or exceeds its buffer (heavy duplication below T) is redone by the exact streaming
 // kernel above (retry list built on the device, no host round trip).  So:
-//   A. sketch_thresh_walk_kernel<K>: one WARP per work item (<= 8 chunks of 32 x 68 positions of one
-//      row; long sequences become many items, so there is no host-side slicing and no merge pass).
-//      Chunks arrive by double-buffered 1-D TMA bulk copies; lane l walks 68 consecutive k-mers with
-//      the register ring of kmer_walk.cuh (lanes read 17 words apart: bank-conflict free; one ring
-//      prologue per 68 k-mers instead of per 20) and drops the hashes below T into its private strip
-//      column -- a compare, a predicated store and a predicated add: no vote, no atomic, no barrier.
-//      After the chunk the strips are compacted row by row with ballots into the row's candidate list
-//      in global memory (one global atomic per warp-chunk reserves the space; coalesced stores).
-//   B. sketch_thresh_select_kernel: one CTA per row loads the ~mu candidates and runs the exact
-//      bucket sort-select (ties counted) -> ascending bottom-s, stored to every destination.
+//   A. sketch_thresh_walk_kernel<K, RARE, ROLLED>: one WARP per work item (<= 8 chunks of 32 x SEG
+//      positions of one row, SeltGeom<K>; long sequences become many items, so there is no host-side
+//      slicing and no merge pass).  Chunks arrive by double-buffered 1-D TMA bulk copies; lane l walks SEG
+//      consecutive k-mers with the register ring of kmer_walk.cuh (one ring prologue per SEG k-mers
+//      instead of per 20) and stores every hash into its private strip column, whose fill count advances
+//      only for hashes <= T -- a store, a compare and an add, branch-free: no vote, no atomic, no barrier.
+//      After the chunk the strips are compacted into the row's candidate list in global memory (one
+//      global atomic per warp-chunk reserves the space; dense run of stores through the dead stage buffer).
+//   B. sketch_thresh_select_kernel<U>: one CTA per row, counting sort of the ~mu candidates over 2048
+//      value buckets + exact rank inside each bucket (ties counted) -> ascending bottom-s, stored to
+//      every destination.
 // Extra HBM traffic: mu words per row written and read once (cfg3: 2 x 1 GB next to 1.8 GB algorithmic).
 // Positions per lane per chunk: 4 x an ODD number of word steps (lanes read their staged words an odd number
 // of words apart: bank-conflict free) that is a multiple of NB = K / 4 where NB is odd, so that a full
@@ -734,14 +750,15 @@ select_merge_kernel(const uint32_t *__restrict__ part, const uint32_t *__restric
 template <int K>
 struct SeltGeom {
     static constexpr int NB = K / 4;
-    static constexpr int STEPS = NB == 2 ? 17 : NB == 3 ? 21 : NB == 4 ? 17 : NB == 5 ? 15 : NB == 6 ? 19 : NB == 7 ? 21 : 17;
+    static constexpr int STEPS = NB == 2 ? 17 : NB == 3 ? 21 : NB == 4 ? 17 : NB == 5 ? 15 : 21;  // NB >= 6: whole groups of 3 steps
     static constexpr int SEG = 4 * STEPS;      // 60 .. 84 k-mer positions
     static constexpr int CHUNK = 32 * SEG;     // per warp chunk
     static constexpr int STAGE = (15 + CHUNK + 32 + 48 + 15 + 255) / 256 * 256;  // head + chunk + k + over-read pad; also the dense flush buffer
     static_assert(STEPS % 2 == 1 && (NB % 2 == 0 || STEPS % NB == 0), "segment geometry");
 };
 constexpr int SELT_ITEM_CHUNKS = 8;
-// one-step rolled body from NB = 6 (k >= 24) on: k = 31 walk 2.55 -> 2.04 ms; k = 21 (NB = 5) 1.38 -> 1.43 ms (profiles/r02_k2_tuning.md)
+// rolled body (groups of 3 steps, then a ring rotation) from NB = 6 (k >= 24) on; k = 21 (NB = 5) keeps the unrolled 5-step
+// body: 1.38 vs 1.43 ms (profiles/r02_k2_tuning.md)
 #define SELT_ROLLED_DEFAULT(K_) ((K_) / 4 >= 6)
 constexpr int SELT_SEL_THREADS = 256;
 
@@ -751,11 +768,20 @@ __host__ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint3
     return t ? (uint32_t)(t - 1) : 0u;
 }
 
+__device__ __forceinline__ void strip_put(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void strip_advance_if_le(uint32_t &saddr, uint32_t h, uint32_t t) {
+    asm("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p add.u32 %0, %0, 128;\n\t}" : "+r"(saddr) : "r"(h), "r"(t));
+}
+
 // branch-free: the hash is always stored at the lane's next strip slot and the slot is only kept when the
 // hash is admitted (nvcc turned the `if` into a BSSY / BRA / BSYNC region per k-mer: 11 instructions and a
 // fetch redirect instead of 4 straight-line ones).  c <= number of k-mers walked so far < rows of the strip.
+// The slot is a running shared-space address: a store, a compare and a predicated add per k-mer (indexing
+// my_strip[c * 32] cost a shift, an or and an add more, ncu source page).
 #define PG_EMIT_STRIP(R_, H_) \
-    { my_strip[c * 32u] = (H_); c += ((H_) <= tm1) ? 1u : 0u; }
+    { strip_put(sa, (H_)); strip_advance_if_le(sa, (H_), tm1); }
 // RARE variant (expected admissions per warp step << 1, e.g. genomes: T/2^32 ~ s/n ~ 3e-4): one test of the
 // minimum of the step's four hashes and a branch that is almost never taken, instead of four predicated
 // compare/store/add triples.  Only valid for unchecked steps (all four hashes of the step exist).
@@ -763,7 +789,7 @@ __host__ __device__ __forceinline__ uint32_t selt_threshold_m1(uint64_t n, uint3
     if ((R_) == 3) {                                                                     \
         if (min(min(h[0], h[1]), min(h[2], h[3])) <= tm1) {                              \
             _Pragma("unroll") for (int rr = 0; rr < 4; ++rr)                             \
-                if (h[rr] <= tm1) { my_strip[c * 32u] = h[rr]; ++c; }                    \
+                if (h[rr] <= tm1) { strip_put(sa, h[rr]); sa += 128u; }                  \
         }                                                                                \
     }
 
@@ -808,6 +834,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
     uint32_t *my_cand = gcand + lrow * (uint64_t)cap;
     uint32_t *strip = reinterpret_cast<uint32_t *>(smem + 2 * SELT_STAGE_BYTES);
     uint32_t *my_strip = strip + lane;
+    const uint32_t sa0 = smem_u32(my_strip);
 
     if (lane == 0) {
         mbar_init(&s_bar[0], 1);
@@ -856,7 +883,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
         else          { mbar_wait(&s_bar[1], par1); par1 ^= 1u; }
         if (!tail_by_tma(c0, ch)) __syncwarp();  // plain-store part of this stage
 
-        uint32_t c = 0;  // hashes this lane admitted in this chunk
+        uint32_t sa = sa0;  // shared address of the lane's next strip slot: (sa - sa0) / 128 hashes admitted in this chunk
         // A full chunk gives every lane SELT_SEG positions.  A shorter (last) chunk is spread over all lanes
         // instead of leaving the upper lanes idle while the lower ones walk full segments: an odd number
         // of word steps per lane keeps the lanes' staged words in different banks.
@@ -894,15 +921,28 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
             // whole groups of NB word steps without bounds tests, then < NB checked steps: the loop body is
             // NB steps of code (it stays in the instruction cache) instead of a fully unrolled segment
             uint32_t i = 0;
-            if (ROLLED) {  // one step of code, ring shifted by register moves: the body fits the L0 instruction cache
+            if (ROLLED) {  // groups of 3 steps of code with the ring rotated after each group: the body fits the instruction cache
                 const uint32_t n_full = nk & ~3u;
+                const uint32_t n_grp = (nk / 12u) * 12u;
                 if (RARE) {
 #pragma unroll 1
-                    while (i < n_full) PG_KMER_STEP_ROLLED(false, PG_EMIT_STRIP_RARE)
+                    while (i < n_grp) {
+                        PG_KMER_STEP(0, false, PG_EMIT_STRIP_RARE)
+                        PG_KMER_STEP(1, false, PG_EMIT_STRIP_RARE)
+                        PG_KMER_STEP(2, false, PG_EMIT_STRIP_RARE)
+                        PG_RING_ROTATE(3)
+                    }
                 } else {
 #pragma unroll 1
-                    while (i < n_full) PG_KMER_STEP_ROLLED(false, PG_EMIT_STRIP)
+                    while (i < n_grp) {
+                        PG_KMER_STEP(0, false, PG_EMIT_STRIP)
+                        PG_KMER_STEP(1, false, PG_EMIT_STRIP)
+                        PG_KMER_STEP(2, false, PG_EMIT_STRIP)
+                        PG_RING_ROTATE(3)
+                    }
                 }
+#pragma unroll 1
+                while (i < n_full) PG_KMER_STEP_ROLLED(false, PG_EMIT_STRIP)  // < 3 whole steps left: one step of code, ring shifted per step
                 if (i < nk) PG_KMER_STEP_ROLLED(true, PG_EMIT_STRIP)
             } else {
                 const uint32_t n_main = (nk / (4 * NB)) * (4 * NB);
@@ -926,6 +966,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
             }
         }
         // flush: compact the strip columns into the row's candidate list (order is irrelevant: a multiset)
+        const uint32_t c = (sa - sa0) >> 7;
         uint32_t incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -971,6 +1012,7 @@ sketch_thresh_walk_kernel(const uint8_t *__restrict__ bases, const uint64_t *__r
 // one bucket (degenerate distribution: ranking would be quadratic), go onto the retry list for the exact
 // streaming kernel.  Shared memory is only the bucket-grouped copy (cap words) and the 2048 counters, so ~10
 // rows are in flight per SM; the candidates themselves are read from global memory twice (second time from L2).
+template <int U, bool MUL>  // MUL: scaled buckets (all 2048 in use whatever T is) or plain shift; U: candidates loaded per thread and batch: chosen so that a typical row is a whole number of batches
 __global__ void __launch_bounds__(SELT_SEL_THREADS)
 sketch_thresh_select_kernel(const uint64_t *__restrict__ offsets, uint32_t uniform_len, uint64_t row0, uint64_t n_rows, uint32_t k,
                             uint32_t s, uint32_t mu, uint32_t cap, const uint32_t *__restrict__ gcand,
@@ -995,23 +1037,29 @@ sketch_thresh_select_kernel(const uint64_t *__restrict__ offsets, uint32_t unifo
         }
         const uint32_t *src = gcand + lrow * (uint64_t)cap;
         uint32_t *dst = out + row * row_stride;
+        asm volatile("" : "+l"(dst));  // keep the row pointer in registers: nvcc otherwise redoes the 64-bit multiply per store
         const uint32_t tm1 = offsets ? selt_threshold_m1(n, mu) : tm1_uniform;
+        // shift: bucket(e) = e >> (bits(T) - 11), between 1024 and 2048 buckets in use.  MUL (rows whose T sits just above a
+        // power of two, ragged batches): the 16 leading bits of e times 2048 * 2^16 / (T16 + 1) -- monotone, < 2048 for
+        // e <= T, (nearly) all 2048 buckets in use; a shift, a 32-bit multiply and a shift (__umulhi measured slower)
         const uint32_t bits = 32u - __clz(tm1 | 1u);
-        const uint32_t bshift = bits > 11u ? bits - 11u : 0u;  // candidates are <= tm1: at most 2048 buckets
+        const uint32_t bshift = MUL ? (bits > 16u ? bits - 16u : 0u) : (bits > 11u ? bits - 11u : 0u);
+        const uint32_t bscale = MUL ? ((uint32_t)SEL_NBK << 16) / ((tm1 >> bshift) + 1u) : 0u;
+        auto bucket = [&](uint32_t e) -> uint32_t { return MUL ? ((e >> bshift) * bscale) >> 16 : e >> bshift; };
         for (uint32_t i = tid; i < SEL_NBK; i += SELT_SEL_THREADS) smem_w[o_cur + i] = 0;
         if (tid == 0) smem_w[o_flag] = 0;
         __syncthreads();
-        // histogram; loads in batches of 8 per thread so that a batch is one global round trip
-        for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
-            uint32_t v[8];
+        // histogram; loads in batches of U per thread so that a batch is one global round trip
+        for (uint32_t base = 0; base < cnt; base += U * SELT_SEL_THREADS) {
+            uint32_t v[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const uint32_t i = base + u * SELT_SEL_THREADS + tid;
                 v[u] = i < cnt ? __ldg(src + i) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (base + u * SELT_SEL_THREADS + tid < cnt) atomicAdd(&smem_w[o_cur + (v[u] >> bshift)], 1u);
+            for (int u = 0; u < U; ++u)
+                if (base + u * SELT_SEL_THREADS + tid < cnt) atomicAdd(&smem_w[o_cur + bucket(v[u])], 1u);
         }
         __syncthreads();
         {   // exclusive scan over the buckets: 8 per thread, warp scan, warp totals
@@ -1041,31 +1089,42 @@ sketch_thresh_select_kernel(const uint64_t *__restrict__ offsets, uint32_t unifo
             continue;
         }
         // scatter into bucket order (second read of the candidates: L2); cur[b] ends as the END of bucket b
-        for (uint32_t base = 0; base < cnt; base += 8 * SELT_SEL_THREADS) {
-            uint32_t v[8];
+        for (uint32_t base = 0; base < cnt; base += U * SELT_SEL_THREADS) {
+            uint32_t v[U];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const uint32_t i = base + u * SELT_SEL_THREADS + tid;
                 v[u] = i < cnt ? __ldg(src + i) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (base + u * SELT_SEL_THREADS + tid < cnt) smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + (v[u] >> bshift)])] = v[u];
+            for (int u = 0; u < U; ++u)
+                if (base + u * SELT_SEL_THREADS + tid < cnt) smem_w[o_tmp + smem_fetch_inc(&smem_w[o_cur + bucket(v[u])])] = v[u];
         }
         __syncthreads();
+        {   // rank inside the bucket, through explicit shared-space addresses (kept in registers across the loop)
+            const uint32_t s_tmp = smem_u32(smem_w + o_tmp), s_cur = smem_u32(smem_w + o_cur);
 #pragma unroll 2
-        for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
-            const uint32_t e = smem_w[o_tmp + p], b = e >> bshift;
-            const uint32_t lo = b ? smem_w[o_cur + b - 1] : 0u;
-            if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
-            const uint32_t hi = smem_w[o_cur + b];
-            uint32_t r = lo;
+            for (uint32_t p = tid; p < cnt; p += SELT_SEL_THREADS) {
+                const uint32_t e = lds_u32(s_tmp + 4u * p), b = bucket(e);
+                const uint32_t lo = b ? lds_u32(s_cur + 4u * b - 4u) : 0u;
+                if (lo >= s) continue;  // the whole bucket lies beyond the s-th smallest
+                uint32_t a = s_tmp + 4u * lo;
+                const uint32_t a_hi = s_tmp + 4u * lds_u32(s_cur + 4u * b);
+                uint32_t r = lo, m = 0;  // r: strictly smaller values in front; m: copies of e in the bucket (itself included)
 #pragma unroll 1
-            for (uint32_t q = lo; q < hi; ++q) {
-                const uint32_t x = smem_w[o_tmp + q];
-                r += (x < e) + ((x == e) & (q < p));  // ties keep distinct slots through the index
+                do {  // the bucket holds e itself: never empty
+                    const uint32_t x = lds_u32(a);
+                    a += 4u;
+                    count_lt_eq(x, e, r, m);
+                } while (a != a_hi);
+                // every copy of a tied value writes the whole run r .. r + m - 1 (same words): no tie-break by index needed
+                if (r < s) stg_u32(dst + r, e);
+                if (m > 1) {
+#pragma unroll 1
+                    for (uint32_t t = 1; t < m; ++t)
+                        if (r + t < s) stg_u32(dst + r + t, e);
+                }
             }
-            if (r < s) dst[r] = e;
         }
         if (extra.n > 0) {  // fused all-gather: replicate the finished row into every rank's buffer
             __syncthreads();
@@ -1194,7 +1253,7 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     if (ipr > 0xffffffffull) return PG_OK;
     // ragged batches map items as row x ipr (rows shorter than the longest leave empty items): bounded waste only
     if (d_offsets && ipr > 1 && n_reads * ipr > (4ull << 20)) return PG_OK;
-    const uint32_t mu = (uint32_t)s + 8u * (uint32_t)ceil(sqrt((double)s)) + 64u;
+    const uint32_t mu = (uint32_t)s + 6u * (uint32_t)ceil(sqrt((double)s)) + 48u;
     uint32_t cap = mu + 8u * (uint32_t)ceil(sqrt((double)mu)) + 96u;
     cap = (cap + 3u) & ~3u;
     const size_t smem_a = 2 * (size_t)SeltGeom<K>::STAGE + (size_t)SeltGeom<K>::SEG * 32 * 4;
@@ -1203,15 +1262,38 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
     // admission probability of the longest rows: below 1/512 a warp step (128 hashes) admits something a quarter of the time
     const uint32_t tm1_u = d_offsets ? 0u : selt_threshold_m1(nmax, mu);  // every row of a fixed-length batch has n == nmax
     const bool rare = (uint64_t)mu * 512 < nmax;
-    // PG_K2T_ROLLED=1: one-step loop body with the ring shifted by register moves (A/B knob)
-    static const int rolled_env = [] { const char *e = getenv("PG_K2T_ROLLED"); return e ? atoi(e) : -1; }();
-    const bool rolled = rolled_env >= 0 ? rolled_env != 0 : SELT_ROLLED_DEFAULT(K);
+    // PG_K2T_ROLLED=1: 3-step loop body with the ring rotated by register moves, =0: NB-step body (A/B and test knob)
+    const int rolled_env = [] { const char *e = getenv("PG_K2T_ROLLED"); return e ? atoi(e) : -1; }();
+    const bool rolled = K / 4 >= 3 && (rolled_env >= 0 ? rolled_env != 0 : SELT_ROLLED_DEFAULT(K));  // the 3-step group needs NB >= 3
     const void *walk_fn = rare ? (rolled ? (const void *)sketch_thresh_walk_kernel<K, true, true> : (const void *)sketch_thresh_walk_kernel<K, true, false>)
                                : (rolled ? (const void *)sketch_thresh_walk_kernel<K, false, true> : (const void *)sketch_thresh_walk_kernel<K, false, false>);
     { const int rc_ = func_smem(walk_fn, smem_a); if (rc_ != PG_OK) return rc_; }
-    { const int rc_ = func_smem((const void *)sketch_thresh_select_kernel, smem_b); if (rc_ != PG_OK) return rc_; }
+    // batch width of the select: fewest load slots for a typical row (mu + 2.5 sigma candidates), ties to the wider batch
+    const uint32_t typ = mu + (uint32_t)(2.5 * sqrt((double)mu));
+    int sel_u = 8;
+    {
+        uint32_t best = ~0u;
+        for (int u : {3, 4, 5, 6, 8}) {
+            const uint32_t slots = (typ + u * SELT_SEL_THREADS - 1) / (u * SELT_SEL_THREADS) * u;
+            if (slots <= best) { best = slots; sel_u = u; }
+        }
+    }
+    const int sel_u_env = [] { const char *e = getenv("PG_K2T_SEL_U"); return e ? atoi(e) : 0; }();      // A/B and test knobs, read per call
+    const int sel_mul_env = [] { const char *e = getenv("PG_K2T_SEL_MUL"); return e ? atoi(e) : -1; }();
+    if (sel_u_env == 3 || sel_u_env == 4 || sel_u_env == 5 || sel_u_env == 6 || sel_u_env == 8) sel_u = sel_u_env;
+    // bucket function: the plain shift when it uses >= 3/4 of the 2048 buckets (fixed-length batch: T known here)
+    bool sel_mul = true;
+    if (!d_offsets) {
+        const uint32_t tb = 32u - (uint32_t)__builtin_clz(tm1_u | 1u);
+        sel_mul = ((tm1_u >> (tb > 11u ? tb - 11u : 0u)) + 1u) < 1536u;
+    }
+    if (sel_mul_env >= 0) sel_mul = sel_mul_env != 0;
+#define PG_SEL_FN(U_) (sel_mul ? (const void *)sketch_thresh_select_kernel<U_, true> : (const void *)sketch_thresh_select_kernel<U_, false>)
+    const void *sel_fn = sel_u == 3 ? PG_SEL_FN(3) : sel_u == 4 ? PG_SEL_FN(4) : sel_u == 5 ? PG_SEL_FN(5) : sel_u == 6 ? PG_SEL_FN(6) : PG_SEL_FN(8);
+#undef PG_SEL_FN
+    { const int rc_ = func_smem(sel_fn, smem_b); if (rc_ != PG_OK) return rc_; }
     int per_sm = 1;
-    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sketch_thresh_select_kernel, SELT_SEL_THREADS, smem_b));
+    PG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sel_fn, SELT_SEL_THREADS, smem_b));
     // candidate lists: cap words per row, rows in groups of <= 1.5 GiB of temporaries
     uint64_t rows_per_group = std::max<uint64_t>(1, std::min<uint64_t>((3ull << 28) / cap, 0x7fffffffull / ipr));
     if (const char *e = getenv("PG_K2T_GROUP_ROWS"))  // test knob: force several launch groups
@@ -1237,9 +1319,20 @@ static int launch_select_thresh(const uint8_t *d_bases, const uint64_t *d_offset
 #undef PG_LAUNCH_WALK
         PG_LAUNCH_CHECK("sketch_thresh_walk_kernel");
         const uint64_t blocks = std::min<uint64_t>(rows, (uint64_t)sm_count() * std::max(per_sm, 1));
-        sketch_thresh_select_kernel<<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_offsets, read_len, r0, rows, (uint32_t)K, (uint32_t)s, mu, cap,
-                                                                                         d_cand, d_cnt, d_out, row_stride, d_count, d_status, ex,
-                                                                                         d_retry, d_nretry, tm1_u);
+#define PG_LAUNCH_SEL_(U_, M_)                                                                                                 \
+    sketch_thresh_select_kernel<U_, M_><<<(unsigned)blocks, SELT_SEL_THREADS, smem_b, st>>>(d_offsets, read_len, r0, rows, (uint32_t)K, (uint32_t)s, \
+                                                                                             mu, cap, d_cand, d_cnt, d_out, row_stride, d_count,     \
+                                                                                             d_status, ex, d_retry, d_nretry, tm1_u)
+#define PG_LAUNCH_SEL(U_) do { if (sel_mul) PG_LAUNCH_SEL_(U_, true); else PG_LAUNCH_SEL_(U_, false); } while (0)
+        switch (sel_u) {
+            case 3: PG_LAUNCH_SEL(3); break;
+            case 4: PG_LAUNCH_SEL(4); break;
+            case 5: PG_LAUNCH_SEL(5); break;
+            case 6: PG_LAUNCH_SEL(6); break;
+            default: PG_LAUNCH_SEL(8); break;
+        }
+#undef PG_LAUNCH_SEL
+#undef PG_LAUNCH_SEL_
         PG_LAUNCH_CHECK("sketch_thresh_select_kernel");
     }
     // rows the estimate failed on (few distinct k-mers, heavy duplication): exact streaming kernel, device-side list

@@ -435,18 +435,27 @@ def test_select_threshold_path(gpu, oracle, monkeypatch):
     retry list hands to the exact streaming kernel.  Everything bit-exact against the oracle."""
     rng = np.random.default_rng(77)
     monkeypatch.setenv("PG_K2T_GROUP_ROWS", "7")
-    for k, s, L, n in [(21, 1000, 40_000, 20), (31, 2000, 10_000, 40), (16, 64, 5_000, 33), (21, 1000, 1021 + 21, 9), (21, 1000, 1300, 9),
-                       (24, 5000, 30_000, 5), (32, 3, 9_000, 12), (11, 500, 2176 * 8 + 11 + 1, 6)]:
-        reads = rng.choice(list(b"ACGT"), size=n * L).astype(np.uint8).reshape(n, L)
-        reads[1] = ord("A")                                                   # homopolymer: one distinct hash
-        reads[2] = np.frombuffer((b"ACG" * (L // 3 + 1))[:L], dtype=np.uint8)  # period 3: three distinct hashes
-        reads[3] = rng.choice(list(b"AC"), size=L).astype(np.uint8)           # low complexity
-        reads[4, : L // 2] = reads[4, L // 2: 2 * (L // 2)]                    # every k-mer of one half twice
-        got = mash.sketch_uniform(reads.reshape(-1), n, L, k, s)
-        rc, want = oracle.sketch_batch(reads.reshape(-1), synth.uniform_offsets(n, L), k, s, variant=1)
-        assert rc == 0
-        cnt = min(L - k, s)
-        assert np.array_equal(got, want[:, :cnt]), (k, s, L, n, [i for i in range(n) if not np.array_equal(got[i], want[i, :cnt])])
+    cases = [(21, 1000, 40_000, 20), (31, 2000, 10_000, 40), (16, 64, 5_000, 33), (21, 1000, 1021 + 21, 9), (21, 1000, 1300, 9),
+             (24, 5000, 30_000, 5), (32, 3, 9_000, 12), (11, 500, 2176 * 8 + 11 + 1, 6), (28, 300, 7_013, 8)]
+    # both bucket functions of the select stage and both loop shapes of the walk, on every case
+    for knobs in ({}, {"PG_K2T_SEL_MUL": "0", "PG_K2T_ROLLED": "0", "PG_K2T_SEL_U": "3"}, {"PG_K2T_SEL_MUL": "1", "PG_K2T_ROLLED": "1", "PG_K2T_SEL_U": "8"}):
+        for name in ("PG_K2T_SEL_MUL", "PG_K2T_ROLLED", "PG_K2T_SEL_U"):
+            monkeypatch.delenv(name, raising=False)
+        for name, v in knobs.items():
+            monkeypatch.setenv(name, v)
+        for k, s, L, n in cases:
+            reads = rng.choice(list(b"ACGT"), size=n * L).astype(np.uint8).reshape(n, L)
+            reads[1] = ord("A")                                                   # homopolymer: one distinct hash
+            reads[2] = np.frombuffer((b"ACG" * (L // 3 + 1))[:L], dtype=np.uint8)  # period 3: three distinct hashes
+            reads[3] = rng.choice(list(b"AC"), size=L).astype(np.uint8)           # low complexity
+            reads[4, : L // 2] = reads[4, L // 2: 2 * (L // 2)]                    # every k-mer of one half twice
+            got = mash.sketch_uniform(reads.reshape(-1), n, L, k, s)
+            rc, want = oracle.sketch_batch(reads.reshape(-1), synth.uniform_offsets(n, L), k, s, variant=1)
+            assert rc == 0
+            cnt = min(L - k, s)
+            assert np.array_equal(got, want[:, :cnt]), (knobs, k, s, L, n, [i for i in range(n) if not np.array_equal(got[i], want[i, :cnt])])
+    for name in ("PG_K2T_SEL_MUL", "PG_K2T_ROLLED", "PG_K2T_SEL_U"):
+        monkeypatch.delenv(name, raising=False)
     # ragged batch whose longest read spans several items: row x item mapping with empty items
     lens = [int(x) for x in rng.integers(1200, 50_000, 30)] + [0, 5, 1021, 1022, 1023]
     seqs = [bytes(rng.choice(list(b"ACGT"), size=l).astype(np.uint8)) for l in lens] + [b"T" * 30_000]
