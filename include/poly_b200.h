@@ -98,7 +98,8 @@ int pg_stream_sync(void *stream);
  * status[i] (may be NULL) reports per-read PG_ITEM_PANIC for s in {0,1} inputs on
  * which mash.go:96-98 indexes Sketches[-1]; k < 0 or s < 0 is PG_ERR_ARG.
  * Reads may be of any length (a batch of few long sequences is cut into slices that are sketched
- * in parallel and merged); in the n_i >= s regime s <= 16384 and k <= 1024, PG_ERR_UNSUPPORTED beyond.
+ * in parallel and merged) and k and s of any size: in the n_i >= s regime, sketches above 16384 words
+ * or k above 1024 take a slower global-memory path instead of the shared-memory kernels.
  */
 #define PG_SKETCH_PAD_ZERO 1u
 

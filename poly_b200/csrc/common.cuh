@@ -73,6 +73,10 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
                          uint64_t n_reads, int k, int s, uint32_t flags, uint32_t *d_out,
                          uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st,
                          const SketchDst *extra = nullptr, uint64_t max_read_len = 0);
+// sketch_select_large.cu: the select regime for s > 16384 or k > 1024 (hashes through global memory)
+int launch_sketch_select_large(const uint8_t *d_bases, const uint64_t *d_offsets, uint32_t read_len, uint64_t n_reads, int k, int s,
+                               uint32_t *d_out, uint64_t row_stride, uint32_t *d_count, int32_t *d_status, cudaStream_t st,
+                               const SketchDst &ex);
 // distance.cu
 int launch_similarity_pairs(const uint32_t *d_sk, const uint64_t *d_off, uint64_t n_sk,
                             const uint32_t *d_a, const uint32_t *d_b, uint64_t n_pairs,

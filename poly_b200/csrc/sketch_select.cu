@@ -34,7 +34,7 @@ namespace {
 
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_CHUNK = 2048;     // k-mer positions per chunk
-constexpr int SEL_MAX_S = 16384;    // largest sketch size in the select regime
+constexpr int SEL_MAX_S = 16384;    // largest sketch size of the shared-memory kernels (beyond: sketch_select_large.cu)
 constexpr int SEL_LOOKAHEAD = 1024; // max k supported by the staged path (bytes beyond chunk)
 constexpr int SEL_NBK = 2048;       // value buckets of the final sort-select (v >> 21)
 constexpr int SEL_BSHIFT = 21;
@@ -1373,21 +1373,16 @@ int launch_sketch_select(const uint8_t *d_bases, const uint64_t *d_offsets, uint
     SketchDst ex;
     ex.n = 0;
     if (extra) ex = *extra;
-    if (s > SEL_MAX_S) {
-        set_error("sketch size %d > %d is not supported when L-k >= s (select regime)", s, SEL_MAX_S);
-        return PG_ERR_UNSUPPORTED;
-    }
-    if (k > SEL_LOOKAHEAD) {
-        set_error("k = %d > %d is not supported when L-k >= s (select regime)", k, SEL_LOOKAHEAD);
-        return PG_ERR_UNSUPPORTED;
-    }
-    uint32_t P = 1;
-    while (P < (uint32_t)std::max(s, 1)) P <<= 1;
-    if (P < 2) P = 2;
     // rows wider than s: the header promises zeros in [count, row_stride) -- the select kernels write
     // exactly s words, so clear the tail columns first (fill-regime rows of a ragged batch zero their own)
     if (row_stride > (uint64_t)s)
         PG_CUDA(cudaMemset2DAsync(d_out + s, row_stride * 4, 0, (row_stride - (uint64_t)s) * 4, n_reads, st));
+    // beyond the shared-memory kernels (sketch or k-mer too large for them): the global-memory path, no limit on either
+    if (s > SEL_MAX_S || k > SEL_LOOKAHEAD)
+        return launch_sketch_select_large(d_bases, d_offsets, read_len, n_reads, k, s, d_out, row_stride, d_count, d_status, st, ex);
+    uint32_t P = 1;
+    while (P < (uint32_t)std::max(s, 1)) P <<= 1;
+    if (P < 2) P = 2;
     // K2w (register-ring walk) for the instantiated k; PG_K2_GENERIC=1 forces the generic kernel (A/B knob)
     static const bool force_generic = [] { const char *e = getenv("PG_K2_GENERIC"); return e && atoi(e) != 0; }();
     if (!force_generic && (size_t)s * 8 + 56 * 1024 <= 227 * 1024) {  // shared memory of the walk kernel

@@ -465,6 +465,46 @@ def test_select_threshold_path(gpu, oracle, monkeypatch):
     assert rc == 0 and not status.any() and np.array_equal(out, want)
 
 
+def test_select_beyond_shared_memory_limits(gpu, oracle):
+    """Sketch sizes above 16384 and k above 1024 in the select regime (sketch_select_large.cu: hashes through
+    global memory, radix select, bitonic sort in tiles and across tiles): the reference has no limit there
+    (mash.go:68-104).  Uniform and ragged batches, ties, fill-regime rows in between, the s = 1 panic rule."""
+    rng = np.random.default_rng(2026)
+    for k, s, L, n in [(21, 20_000, 50_000, 5), (31, 16_385, 16_385 + 31 + 7, 3), (1500, 64, 6_000, 4), (17, 70_000, 300_000, 2),
+                       (1025, 3, 4_000, 3), (24, 16_385, 16_385 + 24, 2)]:
+        reads = rng.choice(list(b"ACGT"), size=n * L).astype(np.uint8).reshape(n, L)
+        reads[1] = rng.choice(list(b"AC"), size=L).astype(np.uint8)            # low complexity: many tied hashes
+        if n > 2:
+            reads[2, : L // 2] = reads[2, L // 2: 2 * (L // 2)]                 # every k-mer of one half twice
+        got = mash.sketch_uniform(reads.reshape(-1), n, L, k, s)
+        rc, want = oracle.sketch_batch(reads.reshape(-1), synth.uniform_offsets(n, L), k, s, variant=1)
+        assert rc == 0
+        cnt = min(L - k, s)
+        assert np.array_equal(got, want[:, :cnt]), (k, s, L, n, [i for i in range(n) if not np.array_equal(got[i], want[i, :cnt])])
+    # ragged: select-regime rows (n >= s) between fill-regime and empty rows, rows wider than s
+    s, k = 17_000, 21
+    lens = [40_000, 100, 17_021, 17_020, 0, 90_001, 17_022, 5]
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=l).astype(np.uint8)) for l in lens] + [b"G" * 30_000]
+    bases, offsets = mash.flatten(seqs)
+    out, count, status = mash.sketch_arrays(bases, offsets, k, s, pad_zero=True)
+    rc, want = oracle.sketch_batch(bases, offsets, k, s, variant=1)
+    assert rc == 0 and not status.any() and np.array_equal(out, want)
+    assert list(count) == [min(max(l - k, 0), s) for l in lens] + [s]
+    # s = 1 beyond k = 1024: Sketches[0] is the minimum; the reference panics iff a later hash is below the first
+    L, k = 3_000, 1100
+    reads = rng.choice(list(b"ACGT"), size=6 * L).astype(np.uint8)
+    out, count, status = mash.sketch_arrays(reads, synth.uniform_offsets(6, L), k, 1, pad_zero=True)
+    saw = set()
+    for i in range(6):
+        o = oracle.OracleMash(k, 1)
+        rc = o.Sketch(bytes(reads[i * L:(i + 1) * L]))
+        saw.add(rc != 0)
+        assert (status[i] != 0) == (rc != 0)
+        if rc == 0:
+            assert out[i, 0] == o.Sketches[0]
+    assert saw  # the six reads ran
+
+
 def test_select_rows_wider_than_s_are_zero_filled(gpu, oracle):
     """include/poly_b200.h: words [count, row_stride) of every row are zeros -- also in the select regime
     and for device-pointer callers that hand in a dirty buffer."""

@@ -63,7 +63,15 @@ print(json.dumps({"kernel": "K2 sketch_select (256 x 4 Mbp genomes)", "k": gk, "
 ms_1 = timed(lambda: _lib.check(L.pg_mash_sketch_uniform_dev(d_gen.data_ptr(), 1, gL, gk, gs, 0, d_gsk.data_ptr(), gs, None, st)))
 print(json.dumps({"kernel": "K2 sketch_select (ONE 4 Mbp sequence = mash.Sketch(genome))", "ms": ms_1, "gbases_per_s": gL / ms_1 / 1e6,
                   "same_as_batch_row0": bool((d_gsk[0].cpu().numpy().view(np.uint32) == g[0]).all()), "kernel_name": L.pg_last_kernel().decode()}))
-del d_gen
+# beyond the shared-memory kernels (sketch_select_large.cu): 64 of the genomes at s = 100000
+xs, xn = 100_000, 64
+d_xsk = torch.empty((xn, xs), dtype=torch.int32, device=dev)
+ms_x = timed(lambda: _lib.check(L.pg_mash_sketch_uniform_dev(d_gen.data_ptr(), xn, gL, gk, xs, 0, d_xsk.data_ptr(), xs, None, st)), iters=2)
+gx = d_xsk.cpu().numpy().view(np.uint32)
+print(json.dumps({"kernel": "K2x large sketch (64 x 4 Mbp genomes, s = 100000)", "k": gk, "s": xs, "ms": ms_x, "gbases_per_s": xn * gL / ms_x / 1e6,
+                  "ascending": bool((np.diff(gx.astype(np.int64), axis=1) >= 0).all()),
+                  "head_equals_s1000_sketch": bool((gx[:, :gs] == g[:xn]).all()), "kernel_name": L.pg_last_kernel().decode()}))
+del d_gen, d_xsk
 if args.only_k2:
     sys.exit(0)
 rows = min(args.rows, n)
