@@ -99,6 +99,35 @@ func SketchBatchMulti(bases []byte, offsets []uint64, k, s int, rowStride int, d
 	return out, count, status, err
 }
 
+// SketchInto wraps pg_mash_sketch_batch_multi with PG_SKETCH_TAIL_KEEP: sketches is the caller's n x s slab (the
+// Sketches arrays of n Mash values back to back); row i receives its min(len_i-k, s) words and nothing else is
+// written -- a fresh make([]uint32, n*s) therefore ends up as n full, zero-tailed Sketches arrays without a
+// per-read allocation or copy on the Go side, and a reused slab keeps its tails as (*Mash).Sketch does.
+func SketchInto(bases []byte, offsets []uint64, k, s int, sketches []uint32, devices []int32) (count []uint32, status []int32, err error) {
+	n := len(offsets) - 1
+	if len(sketches) < n*s {
+		return nil, nil, fmt.Errorf("polyb200: sketches holds %d words, need %d", len(sketches), n*s)
+	}
+	count = make([]uint32, n+1)
+	status = make([]int32, n+1)
+	if n == 0 {
+		return count[:n], status[:n], nil
+	}
+	if len(bases) == 0 {
+		bases = make([]byte, 1)
+	}
+	if len(sketches) == 0 { // s == 0: the call still reports the reads on which the reference panics
+		sketches = make([]uint32, 1)
+	}
+	dp, dn := devicePtr(devices)
+	err = locked(func() C.int {
+		return C.pg_mash_sketch_batch_multi((*C.uint8_t)(unsafe.Pointer(&bases[0])), (*C.uint64_t)(unsafe.Pointer(&offsets[0])), C.uint64_t(n),
+			C.int32_t(k), C.int32_t(s), C.PG_SKETCH_TAIL_KEEP, (*C.uint32_t)(unsafe.Pointer(&sketches[0])), C.uint64_t(s),
+			(*C.uint32_t)(unsafe.Pointer(&count[0])), (*C.int32_t)(unsafe.Pointer(&status[0])), dp, dn)
+	})
+	return count[:n], status[:n], err
+}
+
 // SketchDistanceMulti wraps pg_mash_sketch_distance_multi for fixed-length reads stored back to back:
 // sketches (n x s full arrays), matching counts and distances (n x n), computed on all listed GPUs with
 // the all-gather of the sketches fused into the sketch kernels.

@@ -66,21 +66,14 @@ func (mash *Mash) Distance(other *Mash) float64 { _, d := mash.pair(other); retu
 // SketchBatch is New(kmerSize, sketchSize) + Sketch(seq) for every sequence: one call, sharded over every
 // GPU of the box (reads are independent, mash.go:68-104; no collective is involved).
 func SketchBatch(sequences []string, kmerSize, sketchSize int) []*Mash {
+	if sketchSize < 0 {
+		panic("runtime error: makeslice: len out of range") // mash.New would
+	}
 	bases, offsets := polyb200.Flatten(sequences)
-	maxn := 0
-	for _, s := range sequences {
-		if n := len(s) - kmerSize; n > maxn {
-			maxn = n
-		}
-	}
-	stride := maxn
-	if stride > sketchSize {
-		stride = sketchSize
-	}
-	if stride < 1 {
-		stride = 1
-	}
-	out, count, status, err := polyb200.SketchBatchMulti(bases, offsets, kmerSize, sketchSize, stride, nil)
+	// one zeroed slab for all Sketches arrays (the runtime hands out zeroed memory, as New's make does per read);
+	// the library writes the informative words of every row in place and leaves the zero tails alone
+	slab := make([]uint32, len(sequences)*sketchSize)
+	_, status, err := polyb200.SketchInto(bases, offsets, kmerSize, sketchSize, slab, nil)
 	if err != nil && !errors.Is(err, polyb200.ErrPanic) {
 		panic(err)
 	}
@@ -89,9 +82,8 @@ func SketchBatch(sequences []string, kmerSize, sketchSize int) []*Mash {
 		if status[i] != 0 {
 			panic("runtime error: index out of range [-1]")
 		}
-		m := New(kmerSize, sketchSize)
-		copy(m.Sketches, out[i*stride:i*stride+int(count[i])]) // the zero tail is materialised here, host side
-		res[i] = m
+		res[i] = &Mash{KmerSize: kmerSize, SketchSize: sketchSize,
+			Sketches: slab[i*sketchSize : (i+1)*sketchSize : (i+1)*sketchSize]}
 	}
 	return res
 }

@@ -129,6 +129,25 @@ inline std::vector<Mash> SketchBatch(const std::vector<std::string> &seqs, int k
     return res;
 }
 
+// In-place form: `slab` holds the Sketches arrays of seqs.size() Mash values back to back (n x s words).  Row i
+// receives its min(len_i - k, s) words, the rest of the row is left as it is -- what (*Mash).Sketch does to an
+// existing Mash (mash.go:73-80); a zeroed slab ends up as n fresh sketches.  Returns the per-read counts.
+inline std::vector<uint32_t> SketchInto(const std::vector<std::string> &seqs, int k, int s, std::vector<uint32_t> &slab,
+                                        const std::vector<int32_t> &devices = {}) {
+    Flat f(seqs);
+    if (slab.size() < seqs.size() * (size_t)std::max(s, 0)) throw std::invalid_argument("slab smaller than n x s");
+    std::vector<uint32_t> count(seqs.size());
+    std::vector<int32_t> status(seqs.size());
+    uint32_t dummy = 0;
+    int rc = pg_mash_sketch_batch_multi(f.bases.data(), f.offsets.data(), seqs.size(), k, s, PG_SKETCH_TAIL_KEEP,
+                                        slab.empty() ? &dummy : slab.data(), (uint64_t)std::max(s, 0), count.data(), status.data(),
+                                        devices.empty() ? nullptr : devices.data(), (int32_t)devices.size());
+    if (rc != PG_OK && rc != PG_ERR_PANIC) check(rc);
+    for (int32_t st : status)
+        if (st == PG_ITEM_PANIC) throw GoPanic("index out of range [-1]");
+    return count;
+}
+
 // batched addition: sketches of fixed-length reads + the all-pairs matrix on several GPUs of this process
 // (sketch kernels store into every device's gathered buffer: fused all-gather; device r computes row block r)
 struct SketchDistance {

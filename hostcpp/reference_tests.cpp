@@ -174,6 +174,17 @@ static void TestSketchPersistenceAndMulti(const char *out_path) {  // SURVEY.md 
     EXPECT(js.rfind("{\"KmerSize\":17,\"SketchSize\":10,\"Sketches\":[", 0) == 0 && js.back() == '}' && js.find(' ') == std::string::npos);
     auto back = mash::FromJSON(js);
     EXPECT(back.KmerSize == 17 && back.SketchSize == 10 && back.Sketches == m.Sketches);
+    {   // in-place batch form: informative words written, tails left alone (what Sketch does to an existing Mash)
+        const std::vector<std::string> seqs = {A, A.substr(0, 20), A.substr(3), std::string()};
+        std::vector<uint32_t> slab(seqs.size() * 50, 0xDEADBEEFu);
+        auto cnt = mash::SketchInto(seqs, 17, 50, slab);
+        for (size_t i = 0; i < seqs.size(); ++i) {
+            auto one = mash::New(17, 50); one.Sketch(seqs[i]);
+            const uint32_t c = (uint32_t)std::min<size_t>(seqs[i].size() > 17 ? seqs[i].size() - 17 : 0, 50);
+            EXPECT(cnt[i] == c);
+            for (uint32_t j = 0; j < 50; ++j) EXPECT(slab[i * 50 + j] == (j < c ? one.Sketches[j] : 0xDEADBEEFu));
+        }
+    }
     EXPECT(mash::FromJSON("{\"KmerSize\":3,\"SketchSize\":2,\"Sketches\":null}").Sketches.empty());
     // a set: fill-regime (compact) and select-regime rows together
     std::vector<std::string> reads;

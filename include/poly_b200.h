@@ -102,6 +102,11 @@ int pg_stream_sync(void *stream);
  * or k above 1024 take a slower global-memory path instead of the shared-memory kernels.
  */
 #define PG_SKETCH_PAD_ZERO 1u
+/* Host-buffer entry points only: write nothing but the count[i] informative words of a row -- the literal
+ * behaviour of (*Mash).Sketch, which never touches Sketches[n:s] in the n < s regime (mash.go:73-80).  A Go
+ * caller that hands in a fresh make([]uint32, n*s) slab (zeroed by the runtime) gets full Sketches arrays
+ * without the library writing 4*s bytes per read; a reused array keeps its old tail, as in the reference. */
+#define PG_SKETCH_TAIL_KEEP 2u
 
 int pg_mash_sketch_batch(const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads, int32_t k,
                          int32_t s, uint32_t flags, uint32_t *out, uint64_t row_stride,

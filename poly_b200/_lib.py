@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpolyb200.so")
 PG_OK, PG_ERR_CUDA, PG_ERR_ARG, PG_ERR_NO_DEVICE, PG_ERR_PANIC, PG_ERR_UNSUPPORTED, PG_ERR_NOMEM = range(7)
 PG_ITEM_OK, PG_ITEM_PANIC, PG_ITEM_UNSUPPORTED = 0, 1, 2
 PG_SKETCH_PAD_ZERO = 1
+PG_SKETCH_TAIL_KEEP = 2
 
 
 class PolyError(RuntimeError):

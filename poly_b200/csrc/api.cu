@@ -456,6 +456,10 @@ static int check_ks(int32_t k, int32_t s) {
     if (s < 0) { set_error("sketchSize %d < 0: the reference panics (makeslice)", s); return PG_ERR_ARG; }
     return PG_OK;
 }
+static int check_dev_flags(uint32_t flags) {
+    if (flags & PG_SKETCH_TAIL_KEEP) { set_error("PG_SKETCH_TAIL_KEEP applies to host buffers only"); return PG_ERR_ARG; }
+    return PG_OK;
+}
 
 int pg_mash_sketch_uniform_dev(const uint8_t *d_bases, uint64_t n_reads, uint32_t read_len,
                                int32_t k, int32_t s, uint32_t flags, uint32_t *d_out,
@@ -463,6 +467,7 @@ int pg_mash_sketch_uniform_dev(const uint8_t *d_bases, uint64_t n_reads, uint32_
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
     if ((rc = check_ks(k, s)) != PG_OK) return rc;
+    if ((rc = check_dev_flags(flags)) != PG_OK) return rc;
     if (n_reads && (!d_bases || !d_out)) { set_error("null buffer"); return PG_ERR_ARG; }
     const uint64_t cnt = std::min<uint64_t>(kmers_of(read_len, k), (uint64_t)s);
     const uint64_t need = (flags & PG_SKETCH_PAD_ZERO) ? (uint64_t)s : cnt;
@@ -478,6 +483,7 @@ int pg_mash_sketch_batch_dev(const uint8_t *d_bases, const uint64_t *d_offsets, 
     int rc = ensure_device();
     if (rc != PG_OK) return rc;
     if ((rc = check_ks(k, s)) != PG_OK) return rc;
+    if ((rc = check_dev_flags(flags)) != PG_OK) return rc;
     if (n_reads && (!d_offsets || !d_out)) { set_error("null buffer"); return PG_ERR_ARG; }
     const uint64_t cnt = std::min<uint64_t>(kmers_of(max_read_len, k), (uint64_t)s);
     const uint64_t need = (flags & PG_SKETCH_PAD_ZERO) ? (uint64_t)s : cnt;
@@ -574,7 +580,11 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
     // buffers instead, filled / emptied by a few host threads while the other slots' DMA runs; the
     // device then always produces compact rows and the zero tail of PG_SKETCH_PAD_ZERO rows is
     // written by the host threads, not shipped over PCIe.
-    const bool stage_in = is_pageable(bases), stage_out = is_pageable(out);
+    // PG_SKETCH_TAIL_KEEP: only the informative words of a row are written.  Ragged batches then always go through
+    // the staging buffers, whose rows are copied out count[i] words at a time.
+    const bool keep_tail = (flags & PG_SKETCH_TAIL_KEEP) != 0;
+    flags &= ~PG_SKETCH_TAIL_KEEP;
+    const bool stage_in = is_pageable(bases), stage_out = is_pageable(out) || (keep_tail && offsets != nullptr);
     if (stage_in || stage_out) cx->pool.start(host_copy_helpers(), cx->device);
     const int nthr = cx->pool.threads();
     const bool want_status = status != nullptr || s <= 1;
@@ -596,17 +606,23 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
         if (stage_out && pd.dstride) {  // staged rows -> caller rows (+ zero tail up to the caller's stride)
             const uint32_t *src = (const uint32_t *)cx->pin_out[sl].p;
             par_rows(pd.nr, [&](uint64_t a, uint64_t b) {
-                if (pd.dstride == row_stride) {
+                if (pd.dstride == row_stride && !(keep_tail && offsets)) {
                     memcpy(out + (pd.r0 + a) * row_stride, src + a * pd.dstride, (b - a) * pd.dstride * 4);
                     return;
                 }
                 for (uint64_t i = a; i < b; ++i) {
                     uint32_t *dst = out + (pd.r0 + i) * row_stride;
+                    if (keep_tail) {  // exactly the informative words of this row
+                        const uint64_t r = pd.r0 + i;
+                        const uint64_t ci = offsets ? std::min<uint64_t>(kmers_of(offsets[r + 1] - offsets[r], k), (uint64_t)s) : pd.dstride;
+                        memcpy(dst, src + i * pd.dstride, ci * 4);
+                        continue;
+                    }
                     memcpy(dst, src + i * pd.dstride, pd.dstride * 4);
                     memset(dst + pd.dstride, 0, (row_stride - pd.dstride) * 4);
                 }
             });
-        } else if (row_stride > pd.dstride) {  // direct DMA wrote dstride words per row: zero the rest of each row
+        } else if (row_stride > pd.dstride && !keep_tail) {  // direct DMA wrote dstride words per row: zero the rest of each row
             par_rows(pd.nr, [&](uint64_t a, uint64_t b) {
                 for (uint64_t i = a; i < b; ++i) memset(out + (pd.r0 + i) * row_stride + pd.dstride, 0, (row_stride - pd.dstride) * 4);
             });
@@ -654,8 +670,8 @@ static int sketch_host(const uint8_t *bases, const uint64_t *offsets, uint32_t u
             const uint64_t need_stride = (flags & PG_SKETCH_PAD_ZERO) ? (uint64_t)s : cnt_max;
             if (row_stride < need_stride) { set_error("row_stride %llu < %llu", (unsigned long long)row_stride, (unsigned long long)need_stride); return PG_ERR_ARG; }
             // staged output: compact device rows, the host threads pad; direct output: the device pads
-            const uint32_t dev_flags = stage_out ? (flags & ~PG_SKETCH_PAD_ZERO) : flags;
-            const uint64_t dev_stride = stage_out ? cnt_max : need_stride;
+            const uint32_t dev_flags = (stage_out || keep_tail) ? (flags & ~PG_SKETCH_PAD_ZERO) : flags;
+            const uint64_t dev_stride = (stage_out || keep_tail) ? cnt_max : need_stride;
 
             int rc2;
             if ((rc2 = drain(slot)) != PG_OK) return rc2;

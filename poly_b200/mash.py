@@ -123,6 +123,29 @@ def sketch_arrays(bases: np.ndarray, offsets: np.ndarray, k: int, s: int, pad_ze
     return out, count, status
 
 
+def sketch_into(bases: np.ndarray, offsets: np.ndarray, k: int, s: int, sketches: np.ndarray, devices=None):
+    """The literal in-place form of (*Mash).Sketch for a batch: `sketches` is the caller's [n, s] uint32 array
+    (the Sketches of n Mash values, e.g. one zeroed slab as Go's make gives); row i receives its min(L_i - k, s)
+    words and the rest of the row is left as it was (mash.go:73-80 never writes Sketches[n:s]) --
+    PG_SKETCH_TAIL_KEEP.  Returns (count, status)."""
+    bases = np.ascontiguousarray(bases, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    if sketches.dtype != np.uint32 or not sketches.flags.c_contiguous or sketches.shape != (n, s):
+        raise ValueError("sketches must be a C-contiguous uint32 array of shape (n, s)")
+    count = np.zeros(n, dtype=np.uint32)
+    status = np.zeros(n, dtype=np.int32)
+    dev, nd = _device_list(devices) if devices is not None else (None, 0)
+    if devices is not None:
+        rc = _lib.lib().pg_mash_sketch_batch_multi(bases.ctypes.data, offsets.ctypes.data, n, k, s, _lib.PG_SKETCH_TAIL_KEEP,
+                                                   sketches.ctypes.data, max(s, 1), count.ctypes.data, status.ctypes.data, _lib.ptr(dev), nd)
+    else:
+        rc = _lib.lib().pg_mash_sketch_batch(bases.ctypes.data, offsets.ctypes.data, n, k, s, _lib.PG_SKETCH_TAIL_KEEP,
+                                             sketches.ctypes.data, max(s, 1), count.ctypes.data, status.ctypes.data)
+    _lib.check(rc, allow=(_lib.PG_ERR_PANIC,))
+    return count, status
+
+
 def sketch_uniform(bases: np.ndarray, n_reads: int, read_len: int, k: int, s: int) -> np.ndarray:
     """Fixed-length reads stored back to back -> compact sketches [n, min(max(L-k,0), s)]."""
     bases = np.ascontiguousarray(bases, dtype=np.uint8)

@@ -505,6 +505,37 @@ def test_select_beyond_shared_memory_limits(gpu, oracle):
     assert saw  # the six reads ran
 
 
+def test_sketch_into_leaves_the_tail_alone(gpu, oracle):
+    """PG_SKETCH_TAIL_KEEP: only count[i] words of a row are written, like (*Mash).Sketch on an existing Mash
+    (mash.go:73-80 never touches Sketches[n:s]).  Pageable and pinned output, ragged and fixed-length reads."""
+    import torch
+    from poly_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    k, s = 21, 200
+    lens = [150, 21, 0, 400, 22, 150, 221, 220, 5000, 90]
+    seqs = [bytes(rng.choice(list(b"ACGT"), size=l).astype(np.uint8)) for l in lens]
+    uniform = [bytes(rng.choice(list(b"ACGT"), size=150).astype(np.uint8)) for _ in range(70)]
+    for batch in (seqs, uniform):
+        bases, offsets = mash.flatten(batch)
+        rc, want = oracle.sketch_batch(bases, offsets, k, s, variant=1)
+        assert rc == 0
+        n = len(batch)
+        pinned = torch.empty((n, s), dtype=torch.int32, pin_memory=True).numpy().view(np.uint32)
+        for out in (np.empty((n, s), dtype=np.uint32), pinned):
+            out[:] = 0xDEADBEEF
+            count, status = mash.sketch_into(bases, offsets, k, s, out)
+            assert not status.any()
+            for i, seq in enumerate(batch):
+                c = min(max(len(seq) - k, 0), s)
+                assert count[i] == c
+                assert np.array_equal(out[i, :c], want[i, :c]) and (out[i, c:] == 0xDEADBEEF).all(), i
+    # the device-pointer entry points refuse the flag (their kernels define the whole row)
+    d = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    o = torch.zeros(64, dtype=torch.int32, device="cuda")
+    assert gpu.lib().pg_mash_sketch_uniform_dev(d.data_ptr(), 1, 64, 21, 10, 2, o.data_ptr(), 10, None, 0) == _lib.PG_ERR_ARG
+
+
 def test_select_rows_wider_than_s_are_zero_filled(gpu, oracle):
     """include/poly_b200.h: words [count, row_stride) of every row are zeros -- also in the select regime
     and for device-pointer callers that hand in a dirty buffer."""
