@@ -695,4 +695,73 @@ inline ParseResult ParseAll(const std::string &text, uint32_t maxLineSize, bool 
 inline ParseResult Parse(const std::string &text, bool bufioAlias = true) { return ParseAll(text, 2 * 32 * 1024, bufioAlias); }
 
 }  // namespace fasta
+
+namespace fastq {
+
+// fastq.Fastq, io/fastq/fastq.go:46-51
+struct Fastq {
+    std::string Identifier;
+    std::map<std::string, std::string> Optionals;
+    std::string Sequence, Quality;
+};
+// ([]Fastq, error) of fastq.Parse: the records before the first one the reference rejects, and that error
+// (code as pg_fastq_ingest reports it, 0 = nil; err_line = the 1-based line the parser stopped at)
+struct ParseResult {
+    std::vector<Fastq> fastqs;
+    int32_t err_code = 0;
+    uint64_t err_line = 0;
+    std::string error() const {
+        const std::string l = std::to_string(err_line);
+        switch (err_code) {
+            case 1: return "line " + l + " failed: unexepcted EOF encountered";  // sic, fastq.go:150
+            case 2: return "empty fastq sequence, got to line " + l;
+            case 3: return "empty quality sequence, got to line " + l;
+            case 4: return "did not find fastq start '@', got to line " + l;
+            case 5: return "reference panics (index out of range) while parsing the identifier at line " + l;
+            case 6: return "line " + l + " too large for buffer, use larger maxLineSize";
+            default: return "";
+        }
+    }
+};
+
+// fastq.Parse, io/fastq/fastq.go:54-59 (ParseNext :117-214): records on the GPU (line index, per-record checks in the
+// reference's order, dense sequences); Identifier / Optionals / Quality are cut out of `text` with the line spans.
+inline ParseResult Parse(const std::string &text) {
+    uint64_t cap = 1;
+    for (char c : text) cap += c == '\n';
+    cap = cap / 4 + 1;
+    std::vector<uint8_t> bases(text.size() + 1);
+    std::vector<uint64_t> off(cap + 1), spans(4 * (cap + 1));
+    uint64_t n = 0, tot = 0;
+    ParseResult r;
+    check(pg_fastq_ingest_records(reinterpret_cast<const uint8_t *>(text.data()), text.size(), bases.data(), bases.size(), off.data(),
+                                  spans.data(), cap, &n, &tot, &r.err_code, &r.err_line));
+    r.fastqs.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        Fastq f;
+        const std::string line = text.substr(spans[4 * i], spans[4 * i + 1]);
+        size_t pos = 0;
+        bool first = true;
+        while (pos <= line.size()) {  // strings.Split(line, " "), fastq.go:157
+            size_t sp = line.find(' ', pos);
+            if (sp == std::string::npos) sp = line.size();
+            const std::string tok = line.substr(pos, sp - pos);
+            if (first) {
+                f.Identifier = tok.substr(1);  // without the '@', fastq.go:158
+                first = false;
+            } else {  // "key=value": strings.Split(datum, "=")[0], [1] (every datum holds '=': checked on the GPU)
+                const size_t eq = tok.find('=');
+                const size_t eq2 = tok.find('=', eq + 1);
+                f.Optionals[tok.substr(0, eq)] = tok.substr(eq + 1, eq2 == std::string::npos ? std::string::npos : eq2 - eq - 1);
+            }
+            pos = sp + 1;
+        }
+        f.Sequence.assign(bases.begin() + off[i], bases.begin() + off[i + 1]);
+        f.Quality = text.substr(spans[4 * i + 2], spans[4 * i + 3]);
+        r.fastqs.push_back(std::move(f));
+    }
+    return r;
+}
+
+}  // namespace fastq
 }  // namespace poly

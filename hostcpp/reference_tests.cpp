@@ -167,6 +167,25 @@ static void TestPcr() {  // primers/pcr/pcr_test.go:12-101, example_test.go:10-6
     EXPECT(panicked);
 }
 
+static void TestFastqParser() {  // io/fastq/fastq_test.go:8-66 restated on in-line records (the fixtures are not in this repo)
+    const std::string two = "@r1 runid=abc ch=7\nACGTTGCA\n+\nIIIIHHHH\n@r2\nGG\n+\n#!\n";
+    auto r = fastq::Parse(two);
+    EXPECT(r.err_code == 0 && r.fastqs.size() == 2);
+    EXPECT(r.fastqs[0].Identifier == "r1" && r.fastqs[0].Optionals.size() == 2 && r.fastqs[0].Optionals["runid"] == "abc" &&
+           r.fastqs[0].Optionals["ch"] == "7" && r.fastqs[0].Sequence == "ACGTTGCA" && r.fastqs[0].Quality == "IIIIHHHH");
+    EXPECT(r.fastqs[1].Identifier == "r2" && r.fastqs[1].Optionals.empty() && r.fastqs[1].Sequence == "GG" && r.fastqs[1].Quality == "#!");
+    r = fastq::Parse("@r1\nACGT\n+\nIIII\n@r2\n\n+\nII\n");  // "empty seq"
+    EXPECT(r.fastqs.size() == 1 && r.err_code == 2 && r.err_line == 6 && r.error() == "empty fastq sequence, got to line 6");
+    r = fastq::Parse("@r1\nACGT\n+\nIIII\nr2\nAC\n+\nII\n");  // "no identifier": reported after the 4th line of the record
+    EXPECT(r.fastqs.size() == 1 && r.err_code == 4 && r.err_line == 8);
+    r = fastq::Parse("@r1\nACGT\n+\nIIII\n@r2\nAC\n+\n\n");  // "no quality"
+    EXPECT(r.fastqs.size() == 1 && r.err_code == 3 && r.err_line == 8);
+    r = fastq::Parse("@r1\nACGT\n+\nIIII\n@r2\nAC\n");  // "no plus EOF"
+    EXPECT(r.fastqs.size() == 1 && r.err_code == 1 && r.err_line == 7);
+    r = fastq::Parse("");
+    EXPECT(r.fastqs.empty() && r.err_code == 0);
+}
+
 static void TestSketchPersistenceAndMulti(const char *out_path) {  // SURVEY.md 8f.4 + the *_multi entry points
     const std::string A = "ATGCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGATCGA";
     auto m = mash::New(17, 10); m.Sketch(A);
@@ -236,6 +255,7 @@ static void TestSketchPersistenceAndMulti(const char *out_path) {  // SURVEY.md 
 int main(int argc, char **argv) {
     check(pg_init(0));
     TestFastaParser();
+    TestFastqParser();
     TestMash();
     TestSmithWaterman();
     TestSantaLucia();
