@@ -1,3 +1,4 @@
+# K2 check: the parity tests of the sketch path, timings of cfg3 / genomes / one genome / the large-sketch path, ncu launch list.
 set -x
 timeout 600 python -m pytest tests/test_gpu_mash.py -x -q --timeout 200 --timeout-method thread 2>&1 | tail -3
 timeout 300 python tools/bench_secondary.py --only-k2 2>&1 | cut -c1-200
