@@ -171,6 +171,37 @@ func DistanceBlock(sketches []uint32, n, s int, rowBegin, rowEnd int) (same []ui
 	return same[:rows*n], dist[:rows*n], check(rc)
 }
 
+// DistanceSparse wraps pg_mash_distance_sparse: the pairs (i, j) of rows [rowBegin,rowEnd) x all n columns that share
+// at least one hash, with their matching counts; every pair not listed has Similarity 0 / Distance 1
+// (mash.go:134,139).  upper: only j > i.  The order of the triples is unspecified.
+func DistanceSparse(sketches []uint32, n, s int, rowBegin, rowEnd int, upper bool) (pi, pj, same []uint32, err error) {
+	capPairs := 4*(rowEnd-rowBegin) + 1024
+	flags := C.uint32_t(0)
+	if upper {
+		flags = C.PG_PAIRS_UPPER
+	}
+	for {
+		pi, pj, same = make([]uint32, capPairs), make([]uint32, capPairs), make([]uint32, capPairs)
+		var cnt C.uint64_t
+		var rc C.int
+		err = locked(func() C.int {
+			rc = C.pg_mash_distance_sparse((*C.uint32_t)(unsafe.Pointer(&sketches[0])), C.uint64_t(n), C.int32_t(s), C.uint64_t(rowBegin),
+				C.uint64_t(rowEnd), flags, (*C.uint32_t)(unsafe.Pointer(&pi[0])), (*C.uint32_t)(unsafe.Pointer(&pj[0])),
+				(*C.uint32_t)(unsafe.Pointer(&same[0])), C.uint64_t(capPairs), &cnt)
+			return rc
+		})
+		if rc == C.PG_ERR_ARG && int(cnt) > capPairs { // the buffers were too small: the call reports the size it needs
+			capPairs = int(cnt)
+			continue
+		}
+		if err != nil {
+			return nil, nil, nil, err
+		}
+		k := int(cnt)
+		return pi[:k], pj[:k], same[:k], nil
+	}
+}
+
 // SWScoreBatch wraps pg_sw_score_batch.
 func SWScoreBatch(queries []byte, qOffsets []uint64, template string, queryIsA bool, lutA, lutB *[256]int16, table []int64,
 	nA, nB int, gap int64) (score []int64, errCode []int32, errPos []int64, err error) {

@@ -109,3 +109,34 @@ func DistanceMatrix(sketches []*Mash) [][]float64 {
 	}
 	return res
 }
+
+// RelatedPair is one pair of sketches that share at least one hash.
+type RelatedPair struct {
+	I, J     int     // indices into the sketch list, I < J
+	Same     int     // matching hashes as the walk of Similarity counts them (mash.go:121-132)
+	Distance float64 // sketches[I].Distance(sketches[J]) == 1 - Same/SketchSize (mash.go:134,139)
+}
+
+// RelatedPairs returns every pair i < j of ascending (select-regime) or zero-padded sketches of one common SketchSize
+// whose Distance is below 1, i.e. the non-trivial entries of DistanceMatrix, without materialising the n x n matrix
+// (for n = 100k sketches: 334 MB instead of 40 GB).  Pairs that are not returned have Distance 1.
+func RelatedPairs(sketches []*Mash) []RelatedPair {
+	n := len(sketches)
+	if n == 0 {
+		return nil
+	}
+	s := sketches[0].SketchSize
+	flat := make([]uint32, 0, n*s)
+	for _, m := range sketches {
+		flat = append(flat, m.Sketches[:s]...)
+	}
+	pi, pj, same, err := polyb200.DistanceSparse(flat, n, s, 0, n, true)
+	if err != nil {
+		panic(err)
+	}
+	out := make([]RelatedPair, len(pi))
+	for t := range pi {
+		out[t] = RelatedPair{I: int(pi[t]), J: int(pj[t]), Same: int(same[t]), Distance: 1 - float64(same[t])/float64(s)}
+	}
+	return out
+}

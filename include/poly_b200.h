@@ -210,7 +210,7 @@ int pg_mash_distance_block_dev(const uint32_t *d_sketches, uint64_t n, int32_t s
  * pair (i, j), row_begin <= i < row_end, j != i (with PG_PAIRS_UPPER: j > i only), whose matching count is
  * non-zero, in no particular order.  Pairs that are not listed have same == 0 (Similarity 0, Distance 1,
  * mash.go:134,139); the diagonal is never listed.  For n sketches this returns O(related pairs) instead of
- * the n x rows matrix (cfg3: ~5e6 triples = 60 MB instead of 40 GB).  *n_pairs receives the number of
+ * the n x rows matrix (cfg3, j > i: 2.8e7 triples = 334 MB instead of 40 GB).  *n_pairs receives the number of
  * qualifying pairs; PG_ERR_ARG (with the first pairs_cap stored) if it exceeds pairs_cap.  The _dev variant
  * takes a DEVICE counter d_n_pairs (which may exceed pairs_cap) and never blocks on the result. */
 #define PG_PAIRS_UPPER 1u
