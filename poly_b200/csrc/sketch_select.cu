@@ -3,7 +3,15 @@
 // /root/reference/search/mash/mash.go:87-102: fill, sort once at i == s-1, then
 // replace-max + re-sort; duplicates are kept).
 //
-// One CTA per read.  The read is streamed through shared memory in chunks:
+// Three kernels share this file (dispatch at the bottom, launch_sketch_select):
+//   K2t  sketch_thresh_walk_kernel + sketch_thresh_select_kernel -- the default for the instantiated k: a value
+//        threshold admits ~s hashes per row into global candidate lists, a counting sort picks the bottom-s
+//        (section "K2t" below); rows on which the estimate fails go to
+//   K2w  sketch_select_walk_kernel -- exact streaming kernel with the register-ring walk, one CTA per row;
+//   generic sketch_select_kernel -- any k <= 1024, described next.
+// Sketches above 16384 words or k above 1024 leave this file for sketch_select_large.cu.
+//
+// The generic kernel: one CTA per read.  The read is streamed through shared memory in chunks:
 //   stage    the chunk's bytes arrive by a 1-D TMA bulk copy (16-byte aligned body; the few
 //            unaligned tail bytes by plain loads), double-buffered one chunk ahead
 //   phase 1  pre-mix K(p) of every position of the chunk, once       (shared via smem)
