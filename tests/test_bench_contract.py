@@ -57,3 +57,26 @@ def test_bench_cli_parses_without_a_gpu():
     assert out.returncode == 0
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in out.stdout
+
+
+def test_documented_numbers_trace_to_the_record_lines():
+    """The round-2 tables of README.md / DESIGN.md quote the committed bench lines (within rounding)."""
+    import re
+
+    d1, d8 = _line("r02_bench_n1.json"), _line("r02_bench_n8.json")
+    sec = {s["name"]: s for s in d1["secondary"]}
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+
+    def quoted(text, pattern):
+        m = re.search(pattern, text)
+        assert m, pattern
+        return float(m.group(1))
+
+    assert abs(quoted(readme, r"\*\*1\.56 ms / pass = (\d+) Gbases/s\*\*") - d1["value"]) / d1["value"] < 0.01
+    assert abs(quoted(readme, r"\*\*(\d+) Gbases/s \(7\.99×\)\*\*") - d8["value"]) / d8["value"] < 0.005
+    assert abs(quoted(readme, r"cfg3 \(100 k × 10 kbp, k=31, s=2000\) \| \*\*([\d.]+) ms") - sec["cfg3 sketch (K2)"]["ms"]) < 0.03
+    assert abs(quoted(readme, r"\*\*([\d.]+) ms = 6\.45 TCUPS\*\*") - sec["cfg5 Smith-Waterman score (K4)"]["ms"]) < 0.2
+    assert abs(quoted(design, r"\| 15\.5 / 30\.1 / 49\.2 / \*\*([\d.]+) Gbases/s\*\*") - d8["e2e"]["value"]) < 0.3
+    assert abs(quoted(design, r"0\.656 of HBM peak \| unchanged \(1\.56 ms, (\d+) Gbases/s") - d1["value"]) / d1["value"] < 0.01
+    assert abs(d1["roofline"]["frac"] - 0.656) < 0.01
